@@ -1,0 +1,111 @@
+/*
+ * nbdt_b200.h -- C ABI of libnbdt_b200.so: the B200 (sm_100a) implementation of the NBDT hot path.
+ *
+ * The reference (alvinwan/neural-backed-decision-trees) is pure Python; it has no FFI.  The entry
+ * points below are what a binding for the hot path replaces, one per reference call site
+ * (file:line into the reference tree):
+ *
+ *   nbdt_tree_create        nbdt/tree.py:146-174 (Tree.__init__/load_hierarchy) + tree.py:105-125
+ *                           (Node.build_class_mappings): the per-node class<->child tables,
+ *                           flattened once and copied to the device.
+ *   nbdt_soft_forward       nbdt/model.py:268-273 SoftEmbeddedDecisionRules.forward
+ *                           (= forward_nodes model.py:101-123 + traverse_tree model.py:207-242)
+ *   nbdt_soft_backward      the autograd backward of the above (the reference relies on torch autograd
+ *                           through model.py:94-117,241)
+ *   nbdt_hard_forward       nbdt/model.py:194-203 HardEmbeddedDecisionRules.forward_with_decisions
+ *                           (= forward_nodes + traverse_tree model.py:145-186)
+ *   nbdt_node_outputs       nbdt/model.py:101-120 EmbeddedDecisionRules.get_all_node_outputs
+ *   nbdt_soft_loss          nbdt/loss.py:191-203 TreeSupLoss.forward with
+ *                           nbdt/loss.py:260-266 SoftTreeSupLoss.forward_tree, and its autograd backward
+ *   nbdt_hard_loss          nbdt/loss.py:191-203 with nbdt/loss.py:212-257 HardTreeSupLoss.forward_tree
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer owned by the caller.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no host sync.
+ *   - return value 0 = ok, otherwise an NBDT_E* code; nbdt_last_error() gives a thread-local message.
+ *   - dtype of logits / grad_logits: NBDT_F32, NBDT_BF16 or NBDT_F16.  All arithmetic is fp32.
+ *   - node ids: leaf with class index c -> c ; inner node i (index into Tree.inodes, i.e. sorted by
+ *     wnid, reference nbdt/tree.py:172-173) -> num_classes + i.
+ *   - There is no CPU implementation behind this ABI: without a CUDA device every compute entry
+ *     point fails with NBDT_ECUDA.
+ */
+#ifndef NBDT_B200_H
+#define NBDT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBDT_B200_VERSION 100
+
+enum { NBDT_OK = 0, NBDT_EINVAL = 1, NBDT_ECUDA = 2, NBDT_ETREE = 3, NBDT_ETOOLARGE = 4 };
+enum { NBDT_F32 = 0, NBDT_BF16 = 1, NBDT_F16 = 2 };
+
+typedef struct nbdt_tree nbdt_tree; /* opaque; owns the device copies of the tree tables */
+
+typedef struct {
+  int32_t num_classes;       /* C: leaves, in wnids-file order (class index)                  */
+  int32_t num_inodes;        /* N: inner nodes, in Tree.inodes order                           */
+  int32_t root;              /* index into inodes of the root                                  */
+  const int32_t* child_ptr;  /* [N+1] CSR offsets into child_node (HOST pointer)               */
+  const int32_t* child_node; /* [S] node ids of the children, in Node.children order (HOST)    */
+} nbdt_tree_desc;
+
+int nbdt_version(void);
+const char* nbdt_last_error(void);
+int nbdt_device_count(void);
+
+/* Validates that desc is a rooted tree covering all leaves; derives leaf counts, depths and the
+ * level schedules; copies everything to `device`.  */
+int nbdt_tree_create(const nbdt_tree_desc* desc, int device, nbdt_tree** out);
+void nbdt_tree_destroy(nbdt_tree* tree);
+int nbdt_tree_max_depth(const nbdt_tree* tree);    /* max #decisions root->leaf                 */
+int nbdt_tree_num_slots(const nbdt_tree* tree);    /* S = sum of children over inner nodes      */
+
+/* class_probs[b,c] = prod over inner nodes n on the path to c of softmax_k(node_logits_n[b,:])[k(n,c)],
+ * node_logits_n[b,k] = mean of logits[b, leaves under child k].  class_probs: fp32 [B, C] contiguous. */
+int nbdt_soft_forward(const nbdt_tree* tree, const void* logits, int dtype, int64_t B, int64_t ld,
+                      float* class_probs, void* stream);
+
+/* Backward of nbdt_soft_forward for an arbitrary criterion on the probabilities:
+ * grad_logits = grad_scale * (d class_probs / d logits)^T grad_probs, recomputing the forward from
+ * `logits`.  grad_probs: fp32 [B, C] contiguous; grad_logits: dtype/ld of logits. */
+int nbdt_soft_backward(const nbdt_tree* tree, const void* logits, int dtype, int64_t B, int64_t ld,
+                       const float* grad_probs, float grad_scale, void* grad_logits, void* stream);
+
+/* Greedy root->leaf walk by per-node argmax (first maximum).  pred: int64 [B] class index.
+ * The path_* outputs may each be NULL; otherwise [B, max_depth]: child index taken (-1 past the
+ * leaf), inode index the decision was taken at (-1 pad), probability of the taken child and
+ * entropy of that node's child distribution.  */
+int nbdt_hard_forward(const nbdt_tree* tree, const void* logits, int dtype, int64_t B, int64_t ld,
+                      int64_t* pred, int32_t* path_child, int32_t* path_inode, float* path_prob,
+                      float* path_entropy, void* stream);
+
+/* Per-node outputs, packed in child-slot order (slot s of inode i is child_ptr[i] + k):
+ * node_logits, node_probs: fp32 [B, S]; preds: int64 [B, N]; entropy: fp32 [B, N]. Any may be NULL. */
+int nbdt_node_outputs(const nbdt_tree* tree, const void* logits, int dtype, int64_t B, int64_t ld,
+                      float* node_logits, float* node_probs, int64_t* preds, float* entropy,
+                      void* stream);
+
+/* loss = (1/batch_rows) * sum_b [ w_xent * CE(logits_b, y_b) + w_tree * CE(class_probs_b, y_b) ]
+ * (the second CE takes the probabilities as logits -- reference loss.py:264-266).
+ * loss: device fp32 scalar (overwritten).  grad_logits: same dtype/shape/ld as logits, receives
+ * grad_scale * dloss/dlogits; may be NULL (forward only).  batch_rows: the batch size the mean is
+ * taken over (pass B on one GPU, the global batch when rows are sharded); <=0 means B. */
+int nbdt_soft_loss(const nbdt_tree* tree, const void* logits, int dtype, const int64_t* targets,
+                   int64_t B, int64_t ld, int64_t batch_rows, float w_xent, float w_tree,
+                   float grad_scale, float* loss, void* grad_logits, void* stream);
+
+/* loss = (1/batch_rows) * sum_b [ w_xent * CE(logits_b, y_b)
+ *          + w_tree * tsw * (2/N) * sum_{n on path(y_b)} -log softmax(node_logits_n[b,:])[child toward y_b] ]
+ * (reference loss.py:212-257: the group-wise CE means weighted by rows/(B*N/2)*tsw collapse to this). */
+int nbdt_hard_loss(const nbdt_tree* tree, const void* logits, int dtype, const int64_t* targets,
+                   int64_t B, int64_t ld, int64_t batch_rows, float w_xent, float w_tree, float tsw,
+                   float grad_scale, float* loss, void* grad_logits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBDT_B200_H */
