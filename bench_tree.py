@@ -1,0 +1,80 @@
+"""Saturating row sweep of the fused tree-loss kernel: achieved HBM GB/s per (rows, classes, dtype).
+
+Algorithmic bytes per launch: 2*B*C*sizeof(logit) + 8*B + 4  (read logits + targets,
+write gradient + loss).  Buffers are larger than L2 (126 MB) where stated, otherwise L2 is flushed
+between iterations.  Prints one JSON line per point; used by bench.py for the tree_roofline block.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "neural-backed-decision-trees_b200"))
+
+import torch  # noqa: E402
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def time_point(tree, kind, rows, C, dtype, iters=10, warmup=3, group=None):
+    from nbdt._b200 import ops
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = (3 * torch.randn((rows, C), device=dev, generator=gen)).to(dtype)
+    y = torch.randint(C, (rows,), device=dev, generator=gen)
+    esz = x.element_size()
+    alg_bytes = 2 * rows * C * esz + 8 * rows + 4
+    flush = None
+    if alg_bytes < 300e6:  # working set not safely above L2: flush between iterations
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        ops.tree_loss(tree, x, y, kind, 1.0, 1.0)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.tree_loss(tree, x, y, kind, 1.0, 1.0)
+        e.record()
+        e.synchronize()
+        times.append(s.elapsed_time(e))
+    times.sort()
+    ms = times[len(times) // 2]
+    return {"rows": rows, "C": C, "dtype": str(dtype).replace("torch.", ""), "kind": kind, "ms": ms,
+            "alg_bytes": alg_bytes, "gbs": alg_bytes / ms / 1e6, "l2": "flush" if flush is not None else "inputs>L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--group", type=int, default=None)
+    args = ap.parse_args()
+    from nbdt.tree import Tree
+
+    pk, src = peaks()
+    if args.group:
+        os.environ["NBDT_B200_TREE_G"] = str(args.group)
+    cases = [("CIFAR10", "induced", 10), ("LookIntoPerson", "induced-HRNet-w48-cls20", 20), ("CIFAR100", "induced", 100),
+             ("ADE20K", "induced-HRNet-w48", 150), ("TinyImagenet200", "induced", 200), ("Imagenet1000", "induced", 1000)]
+    rows_for = {10: [1 << 18, 1 << 22], 20: [1 << 21], 100: [1 << 16, 1 << 20], 150: [1 << 19], 200: [1 << 19], 1000: [1 << 17]}
+    for dataset, hierarchy, C in cases:
+        tree = Tree(dataset, hierarchy=hierarchy)
+        for rows in rows_for[C][-1:] if args.quick else rows_for[C]:
+            for dtype in (torch.float32, torch.bfloat16):
+                for kind in ("soft",) if args.quick else ("soft", "hard"):
+                    r = time_point(tree, kind, rows, C, dtype)
+                    r.update(dataset=dataset, frac=r["gbs"] / pk["hbm_gbs"], peak=pk["hbm_gbs"], peak_source=src)
+                    print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,3 +105,51 @@ def test_oracle_weight_schedule(case, oracle_trees):
     loss, grad = O.soft_tree_sup_loss(t, g["logits"].astype(np.float64), g["targets"], xent_weight=wx, tree_weight=wt)
     np.testing.assert_allclose(loss, g["soft_loss_sched_f64"], rtol=1e-6)
     np.testing.assert_allclose(grad, g["soft_grad_sched_f64"], rtol=2e-5, atol=2e-8)
+
+
+# ---- oracle/torch_port.py (the CPU baseline bench.py times) pinned to the same golden vectors ----
+@pytest.mark.parametrize("case", ["cifar10_induced", "cifar100_wordnet", "tiny200_induced_resnet18"])
+def test_torch_port_tree_losses(case, oracle_trees):
+    import torch
+    import torch.nn as nn
+    from oracle import torch_port as P
+
+    g, t = load_golden(case), oracle_trees[case]
+    y = torch.as_tensor(g["targets"])
+    np.testing.assert_allclose(P.soft_rules(t, torch.as_tensor(g["logits"])).numpy(), g["soft_probs"], rtol=1e-6, atol=1e-9)
+    for name, fn, kw in (("soft", P.soft_tree_sup_loss, {}), ("hard", P.hard_tree_sup_loss, {"tsw": 10.0})):
+        x = torch.as_tensor(g["logits"]).double().requires_grad_(True)
+        loss = fn(t, nn.CrossEntropyLoss(), x, y, 1.0, 10.0, **kw)
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), g[f"{name}_loss_tsw10_f64"], rtol=1e-9)
+        np.testing.assert_allclose(x.grad.numpy(), g[f"{name}_grad_tsw10_f64"], rtol=1e-7, atol=1e-12)
+
+
+def test_torch_port_resnet18_train_step(oracle_trees):
+    """Seeded eager ResNet18 + SoftTreeSupLoss + SGD reproduces the executing reference's step."""
+    import os
+    import torch
+    import torch.nn as nn
+    from conftest import GOLDEN
+    from oracle import torch_port as P
+
+    g = np.load(os.path.join(GOLDEN, "backbone_resnet18.npz"))
+    torch.manual_seed(0)
+    net = P.EagerResNet(num_classes=10)
+    assert [k for k, _ in net.named_parameters()] == list(g["param_names"])
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    tree = oracle_trees["cifar10_induced_resnet18"]
+    x, y = torch.as_tensor(g["x"]), torch.as_tensor(g["y"])
+    net.train()
+    opt.zero_grad()
+    logits = net(x)
+    loss = P.soft_tree_sup_loss(tree, nn.CrossEntropyLoss(), logits, y)
+    loss.backward()
+    np.testing.assert_allclose(logits.detach().numpy(), g["train_logits"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(loss.item(), g["train_loss"], rtol=1e-5)
+    norms = np.array([float(p.grad.double().norm()) for p in net.parameters()])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=1e-3)
+    opt.step()
+    net.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(net(x).numpy(), g["eval_logits_after_step"], rtol=1e-3, atol=1e-4)
