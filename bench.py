@@ -195,11 +195,11 @@ def run_b200(args, rank, world, local_rank):
         if time_tree:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        loss = crit(out, y)
-        loss.backward()
+        loss = crit(out, y)  # fused kernel: loss AND dloss/dlogits in this one launch
         if time_tree:
             e1.record()
             tree_ev.append((e0, e1))
+        loss.backward()
         if reducer is not None:
             reducer.reduce()
         opt.step()

@@ -376,12 +376,15 @@ __global__ void __launch_bounds__(512) tree_kernel(const Params p) {
     {
       T* __restrict__ g = reinterpret_cast<T*>(p.grad);
       const float kgx = (MODE == kSoftBwd) ? 0.f : kx * p.grad_scale;
-      for (int e = lane; e < RPW * C; e += 32) {
-        const int rr = __umulhi((unsigned)e, t.magicC);
+      // warp-uniform trip count: every lane must reach the shuffles (full-mask shfl in a loop that
+      // some lanes have left is undefined -- it faulted as "illegal instruction" on sm_100a)
+      for (int e0 = 0; e0 < RPW * C; e0 += 32) {
+        const int e = e0 + lane;
+        const int rr = min((int)__umulhi((unsigned)e, t.magicC), RPW - 1);
         const int c = e - rr * C;
-        const float l1 = __shfl_sync(0xffffffffu, lse1, min(rr, RPW - 1) * G);
-        const int yy = __shfl_sync(0xffffffffu, y, min(rr, RPW - 1) * G);
-        if (rr < nrows) {
+        const float l1 = __shfl_sync(0xffffffffu, lse1, rr * G);
+        const int yy = __shfl_sync(0xffffffffu, y, rr * G);
+        if (e < RPW * C && rr < nrows) {
           const long long o = (row0 + rr) * p.ld + c;
           float gx = V1[rr * NVp + c];
           if (MODE != kSoftBwd) gx += kgx * (__expf(to_f<T>(x[o]) - l1) - (c == yy ? 1.f : 0.f));
