@@ -105,6 +105,37 @@ int nbdt_hard_loss(const nbdt_tree* tree, const void* logits, int dtype, const i
                    int64_t B, int64_t ld, int64_t batch_rows, float w_xent, float w_tree, float tsw,
                    float grad_scale, float* loss, void* grad_logits, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Backbone: implicit-GEMM convolutions on tcgen05 tensor cores (csrc/conv_gemm.cu).  These replace the
+ * cuDNN calls behind nn.Conv2d in the reference's backbones (nbdt/models/resnet.py:47-65,120 and the
+ * pytorchcv WRN units, nbdt/models/wideresnet.py:1-5).  Activations: NHWC bf16, channel counts
+ * multiples of 64 (pad with zero channels).  ksize in {1,3} with padding ksize/2, stride in {1,2}.
+ * ------------------------------------------------------------------------------------------- */
+
+/* y[N,H/s,W/s,Cout] = conv(x[N,H,W,Cin]; wpack) (+ residual, same shape as y; may be NULL).
+ * wpack: bf16 [ksize*ksize][Cout][Cin] from nbdt_conv_pack_weights. */
+int nbdt_conv2d_fwd(const void* x, const void* wpack, void* y, const void* residual, int N, int H, int W,
+                    int Cin, int Cout, int ksize, int stride, void* stream);
+
+/* dx[N,H,W,Cin] = data gradient of the above for dy[N,H/s,W/s,Cout] (+ accumulate, same shape as dx; may
+ * alias dx).  wpack_t: bf16 [ksize*ksize][Cin][Cout] from nbdt_conv_pack_weights. */
+int nbdt_conv2d_dgrad(const void* dy, const void* wpack_t, void* dx, const void* accumulate, int N, int H,
+                      int W, int Cin, int Cout, int ksize, int stride, void* stream);
+
+/* dwp[ksize*ksize][Cout][Cin] (fp32, overwritten) = weight gradient given x and dy. */
+int nbdt_conv2d_wgrad(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cin, int Cout,
+                      int ksize, int stride, void* stream);
+
+/* fp32 OIHW master weights -> bf16 tap-major matrices, zero padded to (cout_pad, cin_pad); either output
+ * may be NULL.  wpack [taps][cout_pad][cin_pad], wpack_t [taps][cin_pad][cout_pad]. */
+int nbdt_conv_pack_weights(const float* w_oihw, void* wpack, void* wpack_t, int Cout, int Cin, int cout_pad,
+                           int cin_pad, int ksize, void* stream);
+
+/* fp32 dwp [taps][cout_pad][cin_pad] -> OIHW gradient [Cout][Cin][k][k] (accumulate != 0: add into it). */
+int nbdt_conv_unpack_wgrad(const float* dwp, float* dw_oihw, int Cout, int Cin, int cout_pad, int cin_pad,
+                           int ksize, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

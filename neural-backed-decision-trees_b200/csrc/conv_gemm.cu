@@ -1,0 +1,799 @@
+// Implicit-GEMM convolution on 5th-generation tensor cores (tcgen05 + TMEM), operands fed by TMA.
+//
+// Activations are NHWC bf16.  A convolution (forward, or data-gradient) is a sum over filter taps of
+// plain GEMMs between a spatially SHIFTED view of the input and one [Cout x Cin] slice of the packed
+// weights:
+//
+//     out[n, i, j, :] = sum_t  W_t * in_{map(t)}[n, i + dh_t, j + dw_t, :]          ("tap GEMM")
+//
+// The shifted view is never materialised (no im2col buffer): a 4-D TMA tensor map (C, W, H, N)
+// loads the box {64 channels x box_w x box_h x box_n} = 128 pixels x 64 channels at the shifted
+// coordinates, out-of-bounds pixels (the padding halo) are zero-filled by the TMA unit, and the box
+// lands in shared memory exactly as the K-major, 128B-swizzled A tile the UMMA descriptor expects.
+// Stride-2 convolutions use up to four tensor maps over the (row, column) parity classes of the
+// input, which turns every tap into a unit-stride shifted view again; the stride-2 data-gradient
+// is the same kernel run once per OUTPUT parity class with a strided output view.
+//
+// CTA layout (192 threads, persistent, one CTA per SM):
+//   warp 0    TMA producer: per (tap, 64-channel k-block) one A box + one B (weights) box into a
+//             kStages-deep shared-memory ring, completion signalled on `full` mbarriers
+//   warp 1    MMA issuer: one elected thread issues 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per stage,
+//             tcgen05.commit releases the stage (`empty`) and finally publishes the accumulator
+//   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (TMEM, double buffered so the next tile's MMAs
+//             overlap), optional residual add, convert to bf16, vectorised global stores
+//
+// Roofline: tensor-pipe bound.  FLOPs per launch = 2 * N*Ho*Wo * Cout * Cin * taps.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+#include "sm100.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int kBlockM = 128;  // output pixels per tile (UMMA M)
+constexpr int kBlockK = 64;   // bf16 channels per k-block = one 128-byte swizzle row
+constexpr int kMaxTaps = 9;
+
+struct TapGemmParams {
+  int num_taps, kblocks, last_ksteps;  // k-blocks of 64 channels; K=16 steps in the last (partial) one
+  int n_tiles, tiles_w, tiles_h, tiles_n;
+  int box_w, box_h, box_n;
+  int N_img, H_out, W_out, Cout;
+  long long out_sn, out_sh, out_sw;  // output strides in elements (channel stride 1)
+  __nv_bfloat16* out;
+  const __nv_bfloat16* residual;  // same geometry as out, or nullptr
+  int tap_map[kMaxTaps];
+  int tap_dh[kMaxTaps];
+  int tap_dw[kMaxTaps];
+  int tap_wrow[kMaxTaps];  // first row of this tap's [Cout x Cin] slice in the packed weight matrix
+};
+
+template <int BLOCK_N>
+struct TapGemmCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N <= 64) ? 8 : (BLOCK_N <= 128 ? 6 : 5);
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
+                const __grid_constant__ CUtensorMap tm_in2, const __grid_constant__ CUtensorMap tm_in3,
+                const __grid_constant__ CUtensorMap tm_w, const TapGemmParams p) {
+  using Cfg = TapGemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                         // [kStages]
+  uint64_t* empty = bars + Cfg::kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int iters = p.num_taps * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_in0);
+    prefetch_tmap(&tm_w);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full[a]), 1);
+      mbar_init(smem_u32(&tmem_empty[a]), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_base_slot), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m = tile / p.n_tiles;
+        const int w0 = (m % p.tiles_w) * p.box_w;
+        m /= p.tiles_w;
+        const int h0 = (m % p.tiles_h) * p.box_h;
+        const int n0 = (m / p.tiles_h) * p.box_n;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const CUtensorMap* tm = p.tap_map[t] == 0 ? &tm_in0 : (p.tap_map[t] == 1 ? &tm_in1 : (p.tap_map[t] == 2 ? &tm_in2 : &tm_in3));
+          const int cw = w0 + p.tap_dw[t], ch = h0 + p.tap_dh[t];
+          const int wrow = p.tap_wrow[t] + n_tile * BLOCK_N;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+            const uint32_t a_dst = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t b_dst = a_dst + Cfg::kABytes;
+            const uint32_t bar = smem_u32(&full[stage]);
+            mbar_expect_tx(bar, Cfg::kStageBytes);
+            tma_load_4d(a_dst, tm, bar, kb * kBlockK, cw, ch, n0);
+            tma_load_2d(b_dst, &tm_w, bar, kb * kBlockK, wrow);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(smem_u32(&full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(a_addr + Cfg::kABytes, 16, 1024);
+          // channels past Cin in the last k-block are TMA zero fill; do not spend MMAs on them
+          const int ksteps = ((it + 1) % p.kblocks == 0) ? p.last_ksteps : kBlockK / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            // +32 bytes (= 2 in descriptor units) per K=16 step inside the 128-byte swizzle row
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty[stage]));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tmem_full[acc]));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are this warp's
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m = tile / p.n_tiles;
+      const int w0 = (m % p.tiles_w) * p.box_w;
+      m /= p.tiles_w;
+      const int h0 = (m % p.tiles_h) * p.box_h;
+      const int n0 = (m / p.tiles_h) * p.box_n;
+      // row of the tile -> pixel (TMA box order: w fastest, then h, then n)
+      const int pw = w0 + row % p.box_w;
+      const int ph = h0 + (row / p.box_w) % p.box_h;
+      const int pn = n0 + row / (p.box_w * p.box_h);
+      const bool in_range = pw < p.W_out && ph < p.H_out && pn < p.N_img;
+      const long long off = pn * p.out_sn + ph * p.out_sh + pw * p.out_sw + (long long)n_tile * BLOCK_N;
+
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (in_range) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
+          const uint4* res = p.residual ? reinterpret_cast<const uint4*>(p.residual + off + c0) : nullptr;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+            if (res) {
+              const uint4 r = res[q];  // plain load: residual may alias out (in-place accumulate)
+              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+                f[2 * e] += __bfloat162float(b.x);
+                f[2 * e + 1] += __bfloat162float(b.y);
+              }
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              o[e] = *reinterpret_cast<const uint32_t*>(&b);
+            }
+            dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor map with 128-byte swizzle and zero fill; dims/strides innermost first, strides in bytes
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+              const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return nbdt::set_error(NBDT_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint32_t elem_strides[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                  strides_bytes, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return nbdt::set_error(NBDT_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu ...)",
+                           (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1]);
+  return NBDT_OK;
+}
+
+int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct View4 {  // an NHWC view: element (n,h,w,c) at base + n*sn + h*sh + w*sw + c
+  const __nv_bfloat16* base;
+  int N, H, W, C;
+  long long sn, sh, sw;
+};
+
+int view_tmap(CUtensorMap* tm, const View4& v, int box_w, int box_h, int box_n) {
+  cuuint64_t dims[4] = {(cuuint64_t)v.C, (cuuint64_t)v.W, (cuuint64_t)v.H, (cuuint64_t)v.N};
+  cuuint64_t strides[3] = {(cuuint64_t)v.sw * 2, (cuuint64_t)v.sh * 2, (cuuint64_t)v.sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  return make_tmap(tm, v.base, 4, dims, strides, box);
+}
+
+struct Tap {
+  int map, dh, dw, wrow;
+};
+
+// Launch the tap GEMM: out view (strided) = sum over taps of W_t * in_view[tap.map] shifted.
+int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int num_taps, const __nv_bfloat16* wpack,
+                    int w_rows, int Cin, const View4& out, const __nv_bfloat16* residual, cudaStream_t stream) {
+  NBDT_REQUIRE(num_taps >= 1 && num_taps <= kMaxTaps, "bad tap count %d", num_taps);
+  NBDT_REQUIRE(num_views >= 1 && num_views <= 4, "bad view count %d", num_views);
+  NBDT_REQUIRE(Cin % 16 == 0, "input channels (%d) must be a multiple of 16 (pad the activation)", Cin);
+  const int Cout = out.C;
+  int block_n = 0;
+  if (Cout % 160 == 0) block_n = 160;
+  else if (Cout % 128 == 0) block_n = 128;
+  else if (Cout % 64 == 0) block_n = 64;
+  NBDT_REQUIRE(block_n != 0, "output channels (%d) must be a multiple of 64", Cout);
+  NBDT_REQUIRE(out.sw % 8 == 0 && out.sh % 8 == 0 && out.sn % 8 == 0 && (reinterpret_cast<uintptr_t>(out.base) & 15) == 0,
+               "output view must be 16-byte aligned");
+
+  TapGemmParams p = {};
+  p.box_w = std::min(pow2_ceil(out.W), kBlockM);
+  p.box_h = std::min(pow2_ceil(out.H), kBlockM / p.box_w);
+  p.box_n = kBlockM / (p.box_w * p.box_h);
+  p.tiles_w = (out.W + p.box_w - 1) / p.box_w;
+  p.tiles_h = (out.H + p.box_h - 1) / p.box_h;
+  p.tiles_n = (out.N + p.box_n - 1) / p.box_n;
+  p.n_tiles = Cout / block_n;
+  p.num_taps = num_taps;
+  p.kblocks = (Cin + kBlockK - 1) / kBlockK;
+  p.last_ksteps = (Cin - (p.kblocks - 1) * kBlockK) / 16;
+  p.N_img = out.N; p.H_out = out.H; p.W_out = out.W; p.Cout = Cout;
+  p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
+  p.out = const_cast<__nv_bfloat16*>(out.base);
+  p.residual = residual;
+  for (int t = 0; t < num_taps; ++t) {
+    p.tap_map[t] = taps[t].map; p.tap_dh[t] = taps[t].dh; p.tap_dw[t] = taps[t].dw; p.tap_wrow[t] = taps[t].wrow;
+  }
+  CUtensorMap tm_in[4], tm_w;
+  for (int v = 0; v < 4; ++v) {
+    const View4& src = in_views[v < num_views ? v : 0];
+    NBDT_REQUIRE(src.C == Cin, "view %d has %d channels, expected %d", v, src.C, Cin);
+    if (int rc = view_tmap(&tm_in[v], src, p.box_w, p.box_h, p.box_n)) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)w_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
+    if (int rc = make_tmap(&tm_w, wpack, 2, dims, strides, box)) return rc;
+  }
+  int dev = 0;
+  NBDT_CUDA_OK(cudaGetDevice(&dev));
+  nbdt::DeviceInfo info;
+  if (int rc = nbdt::device_info(dev, &info)) return rc;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int grid = std::min(total_tiles, info.sm_count);
+#define NBDT_LAUNCH_TAP(BN)                                                                                     \
+  {                                                                                                             \
+    auto kern = tap_gemm_kernel<BN>;                                                                            \
+    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmCfg<BN>::kSmemBytes)); \
+    kern<<<grid, 192, TapGemmCfg<BN>::kSmemBytes, stream>>>(tm_in[0], tm_in[1], tm_in[2], tm_in[3], tm_w, p);   \
+  }
+  if (block_n == 160) NBDT_LAUNCH_TAP(160)
+  else if (block_n == 128) NBDT_LAUNCH_TAP(128)
+  else NBDT_LAUNCH_TAP(64)
+#undef NBDT_LAUNCH_TAP
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+View4 dense_view(const void* base, int N, int H, int W, int C) {
+  View4 v;
+  v.base = reinterpret_cast<const __nv_bfloat16*>(base);
+  v.N = N; v.H = H; v.W = W; v.C = C;
+  v.sw = C; v.sh = (long long)W * C; v.sn = (long long)H * W * C;
+  return v;
+}
+
+// parity sub-view (ph, pw) of a dense tensor with even H, W: element (n, i, j) -> (n, 2i+ph, 2j+pw)
+View4 parity_view(const void* base, int N, int H, int W, int C, int ph, int pw) {
+  View4 v = dense_view(base, N, H, W, C);
+  v.base += (long long)ph * v.sh + (long long)pw * v.sw;
+  v.H = H / 2; v.W = W / 2;
+  v.sh *= 2; v.sw *= 2;
+  return v;
+}
+
+
+// =============================================================================================
+// Weight gradient:  dW_t[co, ci] = sum over pixels  dy[n, i, j, co] * x_{map(t)}[n, i + dh_t, j + dw_t, ci]
+//
+// A GEMM with the PIXEL index as K: both operands are "MN-major" for the tensor core (the channel
+// index -- M for dy, N for x -- is the contiguous one in NHWC).  TMA loads {64 channels x 64 pixels}
+// boxes (128-byte rows, one per pixel, 128B swizzle); the UMMA descriptors address them as MN-major
+// tiles (LBO = distance between 64-channel chunks, SBO = 1024 B between 8-pixel groups).
+// Work item = (tap, 128-row Cout tile, Cin tile, K split); fp32 partial sums are reduced into
+// dW[tap][Cout][Cin] with red.global.add.f32 (dW must be zeroed by the caller).
+// =============================================================================================
+constexpr int kWgPix = 64;  // pixels per k-block
+
+struct WgradParams {
+  int num_taps, m_tiles, n_tiles, splits;
+  int pix_blocks;              // total 64-pixel blocks = tiles_w * tiles_h * tiles_n
+  int tiles_w, tiles_h;        // pixel-block grid inside one image (box_n images per block when the image is small)
+  int box_w, box_h, box_n;
+  int Cout, Cin;
+  float* dw;                   // [taps][Cout][Cin] fp32
+  int tap_map[kMaxTaps];
+  int tap_dh[kMaxTaps];
+  int tap_dw[kMaxTaps];
+};
+
+template <int BLOCK_N>
+struct WgradCfg {
+  static constexpr int kChunkBytes = kWgPix * 128;                 // 64 pixels x 64 channels bf16
+  static constexpr int kAChunks = 2;                               // M = 128 channels of dy
+  static constexpr int kBChunks = (BLOCK_N + 63) / 64;
+  static constexpr int kStageBytes = (kAChunks + kBChunks) * kChunkBytes;
+  static constexpr int kStages = (190 * 1024) / kStageBytes > 8 ? 8 : (190 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x0,
+             const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
+             const __grid_constant__ CUtensorMap tm_x3, const WgradParams p) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_items = p.num_taps * p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_dy);
+    prefetch_tmap(&tm_x0);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full[a]), 1);
+      mbar_init(smem_u32(&tmem_empty[a]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_base_slot), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  // item -> (split, n_tile, m_tile, tap); split fastest so concurrently running CTAs share operand tiles in L2
+  auto decode = [&](int item, int& tap, int& m_tile, int& n_tile, int& kb0, int& kb1) {
+    const int split = item % p.splits;
+    item /= p.splits;
+    n_tile = item % p.n_tiles;
+    item /= p.n_tiles;
+    m_tile = item % p.m_tiles;
+    tap = item / p.m_tiles;
+    const int per = (p.pix_blocks + p.splits - 1) / p.splits;
+    kb0 = split * per;
+    kb1 = min(kb0 + per, p.pix_blocks);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int tap, m_tile, n_tile, kb0, kb1;
+        decode(item, tap, m_tile, n_tile, kb0, kb1);
+        const CUtensorMap* tmx = p.tap_map[tap] == 0 ? &tm_x0 : (p.tap_map[tap] == 1 ? &tm_x1 : (p.tap_map[tap] == 2 ? &tm_x2 : &tm_x3));
+        for (int kb = kb0; kb < kb1; ++kb) {
+          int b = kb;
+          const int w0 = (b % p.tiles_w) * p.box_w;
+          b /= p.tiles_w;
+          const int h0 = (b % p.tiles_h) * p.box_h;
+          const int n0 = (b / p.tiles_h) * p.box_n;
+          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          const uint32_t dst = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t bar = smem_u32(&full[stage]);
+          mbar_expect_tx(bar, Cfg::kStageBytes);
+#pragma unroll
+          for (int c = 0; c < Cfg::kAChunks; ++c)
+            tma_load_4d(dst + c * Cfg::kChunkBytes, &tm_dy, bar, m_tile * kBlockM + c * 64, w0, h0, n0);
+#pragma unroll
+          for (int c = 0; c < Cfg::kBChunks; ++c)
+            tma_load_4d(dst + (Cfg::kAChunks + c) * Cfg::kChunkBytes, tmx, bar, n_tile * BLOCK_N + c * 64,
+                        w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 1, 1);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int tap, m_tile, n_tile, kb0, kb1;
+        decode(item, tap, m_tile, n_tile, kb0, kb1);
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_smem_desc(a_addr, Cfg::kChunkBytes, 1024);
+          const uint64_t bdesc = make_smem_desc(a_addr + Cfg::kAChunks * Cfg::kChunkBytes, Cfg::kChunkBytes, 1024);
+#pragma unroll
+          for (int k = 0; k < kWgPix / 16; ++k) {
+            // K=16 pixels = two 8-pixel swizzle atoms = 2048 bytes (128 descriptor units)
+            umma_bf16(tmem_d, adesc + 128 * k, bdesc + 128 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty[stage]));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tmem_full[acc]));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int tap, m_tile, n_tile, kb0, kb1;
+      decode(item, tap, m_tile, n_tile, kb0, kb1);
+      const int co = m_tile * kBlockM + row;
+      float* dst = p.dw + ((long long)tap * p.Cout + co) * p.Cin + n_tile * BLOCK_N;
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      if (kb1 > kb0) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_wait();
+          if (co < p.Cout) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (n_tile * BLOCK_N + c0 + e < p.Cin) atomicAdd(dst + c0 + e, __uint_as_float(v[e]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight repacking: fp32 OIHW master weights <-> the bf16 tap-major matrices the GEMMs read
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                    __nv_bfloat16* __restrict__ wpt, int Cout, int Cin, int cin_pad, int cout_pad,
+                                    int taps) {
+  // w: [Cout][Cin][taps] (OIHW);  wp: [taps][cout_pad][cin_pad];  wpt: [taps][cin_pad][cout_pad]  (zero padded)
+  const long long total = (long long)taps * cout_pad * cin_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad);
+    const int co = (int)((i / cin_pad) % cout_pad);
+    const int t = (int)(i / ((long long)cin_pad * cout_pad));
+    const float v = (ci < Cin && co < Cout) ? w[((long long)co * Cin + ci) * taps + t] : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    if (wp) wp[i] = b;
+    if (wpt) wpt[((long long)t * cin_pad + ci) * cout_pad + co] = b;
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin,
+                                    int cin_pad, int cout_pad, int taps, int accumulate) {
+  // dwp: [taps][cout_pad][cin_pad] fp32  ->  dw: [Cout][Cin][taps] (OIHW)
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    const int co = (int)(i / ((long long)taps * Cin));
+    const float v = dwp[((long long)t * cout_pad + co) * cin_pad + ci];
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) (+ residual), ksize in {1,3} (pad = ksize/2), stride in {1,2}.
+// wpack: bf16 [ksize*ksize][Cout][Cin] (tap-major, K contiguous), from nbdt_conv_pack_weights.
+int nbdt_conv2d_fwd(const void* x, const void* wpack, void* y, const void* residual, int N, int H, int W, int Cin,
+                    int Cout, int ksize, int stride, void* stream) {
+  NBDT_REQUIRE(x && wpack && y, "NULL tensor");
+  NBDT_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "unsupported conv %dx%d stride %d", ksize, ksize, stride);
+  NBDT_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), "stride-2 conv needs even H, W");
+  const int Ho = H / stride, Wo = W / stride;
+  View4 out = dense_view(y, N, Ho, Wo, Cout);
+  View4 views[4];
+  Tap taps[kMaxTaps];
+  int nt = 0, nv = 1;
+  const int pad = ksize / 2;
+  if (stride == 1) {
+    views[0] = dense_view(x, N, H, W, Cin);
+    for (int r = 0; r < ksize; ++r)
+      for (int s = 0; s < ksize; ++s) taps[nt++] = Tap{0, r - pad, s - pad, (r * ksize + s) * Cout};
+  } else {
+    nv = 4;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) views[ph * 2 + pw] = parity_view(x, N, H, W, Cin, ph, pw);
+    for (int r = 0; r < ksize; ++r)
+      for (int s = 0; s < ksize; ++s) {
+        // input row 2*ho + r - pad = 2*(ho + dh) + ph
+        const int rr = r - pad, ss = s - pad;
+        const int ph = ((rr % 2) + 2) % 2, pw = ((ss % 2) + 2) % 2;
+        taps[nt++] = Tap{ph * 2 + pw, (rr - ph) / 2, (ss - pw) / 2, (r * ksize + s) * Cout};
+      }
+  }
+  return launch_tap_gemm(views, nv, taps, nt, reinterpret_cast<const __nv_bfloat16*>(wpack), ksize * ksize * Cout, Cin,
+                         out, reinterpret_cast<const __nv_bfloat16*>(residual), (cudaStream_t)stream);
+}
+
+// dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w) (+ accumulate), the data gradient of nbdt_conv2d_fwd.
+// wpack_t: bf16 [ksize*ksize][Cin][Cout] (tap-major, Cout contiguous), from nbdt_conv_pack_weights.
+int nbdt_conv2d_dgrad(const void* dy, const void* wpack_t, void* dx, const void* accumulate, int N, int H, int W,
+                      int Cin, int Cout, int ksize, int stride, void* stream) {
+  NBDT_REQUIRE(dy && wpack_t && dx, "NULL tensor");
+  NBDT_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "unsupported conv %dx%d stride %d", ksize, ksize, stride);
+  NBDT_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), "stride-2 conv needs even H, W");
+  const int Ho = H / stride, Wo = W / stride;
+  const int pad = ksize / 2;
+  const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(wpack_t);
+  View4 in = dense_view(dy, N, Ho, Wo, Cout);
+  if (stride == 1) {
+    // dx[h,w] = sum_{r,s} W[r,s]^T dy[h + pad - r, w + pad - s]
+    Tap taps[kMaxTaps];
+    int nt = 0;
+    for (int r = 0; r < ksize; ++r)
+      for (int s = 0; s < ksize; ++s) taps[nt++] = Tap{0, pad - r, pad - s, (r * ksize + s) * Cin};
+    View4 out = dense_view(dx, N, H, W, Cin);
+    return launch_tap_gemm(&in, 1, taps, nt, wp, ksize * ksize * Cin, Cout, out,
+                           reinterpret_cast<const __nv_bfloat16*>(accumulate), (cudaStream_t)stream);
+  }
+  if (ksize == 1) {
+    NBDT_REQUIRE(accumulate == nullptr, "1x1 stride-2 dgrad cannot accumulate; run it first and accumulate the 3x3 dgrad on top");
+    NBDT_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)N * H * W * Cin * 2, (cudaStream_t)stream));
+  }
+  // stride 2: dx[2i+ph, 2j+pw] = sum over taps with r == ph + pad (mod 2), s likewise, of
+  //           W[r,s]^T dy[i + (ph + pad - r)/2, j + (pw + pad - s)/2]
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      Tap taps[kMaxTaps];
+      int nt = 0;
+      for (int r = 0; r < ksize; ++r)
+        for (int s = 0; s < ksize; ++s) {
+          const int a = ph + pad - r, b = pw + pad - s;
+          if ((a & 1) || (b & 1)) continue;
+          taps[nt++] = Tap{0, a / 2, b / 2, (r * ksize + s) * Cin};
+        }
+      View4 out = parity_view(dx, N, H, W, Cin, ph, pw);
+      const __nv_bfloat16* acc = accumulate ? parity_view(accumulate, N, H, W, Cin, ph, pw).base : nullptr;
+      if (nt == 0) continue;  // (1x1 stride 2: odd positions get no gradient; dx was zero-filled above)
+      if (int rc = launch_tap_gemm(&in, 1, taps, nt, wp, ksize * ksize * Cin, Cout, out, acc, (cudaStream_t)stream)) return rc;
+    }
+  return NBDT_OK;
+}
+
+// dwp[taps][Cout][Cin] (fp32, zeroed here) = weight gradient of nbdt_conv2d_fwd given x and dy.
+int nbdt_conv2d_wgrad(const void* x, const void* dy, float* dwp, int N, int H, int W, int Cin, int Cout, int ksize,
+                      int stride, void* stream) {
+  NBDT_REQUIRE(x && dy && dwp, "NULL tensor");
+  NBDT_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "unsupported conv %dx%d stride %d", ksize, ksize, stride);
+  NBDT_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), "stride-2 conv needs even H, W");
+  NBDT_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "channel counts must be multiples of 8");
+  const int Ho = H / stride, Wo = W / stride;
+  const int pad = ksize / 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = ksize * ksize;
+  NBDT_CUDA_OK(cudaMemsetAsync(dwp, 0, (size_t)taps * Cout * Cin * sizeof(float), st));
+
+  WgradParams p = {};
+  int nv = 1;
+  View4 xviews[4];
+  if (stride == 1) {
+    xviews[0] = dense_view(x, N, H, W, Cin);
+    int nt = 0;
+    for (int r = 0; r < ksize; ++r)
+      for (int s = 0; s < ksize; ++s) { p.tap_map[nt] = 0; p.tap_dh[nt] = r - pad; p.tap_dw[nt] = s - pad; ++nt; }
+  } else {
+    nv = 4;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) xviews[ph * 2 + pw] = parity_view(x, N, H, W, Cin, ph, pw);
+    int nt = 0;
+    for (int r = 0; r < ksize; ++r)
+      for (int s = 0; s < ksize; ++s) {
+        const int rr = r - pad, ss = s - pad;
+        const int ph = ((rr % 2) + 2) % 2, pw = ((ss % 2) + 2) % 2;
+        p.tap_map[nt] = ph * 2 + pw; p.tap_dh[nt] = (rr - ph) / 2; p.tap_dw[nt] = (ss - pw) / 2; ++nt;
+      }
+  }
+  int block_n;
+  if (Cin % 160 == 0) block_n = 160;
+  else if (Cin % 256 == 0) block_n = 256;
+  else if (Cin % 128 == 0) block_n = 128;
+  else if (Cin % 64 == 0) block_n = 64;
+  else return nbdt::set_error(NBDT_EINVAL, "wgrad: input channels (%d) must be a multiple of 64", Cin);
+  p.num_taps = taps;
+  p.m_tiles = (Cout + kBlockM - 1) / kBlockM;
+  p.n_tiles = Cin / block_n;
+  p.box_w = std::min(pow2_ceil(Wo), kWgPix);
+  p.box_h = std::min(pow2_ceil(Ho), kWgPix / p.box_w);
+  p.box_n = kWgPix / (p.box_w * p.box_h);
+  p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
+  p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
+  const int tiles_n = (N + p.box_n - 1) / p.box_n;
+  p.pix_blocks = p.tiles_w * p.tiles_h * tiles_n;
+  p.Cout = Cout; p.Cin = Cin; p.dw = dwp;
+  int dev = 0;
+  NBDT_CUDA_OK(cudaGetDevice(&dev));
+  nbdt::DeviceInfo info;
+  if (int rc = nbdt::device_info(dev, &info)) return rc;
+  const int base_items = taps * p.m_tiles * p.n_tiles;
+  p.splits = std::max(1, std::min(p.pix_blocks, (2 * info.sm_count + base_items - 1) / base_items));
+  CUtensorMap tm_dy, tm_x[4];
+  {
+    View4 dyv = dense_view(dy, N, Ho, Wo, Cout);
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)dyv.sw * 2, (cuuint64_t)dyv.sh * 2, (cuuint64_t)dyv.sn * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.box_w, (cuuint32_t)p.box_h, (cuuint32_t)p.box_n};
+    if (int rc = make_tmap(&tm_dy, dyv.base, 4, dims, strides, box)) return rc;
+  }
+  for (int v = 0; v < 4; ++v)
+    if (int rc = view_tmap(&tm_x[v], xviews[v < nv ? v : 0], p.box_w, p.box_h, p.box_n)) return rc;
+  const int total_items = base_items * p.splits;
+  const int grid = std::min(total_items, info.sm_count);
+#define NBDT_LAUNCH_WG(BN)                                                                                      \
+  {                                                                                                             \
+    auto kern = wgrad_kernel<BN>;                                                                               \
+    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<BN>::kSmemBytes)); \
+    kern<<<grid, 192, WgradCfg<BN>::kSmemBytes, st>>>(tm_dy, tm_x[0], tm_x[1], tm_x[2], tm_x[3], p);             \
+  }
+  if (block_n == 160) NBDT_LAUNCH_WG(160)
+  else if (block_n == 256) NBDT_LAUNCH_WG(256)
+  else if (block_n == 128) NBDT_LAUNCH_WG(128)
+  else NBDT_LAUNCH_WG(64)
+#undef NBDT_LAUNCH_WG
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+// fp32 OIHW weights -> bf16 wpack [taps][cout_pad][cin_pad] and/or wpack_t [taps][cin_pad][cout_pad] (zero padded).
+int nbdt_conv_pack_weights(const float* w_oihw, void* wpack, void* wpack_t, int Cout, int Cin, int cout_pad,
+                           int cin_pad, int ksize, void* stream) {
+  NBDT_REQUIRE(w_oihw && (wpack || wpack_t), "NULL tensor");
+  NBDT_REQUIRE(cout_pad >= Cout && cin_pad >= Cin, "padded sizes smaller than the real ones");
+  const long long total = (long long)ksize * ksize * cout_pad * cin_pad;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(wpack),
+                                                               reinterpret_cast<__nv_bfloat16*>(wpack_t), Cout, Cin,
+                                                               cin_pad, cout_pad, ksize * ksize);
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+// fp32 dwp [taps][cout_pad][cin_pad] -> OIHW gradient [Cout][Cin][k][k] (optionally accumulating).
+int nbdt_conv_unpack_wgrad(const float* dwp, float* dw_oihw, int Cout, int Cin, int cout_pad, int cin_pad, int ksize,
+                           int accumulate, void* stream) {
+  NBDT_REQUIRE(dwp && dw_oihw, "NULL tensor");
+  const long long total = (long long)Cout * Cin * ksize * ksize;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+  unpack_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dwp, dw_oihw, Cout, Cin, cin_pad, cout_pad, ksize * ksize,
+                                                              accumulate);
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+}  // extern "C"

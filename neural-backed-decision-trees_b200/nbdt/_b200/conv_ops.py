@@ -1,0 +1,96 @@
+"""Tensor-level wrappers over the tcgen05 implicit-GEMM convolution entry points (csrc/conv_gemm.cu).
+
+Activations are NHWC bf16 tensors of shape (N, H, W, C) with C a multiple of 64; weights stay fp32 OIHW
+(`nn.Conv2d.weight`) and are repacked to bf16 tap-major matrices per call."""
+import torch
+
+from . import lib as L
+from .ops import _count, _p
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def _check_act(t, name):
+    L.require_cuda(t, name)
+    if t.dtype != torch.bfloat16 or t.dim() != 4 or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous NHWC bf16 tensor, got {t.dtype} {tuple(t.shape)}")
+
+
+def pack_weights(weight, cin_pad=None, cout_pad=None, want=(True, True)):
+    """fp32 OIHW -> (wpack [taps][cout_pad][cin_pad], wpack_t [taps][cin_pad][cout_pad]) bf16."""
+    L.require_cuda(weight, "pack_weights")
+    cout, cin, k, _ = weight.shape
+    cin_pad, cout_pad = cin_pad or cin, cout_pad or cout
+    w = weight.detach().float().contiguous()
+    wp = torch.empty((k * k, cout_pad, cin_pad), dtype=torch.bfloat16, device=w.device) if want[0] else None
+    wpt = torch.empty((k * k, cin_pad, cout_pad), dtype=torch.bfloat16, device=w.device) if want[1] else None
+    with torch.cuda.device(w.device):
+        L.check(L.load().nbdt_conv_pack_weights(_p(w), _p(wp), _p(wpt), cout, cin, cout_pad, cin_pad, k,
+                                                L.stream_ptr(w.device)))
+    _count()
+    return wp, wpt
+
+
+def conv_fwd(x, wp, ksize, stride, residual=None):
+    _check_act(x, "conv_fwd input")
+    N, H, W, cin = x.shape
+    taps, cout, cin_w = wp.shape
+    assert taps == ksize * ksize and cin_w == cin, (wp.shape, x.shape, ksize)
+    y = torch.empty((N, H // stride, W // stride, cout), dtype=torch.bfloat16, device=x.device)
+    if residual is not None:
+        _check_act(residual, "conv_fwd residual")
+        assert residual.shape == y.shape
+    with torch.cuda.device(x.device):
+        L.check(L.load().nbdt_conv2d_fwd(_p(x), _p(wp), _p(y), _p(residual), N, H, W, cin, cout, ksize, stride,
+                                         L.stream_ptr(x.device)))
+    _count()
+    return y
+
+
+def conv_dgrad(dy, wpt, in_hw, ksize, stride, accumulate=None):
+    """dx (N, H, W, Cin) for dy (N, H/s, W/s, Cout); `accumulate` (same shape as dx) is added and
+    overwritten in place."""
+    _check_act(dy, "conv_dgrad dy")
+    N, Ho, Wo, cout = dy.shape
+    H, W = in_hw
+    taps, cin, cout_w = wpt.shape
+    assert taps == ksize * ksize and cout_w == cout and Ho == H // stride and Wo == W // stride
+    dx = accumulate if accumulate is not None else torch.empty((N, H, W, cin), dtype=torch.bfloat16, device=dy.device)
+    if accumulate is not None:
+        _check_act(accumulate, "conv_dgrad accumulate")
+        assert accumulate.shape == (N, H, W, cin)
+    with torch.cuda.device(dy.device):
+        L.check(L.load().nbdt_conv2d_dgrad(_p(dy), _p(wpt), _p(dx), _p(accumulate), N, H, W, cin, cout, ksize, stride,
+                                           L.stream_ptr(dy.device)))
+    _count(4 if stride == 2 else 1)
+    return dx
+
+
+def conv_wgrad(x, dy, ksize, stride):
+    """fp32 [taps][Cout][Cin] weight gradient (padded channel counts, as the activations carry them)."""
+    _check_act(x, "conv_wgrad x")
+    _check_act(dy, "conv_wgrad dy")
+    N, H, W, cin = x.shape
+    cout = dy.shape[3]
+    assert dy.shape == (N, H // stride, W // stride, cout)
+    dwp = torch.empty((ksize * ksize, cout, cin), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        L.check(L.load().nbdt_conv2d_wgrad(_p(x), _p(dy), _p(dwp), N, H, W, cin, cout, ksize, stride,
+                                           L.stream_ptr(x.device)))
+    _count()
+    return dwp
+
+
+def unpack_wgrad(dwp, weight_shape, out=None, accumulate=False):
+    cout, cin, k, _ = weight_shape
+    taps, cout_pad, cin_pad = dwp.shape
+    if out is None:
+        out = torch.empty(weight_shape, dtype=torch.float32, device=dwp.device)
+        accumulate = False
+    with torch.cuda.device(dwp.device):
+        L.check(L.load().nbdt_conv_unpack_wgrad(_p(dwp), _p(out), cout, cin, cout_pad, cin_pad, k, int(accumulate),
+                                                L.stream_ptr(dwp.device)))
+    _count()
+    return out

@@ -43,6 +43,11 @@ SIGNATURES = {
     "nbdt_node_outputs": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nbdt_soft_loss": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_ptr, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "nbdt_hard_loss": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_ptr, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
+    "nbdt_conv2d_fwd": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 7 + [c_ptr]),
+    "nbdt_conv2d_dgrad": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 7 + [c_ptr]),
+    "nbdt_conv2d_wgrad": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 7 + [c_ptr]),
+    "nbdt_conv_pack_weights": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 5 + [c_ptr]),
+    "nbdt_conv_unpack_wgrad": (ctypes.c_int, [c_ptr, c_ptr] + [ctypes.c_int] * 6 + [c_ptr]),
 }
 
 _lib = None
