@@ -136,6 +136,42 @@ int nbdt_conv_pack_weights(const float* w_oihw, void* wpack, void* wpack_t, int 
 int nbdt_conv_unpack_wgrad(const float* dwp, float* dw_oihw, int Cout, int Cin, int cout_pad, int cin_pad,
                            int ksize, int accumulate, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backbone: memory-bound kernels around the convolutions (csrc/bn_ops.cu).  Activations bf16 [M][C]
+ * (M = N*H*W rows of an NHWC tensor), parameters / statistics fp32.  They replace nn.BatchNorm2d,
+ * F.relu, the residual add, F.avg_pool2d and optim.SGD of the reference train step
+ * (nbdt/models/resnet.py:50-54,70-73,142; main.py:207,239).  c_real <= C marks zero-padded channels.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Training-mode batch statistics: mean_invstd[2][C], scale_shift[2][C] (y = x*scale + shift), running-stat
+ * update with `momentum` (running_* may be NULL).  sums: [2][C] fp32 scratch. */
+int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float momentum, float eps, float* sums,
+                  float* mean_invstd, float* scale_shift, void* stream);
+/* Eval mode: scale_shift from the running statistics. */
+int nbdt_bn_eval_scale(int C, int c_real, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale_shift, void* stream);
+/* y = act(x*scale + shift (+ residual)), act = ReLU when relu != 0. */
+int nbdt_bn_apply(const void* x, const void* residual, void* y, long long M, int C, const float* scale_shift,
+                  int relu, void* stream);
+/* Backward of nbdt_bn_stats + nbdt_bn_apply.  act = the forward output when ReLU was applied (else NULL);
+ * dx = gradient w.r.t. x (+ extra, may be NULL); dres (may be NULL) = gradient w.r.t. the residual;
+ * dsums[2][C] receives (sum g, sum g*xhat) = (dbeta, dgamma). */
+int nbdt_bn_backward(const void* x, const void* act, const void* dy, const void* extra, void* dx, void* dres,
+                     long long M, int C, int c_real, const float* gamma, const float* mean_invstd, float* dsums,
+                     void* stream);
+/* feat[N][C] (fp32) = mean over the HW rows of each image;  da = dfeat / HW broadcast. */
+int nbdt_avgpool_fwd(const void* a, float* feat, int N, int HW, int C, void* stream);
+int nbdt_avgpool_bwd(const float* dfeat, void* da, int N, int HW, int C, void* stream);
+/* 3-channel 3x3 stem conv: x NCHW fp32 [N,3,H,W], w fp32 [cout][3][3][3] -> y NHWC bf16 [N,H,W,c_phys]
+ * (channels >= cout are written as zero); and its weight gradient. */
+int nbdt_stem_fwd(const float* x, const float* w, void* y, int N, int H, int W, int cout, int c_phys, void* stream);
+int nbdt_stem_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int cout, int c_phys,
+                    void* stream);
+/* Fused SGD over a flat fp32 buffer: m = momentum*m + (g*grad_scale + wd*p); p -= lr*m (first_step: m = g'). */
+int nbdt_sgd_step(float* params, const float* grads, float* momentum_buf, long long n, float lr, float momentum,
+                  float weight_decay, float grad_scale, int first_step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

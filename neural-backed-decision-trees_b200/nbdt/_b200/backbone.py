@@ -1,51 +1,72 @@
-"""Functional backbone ops used by nbdt.models (conv / batch-norm / activation / pool / linear).
-
-INTERIM (round 1, first slice): these dispatch to ATen/cuDNN on the CUDA device while the
-hand-written tcgen05 implicit-GEMM conv + BN kernels (csrc/conv_*.cu) are brought up; each op is
-replaced behind this interface with parity tests against the ATen result.  CUDA tensors only.
+"""Functional backbone ops used by nbdt.models: every conv / batch-norm / activation / pool runs as a
+hand-written sm_100a kernel (tcgen05 implicit-GEMM convolutions, fused BN(+ReLU,+residual) passes) on
+NHWC bf16 activations.  The classifier GEMM (features x FC weight) is a plain library GEMM (cuBLAS via
+F.linear) in fp32.  CUDA tensors only; there is no CPU or ATen/cuDNN convolution path behind these.
 """
 import torch
 import torch.nn.functional as F
 
 from . import lib as L
+from .conv_ops import pad64
+from .nn_ops import AvgPoolFunction, BatchNormActFunction, ConvFunction, StemFunction
+
+BACKBONE_STATUS = "own kernels: tcgen05/TMA implicit-GEMM conv fwd/dgrad/wgrad, fused BN+ReLU(+residual), pool, stem"
 
 
-def _bn(x, bn):
-    return F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias,
-                        bn.training or not bn.track_running_stats, bn.momentum or 0.0, bn.eps)
+def _bn_args(bn):
+    training = bn.training or not bn.track_running_stats
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return bn.weight, bn.bias, bn.running_mean, bn.running_var, training, momentum, bn.eps
+
+
+def _check_conv(conv_mod):
+    k = conv_mod.kernel_size[0]
+    s = conv_mod.stride[0]
+    if (conv_mod.kernel_size != (k, k) or k not in (1, 3) or conv_mod.stride != (s, s) or s not in (1, 2)
+            or conv_mod.padding != (k // 2, k // 2) or conv_mod.bias is not None or conv_mod.groups != 1
+            or conv_mod.dilation != (1, 1)):
+        raise NotImplementedError(f"no B200 kernel for {conv_mod}; supported: 1x1/3x3, stride 1/2, pad k//2, no bias")
+    return s
 
 
 def conv(x, conv_mod, residual=None):
-    L.require_cuda(x, "backbone conv")
-    y = F.conv2d(x, conv_mod.weight.to(x.dtype), None, conv_mod.stride, conv_mod.padding)
-    return y if residual is None else y + residual
+    """NHWC bf16 (N,H,W,Cin) -> (N,H/s,W/s,Cout), optionally + residual (fused in the epilogue)."""
+    stride = _check_conv(conv_mod)
+    return ConvFunction.apply(x, conv_mod.weight, stride, residual)
 
 
-def bn_act(x, bn, relu=True):
-    L.require_cuda(x, "backbone batch-norm")
-    y = _bn(x, bn)
-    return F.relu(y) if relu else y
+def bn_act(x, bn, relu=True, residual=None):
+    return BatchNormActFunction.apply(x, *_bn_args(bn), relu, residual)
 
 
 def conv_bn_act(x, conv_mod, bn, relu=True, residual=None):
-    y = _bn(conv(x, conv_mod), bn)
-    if residual is not None:
-        y = y + residual
-    return F.relu(y) if relu else y
+    return bn_act(conv(x, conv_mod), bn, relu=relu, residual=residual)
 
 
 def stem(x, conv_mod, bn):
+    """NCHW fp32 images -> NHWC bf16 feature map (channels padded to a multiple of 64)."""
     L.require_cuda(x, "backbone stem")
-    return conv_bn_act(x, conv_mod, bn, relu=True) if bn is not None else conv(x, conv_mod)
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"expected (N, 3, H, W) images, got {tuple(x.shape)}")
+    _check_conv(conv_mod)
+    y = StemFunction.apply(x, conv_mod.weight, pad64(conv_mod.out_channels))
+    return bn_act(y, bn, relu=True) if bn is not None else y
 
 
 def global_avg_pool(x):
-    return x.mean(dim=(2, 3))
+    return AvgPoolFunction.apply(x)
 
 
 def avg_pool(x, pool):
-    return pool(x).flatten(1)
+    k = getattr(pool, "kernel_size", None)
+    if isinstance(pool, torch.nn.AdaptiveAvgPool2d) or k in (x.shape[1], (x.shape[1], x.shape[2])):
+        return AvgPoolFunction.apply(x)
+    raise NotImplementedError(f"final pool {pool} on a {x.shape[1]}x{x.shape[2]} map is not a global pool")
 
 
-def linear(x, lin):
-    return F.linear(x, lin.weight.to(x.dtype), lin.bias.to(x.dtype))
+def linear(feat, lin):
+    """Classifier: fp32 features (N, C_phys) x FC weight -- a plain library GEMM."""
+    c = lin.in_features
+    return F.linear(feat[:, :c], lin.weight, lin.bias)

@@ -1,0 +1,155 @@
+"""Autograd functions of the B200 backbone: every forward/backward is a hand-written kernel behind the
+C ABI (csrc/conv_gemm.cu, csrc/bn_ops.cu).  Activations are NHWC bf16 tensors (N, H, W, C); parameters stay
+fp32 `nn.Parameter`s in their PyTorch layouts, so state_dicts, optimizers and checkpoints are unchanged."""
+import torch
+
+from . import conv_ops as C
+from . import lib as L
+from .ops import _count, _p
+
+
+def _stream(t):
+    return L.stream_ptr(t.device)
+
+
+def _pad_vec(v, n, fill=0.0):
+    v = v.detach().float()
+    if v.numel() == n:
+        return v.contiguous()
+    out = torch.full((n,), fill, dtype=torch.float32, device=v.device)
+    out[: v.numel()] = v
+    return out
+
+
+class StemFunction(torch.autograd.Function):
+    """3x3 stride-1 conv on the 3-channel NCHW fp32 input -> NHWC bf16 with `c_phys` physical channels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, c_phys):
+        L.require_cuda(x, "stem conv")
+        x = x.float().contiguous()
+        w = weight.detach().float().contiguous()
+        N, cin, H, W = x.shape
+        assert cin == 3 and tuple(w.shape[1:]) == (3, 3, 3), "the stem kernel handles 3x3 convs on 3 input channels"
+        cout = w.shape[0]
+        y = torch.empty((N, H, W, c_phys), dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.load().nbdt_stem_fwd(_p(x), _p(w), _p(y), N, H, W, cout, c_phys, _stream(x)))
+        _count()
+        ctx.save_for_backward(x)
+        ctx.cout, ctx.c_phys = cout, c_phys
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        N, _, H, W = x.shape
+        dw = torch.empty((ctx.cout, 3, 3, 3), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.load().nbdt_stem_wgrad(_p(x), _p(dy), _p(dw), N, H, W, ctx.cout, ctx.c_phys, _stream(x)))
+        _count()
+        return None, dw, None
+
+
+class ConvFunction(torch.autograd.Function):
+    """y = conv(x, weight) (+ residual) on tcgen05 tensor cores; backward = dgrad + wgrad kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, residual):
+        cout, cin, k, _ = weight.shape
+        cin_phys = x.shape[3]
+        assert cin_phys >= cin
+        wp, wpt = C.pack_weights(weight, cin_pad=cin_phys, cout_pad=cout)
+        y = C.conv_fwd(x, wp, k, stride, residual)
+        ctx.save_for_backward(x, wpt)
+        ctx.meta = (tuple(weight.shape), k, stride, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wpt = ctx.saved_tensors
+        wshape, k, stride, has_res = ctx.meta
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = C.conv_dgrad(dy, wpt, (x.shape[1], x.shape[2]), k, stride)
+        if ctx.needs_input_grad[1]:
+            dw = C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride), wshape)
+        return dx, dw, None, (dy if has_res else None)
+
+
+class BatchNormActFunction(torch.autograd.Function):
+    """y = act(batch_norm(x) (+ residual)); training mode uses batch statistics and updates the running ones."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual):
+        C._check_act(x, "batch norm input")
+        N, H, W, Cp = x.shape
+        M = N * H * W
+        c_real = gamma.numel()
+        dev = x.device
+        g, b = _pad_vec(gamma, Cp, 1.0), _pad_vec(beta, Cp)
+        scale_shift = torch.empty((2, Cp), dtype=torch.float32, device=dev)
+        mean_invstd = torch.empty((2, Cp), dtype=torch.float32, device=dev)
+        lib = L.load()
+        with torch.cuda.device(dev):
+            if training:
+                sums = torch.empty((2, Cp), dtype=torch.float32, device=dev)
+                rm = running_mean if running_mean is not None else None
+                rv = running_var if running_var is not None else None
+                L.check(lib.nbdt_bn_stats(_p(x), M, Cp, c_real, _p(g), _p(b), _p(rm), _p(rv), float(momentum), float(eps),
+                                          _p(sums), _p(mean_invstd), _p(scale_shift), _stream(x)))
+                _count(2)
+            else:
+                L.check(lib.nbdt_bn_eval_scale(Cp, c_real, _p(g), _p(b), _p(running_mean), _p(running_var), float(eps),
+                                               _p(scale_shift), _stream(x)))
+                _count()
+            y = torch.empty_like(x)
+            L.check(lib.nbdt_bn_apply(_p(x), _p(residual), _p(y), M, Cp, _p(scale_shift), int(relu), _stream(x)))
+            _count()
+        ctx.training = training
+        ctx.meta = (M, Cp, c_real, relu, residual is not None)
+        ctx.save_for_backward(x, y if relu else None, g, mean_invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        if not ctx.training:
+            raise NotImplementedError("backward through eval-mode batch norm is not implemented on the B200 path")
+        x, act, g, mean_invstd = ctx.saved_tensors
+        M, Cp, c_real, relu, has_res = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        dsums = torch.empty((2, Cp), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.load().nbdt_bn_backward(_p(x), _p(act), _p(dy), None, _p(dx), _p(dres), M, Cp, c_real, _p(g),
+                                              _p(mean_invstd), _p(dsums), _stream(x)))
+        _count(2)
+        return dx, dsums[1, :c_real].clone(), dsums[0, :c_real].clone(), None, None, None, None, None, None, dres
+
+
+class AvgPoolFunction(torch.autograd.Function):
+    """(N, H, W, C) bf16 -> (N, C) fp32 mean over the spatial positions."""
+
+    @staticmethod
+    def forward(ctx, a):
+        C._check_act(a, "average pool input")
+        N, H, W, Cp = a.shape
+        feat = torch.empty((N, Cp), dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            L.check(L.load().nbdt_avgpool_fwd(_p(a), _p(feat), N, H * W, Cp, _stream(a)))
+        _count()
+        ctx.shape = (N, H, W, Cp)
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        N, H, W, Cp = ctx.shape
+        dfeat = dfeat.float().contiguous()
+        da = torch.empty((N, H, W, Cp), dtype=torch.bfloat16, device=dfeat.device)
+        with torch.cuda.device(dfeat.device):
+            L.check(L.load().nbdt_avgpool_bwd(_p(dfeat), _p(da), N, H * W, Cp, _stream(dfeat)))
+        _count()
+        return da

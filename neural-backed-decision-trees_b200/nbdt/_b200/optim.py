@@ -1,0 +1,69 @@
+"""Fused SGD (momentum + weight decay) over ONE flat fp32 buffer.
+
+All parameters (and their gradients) are re-seated as views of two flat buffers, so the optimizer step
+is a single kernel launch (csrc/bn_ops.cu: sgd_kernel) and the data-parallel gradient all-reduce is a
+single NCCL call on the flat gradient buffer -- no per-tensor launches, no bucket copies.  Semantics
+are torch.optim.SGD's (dampening 0, no nesterov), the optimizer of the reference train step (main.py:207).
+"""
+import torch
+
+from . import lib as L
+from .ops import _count, _p
+
+
+class FusedSGD(torch.optim.Optimizer):
+    def __init__(self, params, lr=0.1, momentum=0.9, weight_decay=0.0):
+        params = [p for p in params if p.requires_grad]
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        assert len(self.param_groups) == 1, "FusedSGD takes a single parameter group"
+        ps = self.param_groups[0]["params"]
+        for p in ps:
+            L.require_cuda(p, "FusedSGD parameter")
+            if p.dtype != torch.float32:
+                raise TypeError("FusedSGD keeps fp32 master parameters")
+        dev = ps[0].device
+        total = sum(p.numel() for p in ps)
+        self.flat_param = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_momentum = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            self.flat_param[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + n].view_as(p)
+            p.grad = self.flat_grad[off:off + n].view_as(p)
+            off += n
+        self._steps = 0
+        self.grad_scale = 1.0
+
+    def zero_grad(self, set_to_none=False):
+        # gradients live in the flat buffer: keep the views, clear the storage with one memset
+        self.flat_grad.zero_()
+        off = 0
+        for p in self.param_groups[0]["params"]:
+            n = p.numel()
+            want = self.flat_grad[off:off + n].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != want.data_ptr():
+                p.grad = want
+            off += n
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        g = self.param_groups[0]
+        # autograd may have REPLACED p.grad (first backward after None) instead of accumulating in place
+        off = 0
+        for p in g["params"]:
+            n = p.numel()
+            if p.grad is not None and p.grad.data_ptr() != self.flat_grad[off:off + n].data_ptr():
+                self.flat_grad[off:off + n].copy_(p.grad.reshape(-1))
+                p.grad = self.flat_grad[off:off + n].view_as(p)
+            off += n
+        with torch.cuda.device(self.flat_param.device):
+            L.check(L.load().nbdt_sgd_step(_p(self.flat_param), _p(self.flat_grad), _p(self.flat_momentum),
+                                           self.flat_param.numel(), float(g["lr"]), float(g["momentum"]),
+                                           float(g["weight_decay"]), float(self.grad_scale), int(self._steps == 0),
+                                           L.stream_ptr(self.flat_param.device)))
+        _count()
+        self._steps += 1
+        return loss

@@ -9,7 +9,7 @@ BatchNorm statistics stay per replica, as in the reference.
 import torch
 import torch.distributed as dist
 
-BACKBONE_STATUS = "interim: conv/BN via ATen-cuDNN under bf16 autocast; own tcgen05 conv kernels pending"
+from .backbone import BACKBONE_STATUS  # noqa: E402,F401
 
 
 def broadcast_parameters(module, src=0):
