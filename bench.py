@@ -171,27 +171,29 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch  # per GPU (weak scaling)
+    from nbdt._b200 import conv_ops
+    from nbdt._b200.optim import FusedSGD
+
     torch.manual_seed(0)
-    net = wrn28_10_cifar10().to(dev).to(memory_format=torch.channels_last)
+    net = wrn28_10_cifar10().to(dev)
     net.train()
     crit = SoftTreeSupLoss(dataset="CIFAR10", criterion=nn.CrossEntropyLoss(), hierarchy="induced-wrn28_10_cifar10")
     crit.batch_rows = B * world  # the mean runs over the global batch; shards add up under all-reduce(sum)
-    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
-    reducer = parallel.GradientAllReduce(net.parameters(), world) if world > 1 else None
     if world > 1:
         parallel.broadcast_parameters(net)
+    opt = FusedSGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    reducer = parallel.FlatGradientAllReduce(opt, world) if world > 1 else None
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_x = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
     host_y = torch.randint(10, (B,), generator=g).pin_memory()
-    dev_x = host_x.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
+    dev_x = host_x.to(dev, non_blocking=True)
     dev_y = host_y.to(dev, non_blocking=True)
     tree_ev = []
 
     def step(x, y, time_tree=False):
-        opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = net(x)
+        opt.zero_grad()
+        out = net(x)
         if time_tree:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -226,16 +228,24 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step(dev_x, dev_y)
     launches0 = ops.launch_count()
+    conv_ops.PROFILE = []
     with ClockSampler(local_rank) as clocks:
         total_ms = timed(lambda: step(dev_x, dev_y, time_tree=True), args.steps)
     launches = ops.launch_count() - launches0
     clock_summary = clocks.summary()
     torch.cuda.synchronize(dev)
+    conv_prof, conv_ops.PROFILE = conv_ops.PROFILE, None
     tree_ms = sum(a.elapsed_time(b) for a, b in tree_ev) / max(len(tree_ev), 1)
+    conv_stats = {}
+    for kind, flops, e0, e1 in conv_prof:
+        st = conv_stats.setdefault(kind, [0.0, 0.0, 0])
+        st[0] += flops
+        st[1] += e0.elapsed_time(e1)
+        st[2] += 1
 
     # end to end through the public API: pinned host batch in, loss value out, every step
     def e2e_step():
-        x = host_x.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
+        x = host_x.to(dev, non_blocking=True)
         y = host_y.to(dev, non_blocking=True)
         return step(x, y).item()
 
@@ -248,24 +258,33 @@ def run_b200(args, rank, world, local_rank):
     ms_per_step = total_ms / args.steps
     value = B * world / (ms_per_step / 1e3)
     e2e_value = B * world / (e2e_ms / args.steps / 1e3)
-    esz = 2  # bf16 logits out of autocast
+    esz = 4  # the classifier GEMM emits fp32 logits
     tree_bytes = 2 * B * 10 * esz + 8 * B + 4
+    conv_flops = sum(v[0] for v in conv_stats.values())
+    conv_ms = sum(v[1] for v in conv_stats.values())
+    conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    peak_tf = peaks["bf16_tflops_sustained"]
     line = {
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                   "l2": "working set (activations ~3 GB/step) >> L2; no flush needed",
-                   "backbone": parallel.BACKBONE_STATUS},
+                   "l2": "working set (activations ~5 GB/step) >> L2; no flush needed",
+                   "backbone": parallel.BACKBONE_STATUS, "optimizer": "fused SGD momentum 0.9 wd 5e-4 (fp32 master weights)"},
         "clocks": clock_summary,
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": host_x.numel() * 4 + host_y.numel() * 8,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "roofline": {"kernel": "tree_kernel<soft loss fwd+bwd> (the only own kernel in the interim step)",
-                     "bound": "hbm", "achieved": tree_bytes / (tree_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": tree_bytes / (tree_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                     "peak_source": peak_src, "launch_us": tree_ms * 1e3,
-                     "note": "25 KB per launch at the BASELINE batch: latency-bound; see profiles/ for the saturating sweep"},
+        "roofline": {"kernel": "tap_gemm_kernel / wgrad_kernel (tcgen05 implicit-GEMM conv fwd + dgrad + wgrad, all launches of the timed steps)",
+                     "bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": conv_tflops / peak_tf, "traffic": None, "peak_source": peak_src + " (bf16_tflops_sustained)",
+                     "per_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms_per_step": v[1] / args.steps,
+                                      "launches_per_step": v[2] / args.steps} for k, v in conv_stats.items()},
+                     "conv_share_of_step": conv_ms / total_ms},
+        "tree_roofline": {"kernel": "tree_kernel<soft loss fwd+bwd>", "bound": "hbm",
+                          "achieved": tree_bytes / (tree_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": tree_bytes / (tree_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_us": tree_ms * 1e3,
+                          "note": "45 KB per launch at the BASELINE batch: latency-bound; saturating sweep in profiles/"},
         "step_tflops": FLOPS_PER_IMAGE * B * world / (ms_per_step / 1e3) / 1e12,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -38,7 +38,18 @@ def _digest(path):
     return h.hexdigest()
 
 
+def _generate():
+    """Hierarchy-specialised tree kernels (csrc/tree_spec_gen.cu) from the shipped hierarchies."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_tree_kernels", os.path.join(CSRC, "gen_tree_kernels.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main()
+
+
 def build(force=False, verbose=False):
+    _generate()
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     objs, rebuilt = [], False

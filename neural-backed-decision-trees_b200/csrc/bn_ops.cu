@@ -40,12 +40,24 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // Shared skeleton of the per-channel reductions: thread (r, o) owns channel octet o of rows
-// r, r + R, ... of this CTA's grid-stride share; NACC float accumulators per channel.
-template <int NACC, typename F>
-__device__ __forceinline__ void reduce_rows(long long M, int C, float* __restrict__ out /*[NACC][C]*/, F body) {
+// r, r + R, ... of this CTA's grid-stride share; NACC float accumulators per channel.  `Op` provides
+//   Pack load(row, o)            -- the global loads of one row (issued 4 rows at a time for memory-level parallelism)
+//   void accum(pack, o, acc)     -- the arithmetic
+template <int NACC, typename Op>
+__device__ __forceinline__ void reduce_rows(long long M, int C, float* __restrict__ out /*[NACC][C]*/, Op op) {
   extern __shared__ float red[];  // [R][NACC][C]  (only when R > 1)
   const int octets = C / 8;
   float acc[NACC][8];
+  auto run = [&](long long row, long long stride, int o) {
+    for (; row + 3 * stride < M; row += 4 * stride) {
+      auto p0 = op.load(row, o);
+      auto p1 = op.load(row + stride, o);
+      auto p2 = op.load(row + 2 * stride, o);
+      auto p3 = op.load(row + 3 * stride, o);
+      op.accum(p0, o, acc); op.accum(p1, o, acc); op.accum(p2, o, acc); op.accum(p3, o, acc);
+    }
+    for (; row < M; row += stride) op.accum(op.load(row, o), o, acc);
+  };
   if (octets <= kThreads) {
     const int R = kThreads / octets;
     const int r = threadIdx.x / octets, o = threadIdx.x % octets;
@@ -54,8 +66,7 @@ __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restric
     for (int a = 0; a < NACC; ++a)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
-    if (active)
-      for (long long row = (long long)blockIdx.x * R + r; row < M; row += (long long)gridDim.x * R) body(row, o, acc);
+    if (active) run((long long)blockIdx.x * R + r, (long long)gridDim.x * R, o);
     if (R > 1) {
       if (active)
 #pragma unroll
@@ -85,7 +96,7 @@ __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restric
       for (int a = 0; a < NACC; ++a)
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
-      for (long long row = blockIdx.x; row < M; row += gridDim.x) body(row, o, acc);
+      run(blockIdx.x, gridDim.x, o);
 #pragma unroll
       for (int a = 0; a < NACC; ++a)
 #pragma unroll
@@ -94,19 +105,25 @@ __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restric
   }
 }
 
-// sums[0][c] = sum_rows x, sums[1][c] = sum_rows x^2.          bytes: M*C*2 read
-__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const uint4* __restrict__ x, long long M, int C,
-                                                            float* __restrict__ sums) {
-  const int octets = C / 8;
-  reduce_rows<2>(M, C, sums, [&](long long row, int o, float (&acc)[2][8]) {
+struct StatsOp {
+  const uint4* x;
+  int octets;
+  __device__ __forceinline__ uint4 load(long long row, int o) const { return __ldg(x + row * octets + o); }
+  __device__ __forceinline__ void accum(const uint4& v, int, float (&acc)[2][8]) const {
     float f[8];
-    unpack8(__ldg(x + row * octets + o), f);
+    unpack8(v, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       acc[0][e] += f[e];
-      acc[1][e] += f[e] * f[e];
+      acc[1][e] = fmaf(f[e], f[e], acc[1][e]);
     }
-  });
+  }
+};
+
+// sums[0][c] = sum_rows x, sums[1][c] = sum_rows x^2.          bytes: M*C*2 read
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const uint4* __restrict__ x, long long M, int C,
+                                                            float* __restrict__ sums) {
+  reduce_rows<2>(M, C, sums, StatsOp{x, C / 8});
 }
 
 // mean/invstd, affine scale/shift, running-stat update (momentum, unbiased variance) -- C threads of work.
@@ -158,11 +175,12 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const uint4* __restr
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ss[i] = scale_shift[i];
   __syncthreads();
   const int octets = C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_octets; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto one = [&](long long i, const uint4& vx, const uint4& vr) {
     const int c0 = (int)(i % octets) * 8;
     float f[8], r[8];
-    unpack8(__ldg(x + i), f);
-    if (res) unpack8(__ldg(res + i), r);
+    unpack8(vx, f);
+    unpack8(vr, r);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float v = fmaf(f[e], ss[c0 + e], ss[C + c0 + e]);
@@ -170,8 +188,52 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const uint4* __restr
       f[e] = relu ? fmaxf(v, 0.f) : v;
     }
     y[i] = pack8(f);
+  };
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < total_octets; i += 4 * stride) {
+    uint4 vx[4], vr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vx[u] = __ldg(x + i + u * stride);
+      vr[u] = res ? __ldg(res + i + u * stride) : zero;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(i + u * stride, vx[u], vr[u]);
   }
+  for (; i < total_octets; i += stride) one(i, __ldg(x + i), res ? __ldg(res + i) : zero);
 }
+
+struct BwdPack {
+  uint4 x, g, a;
+};
+struct BwdReduceOp {
+  const uint4* x;
+  const uint4* act;
+  const uint4* dy;
+  const float* mean_invstd;
+  int octets, C;
+  __device__ __forceinline__ BwdPack load(long long row, int o) const {
+    BwdPack p;
+    p.x = __ldg(x + row * octets + o);
+    p.g = __ldg(dy + row * octets + o);
+    p.a = act ? __ldg(act + row * octets + o) : make_uint4(0, 0, 0, 0);
+    return p;
+  }
+  __device__ __forceinline__ void accum(const BwdPack& p, int o, float (&acc)[2][8]) const {
+    float fx[8], fg[8], fa[8];
+    unpack8(p.x, fx);
+    unpack8(p.g, fg);
+    unpack8(p.a, fa);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float g = (act && !(fa[e] > 0.f)) ? 0.f : fg[e];
+      const float xhat = (fx[e] - __ldg(mean_invstd + o * 8 + e)) * __ldg(mean_invstd + C + o * 8 + e);
+      acc[0][e] += g;
+      acc[1][e] = fmaf(g, xhat, acc[1][e]);
+    }
+  }
+};
 
 // dsums[0][c] = sum g, dsums[1][c] = sum g * xhat, with g = dy * (act > 0) when the forward applied ReLU.
 // bytes: M*C*2 * (2 or 3) read
@@ -179,20 +241,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const uint4* __
                                                                  const uint4* __restrict__ dy, long long M, int C,
                                                                  const float* __restrict__ mean_invstd,
                                                                  float* __restrict__ dsums) {
-  const int octets = C / 8;
-  reduce_rows<2>(M, C, dsums, [&](long long row, int o, float (&acc)[2][8]) {
-    float fx[8], fg[8], fa[8];
-    unpack8(__ldg(x + row * octets + o), fx);
-    unpack8(__ldg(dy + row * octets + o), fg);
-    if (act) unpack8(__ldg(act + row * octets + o), fa);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float g = (act && !(fa[e] > 0.f)) ? 0.f : fg[e];
-      const float xhat = (fx[e] - __ldg(mean_invstd + o * 8 + e)) * __ldg(mean_invstd + C + o * 8 + e);
-      acc[0][e] += g;
-      acc[1][e] += g * xhat;
-    }
-  });
+  reduce_rows<2>(M, C, dsums, BwdReduceOp{x, act, dy, mean_invstd, C / 8, C});
 }
 
 // dx = gamma*invstd * (g - dbeta/M - xhat * dgamma/M) (+ extra);  optionally dres = g (masked dy).
@@ -219,13 +268,15 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const uint4* __r
   for (int c = threadIdx.x; c < C; c += blockDim.x) dg_over_m[c] = dsums[C + c] * inv_m;
   __syncthreads();
   const int octets = C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_octets; i += (long long)gridDim.x * blockDim.x) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  auto one = [&](long long i, const uint4& vx, const uint4& vg, const uint4& va, const uint4& ve) {
     const int c0 = (int)(i % octets) * 8;
     float fx[8], fg[8], fa[8], fe[8];
-    unpack8(__ldg(x + i), fx);
-    unpack8(__ldg(dy + i), fg);
-    if (act) unpack8(__ldg(act + i), fa);
-    if (extra) unpack8(__ldg(extra + i), fe);
+    unpack8(vx, fx);
+    unpack8(vg, fg);
+    unpack8(va, fa);
+    unpack8(ve, fe);
     float o[8], gm[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -239,7 +290,23 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const uint4* __r
     }
     dx[i] = pack8(o);
     if (dres) dres[i] = pack8(gm);
+  };
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < total_octets; i += 2 * stride) {
+    uint4 vx[2], vg[2], va[2], ve[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long k = i + u * stride;
+      vx[u] = __ldg(x + k);
+      vg[u] = __ldg(dy + k);
+      va[u] = act ? __ldg(act + k) : zero;
+      ve[u] = extra ? __ldg(extra + k) : zero;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) one(i + u * stride, vx[u], vg[u], va[u], ve[u]);
   }
+  for (; i < total_octets; i += stride)
+    one(i, __ldg(x + i), __ldg(dy + i), act ? __ldg(act + i) : zero, extra ? __ldg(extra + i) : zero);
 }
 
 // feat[n][c] = mean over HW rows of a[n, :, c]  (fp32 out).      bytes: N*HW*C*2 read
@@ -406,7 +473,7 @@ int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* ga
   NBDT_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st));
   const int octets = C / 8;
   const int R = std::max(1, kThreads / octets);
-  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 4));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 8));
   const size_t smem = R > 1 ? (size_t)R * 2 * C * sizeof(float) : 0;
   bn_stats_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint4*>(x), M, C, sums);
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, M, C, c_real, gamma, beta, running_mean, running_var,
@@ -449,7 +516,7 @@ int nbdt_bn_backward(const void* x, const void* act, const void* dy, const void*
   NBDT_CUDA_OK(cudaMemsetAsync(dsums, 0, 2 * C * sizeof(float), st));
   const int octets = C / 8;
   const int R = std::max(1, kThreads / octets);
-  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 4));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 8));
   const size_t smem = R > 1 ? (size_t)R * 2 * C * sizeof(float) : 0;
   bn_bwd_reduce_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(act),
                                                      reinterpret_cast<const uint4*>(dy), M, C, mean_invstd, dsums);

@@ -64,7 +64,7 @@ struct TapGemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CLUSTER>
 __global__ void __launch_bounds__(192, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
                 const __grid_constant__ CUtensorMap tm_in2, const __grid_constant__ CUtensorMap tm_in3,
@@ -82,16 +82,20 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  // CLUSTER == 2: two CTAs work on adjacent M tiles of the same N tile and share the weight (B) tile:
+  // each loads half of its rows and TMA-multicasts them into both CTAs' shared memory (halves B's L2 traffic).
+  const int m_tiles = (p.tiles_w * p.tiles_h * p.tiles_n + CLUSTER - 1) / CLUSTER;  // per cluster: groups of CLUSTER m tiles
   const int total_tiles = m_tiles * p.n_tiles;
   const int iters = p.num_taps * p.kblocks;
+  const uint32_t cta_rank = CLUSTER > 1 ? cluster_ctarank() : 0;
+  const int first_tile = blockIdx.x / CLUSTER, tile_step = gridDim.x / CLUSTER;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_in0);
     prefetch_tmap(&tm_w);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), 1);
+      mbar_init(smem_u32(&empty[s]), CLUSTER);  // every CTA that received the multicast must release the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full[a]), 1);
@@ -105,6 +109,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync();  // the peer's barriers must exist before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -113,9 +118,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int n_tile = tile % p.n_tiles;
-        int m = tile / p.n_tiles;
+        int m = (tile / p.n_tiles) * CLUSTER + cta_rank;
         const int w0 = (m % p.tiles_w) * p.box_w;
         m /= p.tiles_w;
         const int h0 = (m % p.tiles_h) * p.box_h;
@@ -131,7 +136,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
             const uint32_t bar = smem_u32(&full[stage]);
             mbar_expect_tx(bar, Cfg::kStageBytes);
             tma_load_4d(a_dst, tm, bar, kb * kBlockK, cw, ch, n0);
-            tma_load_2d(b_dst, &tm_w, bar, kb * kBlockK, wrow);
+            if (CLUSTER == 1) {
+              tma_load_2d(b_dst, &tm_w, bar, kb * kBlockK, wrow);
+            } else {
+              constexpr int kHalfRows = BLOCK_N / CLUSTER;
+              tma_load_2d_mcast(b_dst + cta_rank * (kHalfRows * kBlockK * 2), &tm_w, bar, kb * kBlockK,
+                                wrow + cta_rank * kHalfRows, (uint16_t)((1u << CLUSTER) - 1));
+            }
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -145,7 +156,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -161,7 +172,8 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
             // +32 bytes (= 2 in descriptor units) per K=16 step inside the 128-byte swizzle row
             umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(smem_u32(&empty[stage]));
+          if (CLUSTER == 1) umma_commit(smem_u32(&empty[stage]));
+          else umma_commit_mcast(smem_u32(&empty[stage]), (uint16_t)((1u << CLUSTER) - 1));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(&tmem_full[acc]));
@@ -175,9 +187,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int n_tile = tile % p.n_tiles;
-      int m = tile / p.n_tiles;
+      int m = (tile / p.n_tiles) * CLUSTER + cta_rank;
       const int w0 = (m % p.tiles_w) * p.box_w;
       m /= p.tiles_w;
       const int h0 = (m % p.tiles_h) * p.box_h;
@@ -235,6 +247,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync();  // do not exit while the peer may still multicast into this CTA / signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -337,27 +350,42 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
     NBDT_REQUIRE(src.C == Cin, "view %d has %d channels, expected %d", v, src.C, Cin);
     if (int rc = view_tmap(&tm_in[v], src, p.box_w, p.box_h, p.box_n)) return rc;
   }
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)w_rows};
-    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
-    if (int rc = make_tmap(&tm_w, wpack, 2, dims, strides, box)) return rc;
-  }
   int dev = 0;
   NBDT_CUDA_OK(cudaGetDevice(&dev));
   nbdt::DeviceInfo info;
   if (int rc = nbdt::device_info(dev, &info)) return rc;
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
-  const int grid = std::min(total_tiles, info.sm_count);
-#define NBDT_LAUNCH_TAP(BN)                                                                                     \
-  {                                                                                                             \
-    auto kern = tap_gemm_kernel<BN>;                                                                            \
-    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmCfg<BN>::kSmemBytes)); \
-    kern<<<grid, 192, TapGemmCfg<BN>::kSmemBytes, stream>>>(tm_in[0], tm_in[1], tm_in[2], tm_in[3], tm_w, p);   \
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  static const int cluster_env = getenv("NBDT_B200_CONV_CLUSTER") ? atoi(getenv("NBDT_B200_CONV_CLUSTER")) : 2;
+  const int cluster = (cluster_env >= 2 && m_tiles >= 2) ? 2 : 1;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)w_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(block_n / cluster)};
+    if (int rc = make_tmap(&tm_w, wpack, 2, dims, strides, box)) return rc;
   }
-  if (block_n == 160) NBDT_LAUNCH_TAP(160)
-  else if (block_n == 128) NBDT_LAUNCH_TAP(128)
-  else NBDT_LAUNCH_TAP(64)
+  const int groups = ((m_tiles + cluster - 1) / cluster) * p.n_tiles;
+  const int grid = std::min(groups, info.sm_count / cluster) * cluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(192);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define NBDT_LAUNCH_TAP(BN, CL)                                                                                 \
+  {                                                                                                             \
+    auto kern = tap_gemm_kernel<BN, CL>;                                                                        \
+    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmCfg<BN>::kSmemBytes)); \
+    cfg.dynamicSmemBytes = TapGemmCfg<BN>::kSmemBytes;                                                          \
+    NBDT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_in[0], tm_in[1], tm_in[2], tm_in[3], tm_w, p));              \
+  }
+  if (block_n == 160) { if (cluster == 2) NBDT_LAUNCH_TAP(160, 2) else NBDT_LAUNCH_TAP(160, 1) }
+  else if (block_n == 128) { if (cluster == 2) NBDT_LAUNCH_TAP(128, 2) else NBDT_LAUNCH_TAP(128, 1) }
+  else { if (cluster == 2) NBDT_LAUNCH_TAP(64, 2) else NBDT_LAUNCH_TAP(64, 1) }
 #undef NBDT_LAUNCH_TAP
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
@@ -394,7 +422,8 @@ View4 parity_view(const void* base, int N, int H, int W, int C, int ph, int pw) 
 constexpr int kWgPix = 64;  // pixels per k-block
 
 struct WgradParams {
-  int num_taps, m_tiles, n_tiles, splits;
+  int num_taps, m_tiles, n_tiles;
+  long long units_per_cta;     // stream-K: every CTA gets the same number of (item, pixel-block) units
   int pix_blocks;              // total 64-pixel blocks = tiles_w * tiles_h * tiles_n
   int tiles_w, tiles_h;        // pixel-block grid inside one image (box_n images per block when the image is small)
   int box_w, box_h, box_n;
@@ -411,7 +440,7 @@ struct WgradCfg {
   static constexpr int kAChunks = 2;                               // M = 128 channels of dy
   static constexpr int kBChunks = (BLOCK_N + 63) / 64;
   static constexpr int kStageBytes = (kAChunks + kBChunks) * kChunkBytes;
-  static constexpr int kStages = (190 * 1024) / kStageBytes > 8 ? 8 : (190 * 1024) / kStageBytes;
+  static constexpr int kStages = (208 * 1024) / kStageBytes > 8 ? 8 : (208 * 1024) / kStageBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
@@ -433,7 +462,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_items = p.num_taps * p.m_tiles * p.n_tiles * p.splits;
+  const int total_items = p.num_taps * p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_dy);
@@ -457,26 +486,30 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  // item -> (split, n_tile, m_tile, tap); split fastest so concurrently running CTAs share operand tiles in L2
-  auto decode = [&](int item, int& tap, int& m_tile, int& n_tile, int& kb0, int& kb1) {
-    const int split = item % p.splits;
-    item /= p.splits;
+  // Stream-K: the (item, pixel-block) space is cut into gridDim.x equal contiguous ranges, so every CTA
+  // does the same number of k-blocks; a CTA emits one epilogue per item segment it touches.
+  // item -> (n_tile, m_tile, tap), n fastest.
+  const long long total_units = (long long)total_items * p.pix_blocks;
+  const long long u_begin = min((long long)blockIdx.x * p.units_per_cta, total_units);
+  const long long u_end = min(u_begin + p.units_per_cta, total_units);
+  auto decode = [&](long long u, int& tap, int& m_tile, int& n_tile, int& kb0, int& kb1) {
+    int item = (int)(u / p.pix_blocks);
+    kb0 = (int)(u - (long long)item * p.pix_blocks);
+    kb1 = (int)min((long long)p.pix_blocks, kb0 + (u_end - u));
     n_tile = item % p.n_tiles;
     item /= p.n_tiles;
     m_tile = item % p.m_tiles;
     tap = item / p.m_tiles;
-    const int per = (p.pix_blocks + p.splits - 1) / p.splits;
-    kb0 = split * per;
-    kb1 = min(kb0 + per, p.pix_blocks);
   };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (long long u = u_begin; u < u_end;) {
         int tap, m_tile, n_tile, kb0, kb1;
-        decode(item, tap, m_tile, n_tile, kb0, kb1);
+        decode(u, tap, m_tile, n_tile, kb0, kb1);
+        u += kb1 - kb0;
         const CUtensorMap* tmx = p.tap_map[tap] == 0 ? &tm_x0 : (p.tap_map[tap] == 1 ? &tm_x1 : (p.tap_map[tap] == 2 ? &tm_x2 : &tm_x3));
         for (int kb = kb0; kb < kb1; ++kb) {
           int b = kb;
@@ -506,9 +539,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (long long u = u_begin; u < u_end;) {
         int tap, m_tile, n_tile, kb0, kb1;
-        decode(item, tap, m_tile, n_tile, kb0, kb1);
+        decode(u, tap, m_tile, n_tile, kb0, kb1);
+        u += kb1 - kb0;
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -536,9 +570,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    for (long long u = u_begin; u < u_end;) {
       int tap, m_tile, n_tile, kb0, kb1;
-      decode(item, tap, m_tile, n_tile, kb0, kb1);
+      decode(u, tap, m_tile, n_tile, kb0, kb1);
+      u += kb1 - kb0;
       const int co = m_tile * kBlockM + row;
       float* dst = p.dw + ((long long)tap * p.Cout + co) * p.Cin + n_tile * BLOCK_N;
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
@@ -742,7 +777,9 @@ int nbdt_conv2d_wgrad(const void* x, const void* dy, float* dwp, int N, int H, i
   nbdt::DeviceInfo info;
   if (int rc = nbdt::device_info(dev, &info)) return rc;
   const int base_items = taps * p.m_tiles * p.n_tiles;
-  p.splits = std::max(1, std::min(p.pix_blocks, (2 * info.sm_count + base_items - 1) / base_items));
+  const long long total_units = (long long)base_items * p.pix_blocks;
+  const int grid = (int)std::min<long long>(total_units, info.sm_count);
+  p.units_per_cta = (total_units + grid - 1) / grid;
   CUtensorMap tm_dy, tm_x[4];
   {
     View4 dyv = dense_view(dy, N, Ho, Wo, Cout);
@@ -753,8 +790,6 @@ int nbdt_conv2d_wgrad(const void* x, const void* dy, float* dwp, int N, int H, i
   }
   for (int v = 0; v < 4; ++v)
     if (int rc = view_tmap(&tm_x[v], xviews[v < nv ? v : 0], p.box_w, p.box_h, p.box_n)) return rc;
-  const int total_items = base_items * p.splits;
-  const int grid = std::min(total_items, info.sm_count);
 #define NBDT_LAUNCH_WG(BN)                                                                                      \
   {                                                                                                             \
     auto kern = wgrad_kernel<BN>;                                                                               \

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "common.h"
+#include "tree_spec.h"
 
 namespace {
 
@@ -423,9 +424,45 @@ struct nbdt_tree {
   int sm_count;
   int max_smem;
   int force_g;  // env NBDT_B200_TREE_G (0 = heuristic)
+  const SpecEntry* spec;  // hierarchy-specialised straight-line kernels, when generated for this tree
 };
 
 namespace {
+
+unsigned long long tree_hash(const nbdt_tree_desc* d) {
+  unsigned long long h = 0xCBF29CE484222325ull;
+  auto mix = [&](int v) {
+    for (int b = 0; b < 4; ++b) {
+      h ^= (unsigned long long)((v >> (8 * b)) & 0xFF);
+      h *= 0x100000001B3ull;
+    }
+  };
+  mix(d->num_classes); mix(d->num_inodes); mix(d->root);
+  for (int i = 0; i <= d->num_inodes; ++i) mix(d->child_ptr[i]);
+  for (int i = 0; i < d->child_ptr[d->num_inodes]; ++i) mix(d->child_node[i]);
+  return h;
+}
+
+// Launch the specialised kernel if one exists for this tree/mode/dtype and the rows are aligned for its
+// vector width.  Returns -1 when the generic kernel must be used.
+int try_launch_spec(const nbdt_tree* t, int spec_mode, int dtype, const Params& p, cudaStream_t stream) {
+  if (!t->spec || t->force_g || dtype < 0 || dtype > 2) return -1;
+  const int esz = dtype == NBDT_F32 ? 4 : 2;
+  const int row_bytes = t->dev.C * esz;
+  const int vec = row_bytes % 16 == 0 ? 16 : (row_bytes % 8 == 0 ? 8 : (row_bytes % 4 == 0 ? 4 : esz));
+  auto aligned = [&](const void* ptr) { return ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) % vec) == 0; };
+  if (!aligned(p.x) || !aligned(p.grad) || (p.ld * esz) % vec != 0) return -1;
+  if (spec_mode == kSpecSoftFwd && (reinterpret_cast<uintptr_t>(p.class_probs) % 16) != 0) return -1;
+  SpecParams sp;
+  sp.x = p.x; sp.B = p.B; sp.ld = p.ld; sp.targets = p.targets; sp.class_probs = p.class_probs; sp.loss = p.loss;
+  sp.grad = p.grad; sp.w_xent = p.w_xent; sp.w_tree = p.w_tree; sp.inv_rows = p.inv_rows; sp.grad_scale = p.grad_scale;
+  const void* fn = t->spec->fn[spec_mode][dtype];
+  long long grid = (p.B + 127) / 128;
+  grid = std::min<long long>(grid, (long long)t->sm_count * 12);
+  void* args[1] = {&sp};
+  NBDT_CUDA_OK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(128), args, 0, stream));
+  return NBDT_OK;
+}
 
 int pick_group(const nbdt_tree* t) {
   if (t->force_g) return t->force_g;
@@ -478,7 +515,14 @@ int launch(const nbdt_tree* t, int dtype, const Params& p, cudaStream_t stream) 
   int cur = -1;
   NBDT_CUDA_OK(cudaGetDevice(&cur));
   if (cur != t->device) NBDT_CUDA_OK(cudaSetDevice(t->device));
-  int rc;
+  int rc = -1;
+  if (MODE == kSoftLoss) rc = try_launch_spec(t, kSpecSoftLoss, dtype, p, stream);
+  if (MODE == kHardLoss) rc = try_launch_spec(t, kSpecHardLoss, dtype, p, stream);
+  if (MODE == kSoftFwd) rc = try_launch_spec(t, kSpecSoftFwd, dtype, p, stream);
+  if (rc >= 0) {
+    if (cur != t->device) cudaSetDevice(cur);
+    return rc;
+  }
   switch (dtype) {
     case NBDT_F32: rc = launch_t<MODE, float>(t, p, stream); break;
     case NBDT_BF16: rc = launch_t<MODE, __nv_bfloat16>(t, p, stream); break;
@@ -604,6 +648,12 @@ int nbdt_tree_create(const nbdt_tree_desc* d, int device, nbdt_tree** out) {
   t->sm_count = info.sm_count;
   t->max_smem = info.max_smem_optin;
   t->force_g = 0;
+  t->spec = nullptr;
+  if (!getenv("NBDT_B200_TREE_GENERIC")) {
+    const unsigned long long h = tree_hash(d);
+    for (int i = 0; i < kSpecCount; ++i)
+      if (kSpecTable[i].hash == h && kSpecTable[i].C == C) t->spec = &kSpecTable[i];
+  }
   if (const char* env = getenv("NBDT_B200_TREE_G")) {
     const int g = atoi(env);
     if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) t->force_g = g;

@@ -8,6 +8,26 @@ from . import lib as L
 from .ops import _count, _p
 
 
+PROFILE = None  # bench.py sets this to a list to collect (kind, flops, start_event, end_event) per conv launch
+
+
+class _timed:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            PROFILE.append((self.kind, self.flops, self.start, end))
+
+
 def pad64(c):
     return (c + 63) // 64 * 64
 
@@ -42,7 +62,8 @@ def conv_fwd(x, wp, ksize, stride, residual=None):
     if residual is not None:
         _check_act(residual, "conv_fwd residual")
         assert residual.shape == y.shape
-    with torch.cuda.device(x.device):
+    flops = 2.0 * y.numel() * cin * ksize * ksize
+    with torch.cuda.device(x.device), _timed("fwd", flops):
         L.check(L.load().nbdt_conv2d_fwd(_p(x), _p(wp), _p(y), _p(residual), N, H, W, cin, cout, ksize, stride,
                                          L.stream_ptr(x.device)))
     _count()
@@ -61,7 +82,8 @@ def conv_dgrad(dy, wpt, in_hw, ksize, stride, accumulate=None):
     if accumulate is not None:
         _check_act(accumulate, "conv_dgrad accumulate")
         assert accumulate.shape == (N, H, W, cin)
-    with torch.cuda.device(dy.device):
+    flops = 2.0 * dy.numel() * cin * ksize * ksize
+    with torch.cuda.device(dy.device), _timed("dgrad", flops):
         L.check(L.load().nbdt_conv2d_dgrad(_p(dy), _p(wpt), _p(dx), _p(accumulate), N, H, W, cin, cout, ksize, stride,
                                            L.stream_ptr(dy.device)))
     _count(4 if stride == 2 else 1)
@@ -76,7 +98,8 @@ def conv_wgrad(x, dy, ksize, stride):
     cout = dy.shape[3]
     assert dy.shape == (N, H // stride, W // stride, cout)
     dwp = torch.empty((ksize * ksize, cout, cin), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    flops = 2.0 * dy.numel() * cin * ksize * ksize
+    with torch.cuda.device(x.device), _timed("wgrad", flops):
         L.check(L.load().nbdt_conv2d_wgrad(_p(x), _p(dy), _p(dwp), N, H, W, cin, cout, ksize, stride,
                                            L.stream_ptr(x.device)))
     _count()

@@ -60,6 +60,18 @@ class GradientAllReduce:
                 off += n
 
 
+class FlatGradientAllReduce:
+    """All-reduce(sum) of FusedSGD's flat gradient buffer: one NCCL call per step, no copies."""
+
+    def __init__(self, optimizer, world_size):
+        self.optimizer = optimizer
+        self.world_size = world_size
+
+    def reduce(self):
+        if self.world_size > 1:
+            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
+
+
 def shard_rows(total_rows, rank, world_size):
     """[begin, end) of this rank's rows of a global batch (remainder rows go to the low ranks)."""
     base, rem = divmod(total_rows, world_size)
