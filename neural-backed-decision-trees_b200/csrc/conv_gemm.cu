@@ -52,19 +52,25 @@ struct TapGemmParams {
   int tap_dh[kMaxTaps];
   int tap_dw[kMaxTaps];
   int tap_wrow[kMaxTaps];  // first row of this tap's [Cout x Cin] slice in the packed weight matrix
+  int exp;  // perf experiments only (env NBDT_B200_CONV_EXP): 1 skip B loads, 2 skip A loads, 4 skip stores, 8 one MMA per stage
 };
 
+// One pipeline stage holds kUnits consecutive (tap, 64-channel k-block) units: the MMA thread's per-stage
+// handshake (barrier probe, fence, commit ~ 160 cycles + ~32 cycles per tcgen05.mma issue, measured with
+// scripts/ubench_mma.cu) then sits under 8 MMAs = 640 tensor-pipe cycles instead of 4 = 320, which it exceeded.
 template <int BLOCK_N>
 struct TapGemmCfg {
+  static constexpr int kUnits = 2;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N <= 64) ? 8 : (BLOCK_N <= 128 ? 6 : 5);
+  static constexpr int kUnitBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = kUnits * kUnitBytes;
+  static constexpr int kStages = (216 * 1024) / kStageBytes > 6 ? 6 : (216 * 1024) / kStageBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, int CLUSTER>
+template <int BLOCK_N>
 __global__ void __launch_bounds__(192, 1)
 tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
                 const __grid_constant__ CUtensorMap tm_in2, const __grid_constant__ CUtensorMap tm_in3,
@@ -82,20 +88,15 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // CLUSTER == 2: two CTAs work on adjacent M tiles of the same N tile and share the weight (B) tile:
-  // each loads half of its rows and TMA-multicasts them into both CTAs' shared memory (halves B's L2 traffic).
-  const int m_tiles = (p.tiles_w * p.tiles_h * p.tiles_n + CLUSTER - 1) / CLUSTER;  // per cluster: groups of CLUSTER m tiles
-  const int total_tiles = m_tiles * p.n_tiles;
-  const int iters = p.num_taps * p.kblocks;
-  const uint32_t cta_rank = CLUSTER > 1 ? cluster_ctarank() : 0;
-  const int first_tile = blockIdx.x / CLUSTER, tile_step = gridDim.x / CLUSTER;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int units = p.num_taps * p.kblocks;  // (tap, k-block) units per tile, tap-major
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_in0);
     prefetch_tmap(&tm_w);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), CLUSTER);  // every CTA that received the multicast must release the stage
+      mbar_init(smem_u32(&empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full[a]), 1);
@@ -109,77 +110,96 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync();  // the peer's barriers must exist before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int n_tile = tile % p.n_tiles;
-        int m = (tile / p.n_tiles) * CLUSTER + cta_rank;
-        const int w0 = (m % p.tiles_w) * p.box_w;
-        m /= p.tiles_w;
-        const int h0 = (m % p.tiles_h) * p.box_h;
-        const int n0 = (m / p.tiles_h) * p.box_n;
-        for (int t = 0; t < p.num_taps; ++t) {
-          const CUtensorMap* tm = p.tap_map[t] == 0 ? &tm_in0 : (p.tap_map[t] == 1 ? &tm_in1 : (p.tap_map[t] == 2 ? &tm_in2 : &tm_in3));
-          const int cw = w0 + p.tap_dw[t], ch = h0 + p.tap_dh[t];
-          const int wrow = p.tap_wrow[t] + n_tile * BLOCK_N;
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
-            const uint32_t a_dst = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint32_t b_dst = a_dst + Cfg::kABytes;
-            const uint32_t bar = smem_u32(&full[stage]);
-            mbar_expect_tx(bar, Cfg::kStageBytes);
-            tma_load_4d(a_dst, tm, bar, kb * kBlockK, cw, ch, n0);
-            if (CLUSTER == 1) {
-              tma_load_2d(b_dst, &tm_w, bar, kb * kBlockK, wrow);
-            } else {
-              constexpr int kHalfRows = BLOCK_N / CLUSTER;
-              tma_load_2d_mcast(b_dst + cta_rank * (kHalfRows * kBlockK * 2), &tm_w, bar, kb * kBlockK,
-                                wrow + cta_rank * kHalfRows, (uint16_t)((1u << CLUSTER) - 1));
+    // The whole warp runs the loop (warp-uniform control flow keeps descriptors / coordinates in uniform
+    // registers); only the elected lane issues.  A loop under `if (lane == 0)` costs one R2UR per operand
+    // per instruction and made TMA / MMA issue the bottleneck (profiles/r01_conv_issue_experiments.md).
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m = tile / p.n_tiles;
+      const int w0 = (m % p.tiles_w) * p.box_w;
+      m /= p.tiles_w;
+      const int h0 = (m % p.tiles_h) * p.box_h;
+      const int n0 = (m / p.tiles_h) * p.box_n;
+      int t = 0, kb = 0;
+      for (int u = 0; u < units; u += Cfg::kUnits) {
+        const int nu = min(Cfg::kUnits, units - u);
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t bar = full0 + 8 * stage;
+        const uint32_t dst = smem_base + stage * Cfg::kStageBytes;
+        if (leader) mbar_expect_tx(bar, nu * Cfg::kUnitBytes);
+#pragma unroll
+        for (int j = 0; j < Cfg::kUnits; ++j) {
+          if (j < nu) {
+            const int map = p.tap_map[t];
+            const CUtensorMap* tm = map == 0 ? &tm_in0 : (map == 1 ? &tm_in1 : (map == 2 ? &tm_in2 : &tm_in3));
+            if (leader) {
+              tma_load_4d(dst + j * Cfg::kUnitBytes, tm, bar, kb * kBlockK, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n0);
+              tma_load_2d(dst + j * Cfg::kUnitBytes + Cfg::kABytes, &tm_w, bar, kb * kBlockK,
+                          p.tap_wrow[t] + n_tile * BLOCK_N);
             }
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            if (++kb == p.kblocks) { kb = 0; ++t; }
           }
         }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+    // ===================== MMA issuer (warp-uniform loop, elected lane issues) =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    // descriptors differ between stages / units / k-steps only in the 14-bit start-address field (low word)
+    const uint64_t desc0 = make_smem_desc(smem_base, 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      int kb = 0;
+      uint32_t accumulate = 0;
+      for (int u = 0; u < units; u += Cfg::kUnits) {
+        const int nu = min(Cfg::kUnits, units - u);
+        mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(smem_u32(&full[stage]), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(a_addr + Cfg::kABytes, 16, 1024);
-          // channels past Cin in the last k-block are TMA zero fill; do not spend MMAs on them
-          const int ksteps = ((it + 1) % p.kblocks == 0) ? p.last_ksteps : kBlockK / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            // +32 bytes (= 2 in descriptor units) per K=16 step inside the 128-byte swizzle row
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        const uint64_t sdesc = desc0 + (uint64_t)((stage * Cfg::kStageBytes) >> 4);
+#pragma unroll
+        for (int j = 0; j < Cfg::kUnits; ++j) {
+          if (j < nu) {
+            // channels past Cin in a tap's last k-block are TMA zero fill; do not spend MMAs on them
+            const int ksteps = (p.exp & 8) ? 1 : ((kb == p.kblocks - 1) ? p.last_ksteps : kBlockK / 16);
+            const uint64_t adesc = sdesc + (uint64_t)((j * Cfg::kUnitBytes) >> 4);
+            const uint64_t bdesc = adesc + (uint64_t)(Cfg::kABytes >> 4);
+            if (leader) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // +32 bytes (= 2 in descriptor units) per K=16 step inside the 128-byte swizzle row
+                if (k < ksteps) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            accumulate = 1;
+            if (++kb == p.kblocks) kb = 0;
           }
-          if (CLUSTER == 1) umma_commit(smem_u32(&empty[stage]));
-          else umma_commit_mcast(smem_u32(&empty[stage]), (uint16_t)((1u << CLUSTER) - 1));
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&tmem_full[acc]));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (leader) umma_commit(empty0 + 8 * stage);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(smem_u32(&tmem_full[acc]));
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -187,9 +207,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
-      int m = (tile / p.n_tiles) * CLUSTER + cta_rank;
+      int m = tile / p.n_tiles;
       const int w0 = (m % p.tiles_w) * p.box_w;
       m /= p.tiles_w;
       const int h0 = (m % p.tiles_h) * p.box_h;
@@ -198,7 +218,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
       const int pw = w0 + row % p.box_w;
       const int ph = h0 + (row / p.box_w) % p.box_h;
       const int pn = n0 + row / (p.box_w * p.box_h);
-      const bool in_range = pw < p.W_out && ph < p.H_out && pn < p.N_img;
+      const bool in_range = pw < p.W_out && ph < p.H_out && pn < p.N_img && !(p.exp & 4);
       const long long off = pn * p.out_sn + ph * p.out_sh + pw * p.out_sw + (long long)n_tile * BLOCK_N;
 
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
@@ -247,7 +267,6 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync();  // do not exit while the peer may still multicast into this CTA / signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -341,6 +360,7 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
   p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
   p.out = const_cast<__nv_bfloat16*>(out.base);
   p.residual = residual;
+  p.exp = getenv("NBDT_B200_CONV_EXP") ? atoi(getenv("NBDT_B200_CONV_EXP")) : 0;
   for (int t = 0; t < num_taps; ++t) {
     p.tap_map[t] = taps[t].map; p.tap_dh[t] = taps[t].dh; p.tap_dw[t] = taps[t].dw; p.tap_wrow[t] = taps[t].wrow;
   }
@@ -354,38 +374,23 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
   NBDT_CUDA_OK(cudaGetDevice(&dev));
   nbdt::DeviceInfo info;
   if (int rc = nbdt::device_info(dev, &info)) return rc;
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  static const int cluster_env = getenv("NBDT_B200_CONV_CLUSTER") ? atoi(getenv("NBDT_B200_CONV_CLUSTER")) : 2;
-  const int cluster = (cluster_env >= 2 && m_tiles >= 2) ? 2 : 1;
   {
     cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)w_rows};
     cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(block_n / cluster)};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
     if (int rc = make_tmap(&tm_w, wpack, 2, dims, strides, box)) return rc;
   }
-  const int groups = ((m_tiles + cluster - 1) / cluster) * p.n_tiles;
-  const int grid = std::min(groups, info.sm_count / cluster) * cluster;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(192);
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cluster;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-#define NBDT_LAUNCH_TAP(BN, CL)                                                                                 \
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int grid = std::min(total_tiles, info.sm_count);
+#define NBDT_LAUNCH_TAP(BN)                                                                                     \
   {                                                                                                             \
-    auto kern = tap_gemm_kernel<BN, CL>;                                                                        \
+    auto kern = tap_gemm_kernel<BN>;                                                                            \
     NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemmCfg<BN>::kSmemBytes)); \
-    cfg.dynamicSmemBytes = TapGemmCfg<BN>::kSmemBytes;                                                          \
-    NBDT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tm_in[0], tm_in[1], tm_in[2], tm_in[3], tm_w, p));              \
+    kern<<<grid, 192, TapGemmCfg<BN>::kSmemBytes, stream>>>(tm_in[0], tm_in[1], tm_in[2], tm_in[3], tm_w, p);   \
   }
-  if (block_n == 160) { if (cluster == 2) NBDT_LAUNCH_TAP(160, 2) else NBDT_LAUNCH_TAP(160, 1) }
-  else if (block_n == 128) { if (cluster == 2) NBDT_LAUNCH_TAP(128, 2) else NBDT_LAUNCH_TAP(128, 1) }
-  else { if (cluster == 2) NBDT_LAUNCH_TAP(64, 2) else NBDT_LAUNCH_TAP(64, 1) }
+  if (block_n == 160) NBDT_LAUNCH_TAP(160)
+  else if (block_n == 128) NBDT_LAUNCH_TAP(128)
+  else NBDT_LAUNCH_TAP(64)
 #undef NBDT_LAUNCH_TAP
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
@@ -419,38 +424,43 @@ View4 parity_view(const void* base, int N, int H, int W, int C, int ph, int pw) 
 // Work item = (tap, 128-row Cout tile, Cin tile, K split); fp32 partial sums are reduced into
 // dW[tap][Cout][Cin] with red.global.add.f32 (dW must be zeroed by the caller).
 // =============================================================================================
-constexpr int kWgPix = 64;  // pixels per k-block
-
 struct WgradParams {
-  int num_taps, m_tiles, n_tiles;
-  long long units_per_cta;     // stream-K: every CTA gets the same number of (item, pixel-block) units
-  int pix_blocks;              // total 64-pixel blocks = tiles_w * tiles_h * tiles_n
-  int tiles_w, tiles_h;        // pixel-block grid inside one image (box_n images per block when the image is small)
+  int tap_groups, m_tiles, n_tiles;  // work item = (tap group, Cout tile, Cin tile)
+  long long units_per_cta;           // stream-K: every CTA gets the same number of (item, pixel-block) units
+  int pix_blocks;                    // total KPIX-pixel blocks = tiles_w * tiles_h * tiles_n
+  int tiles_w, tiles_h;              // pixel-block grid inside one image (box_n images per block when the image is small)
   int box_w, box_h, box_n;
   int Cout, Cin;
-  float* dw;                   // [taps][Cout][Cin] fp32
+  float* dw;                         // [taps][Cout][Cin] fp32
   int tap_map[kMaxTaps];
   int tap_dh[kMaxTaps];
   int tap_dw[kMaxTaps];
 };
 
-template <int BLOCK_N>
+// TAPS taps that share the dy tile are accumulated side by side in TMEM (TAPS x BLOCK_N columns), so one
+// stage = 1 dy tile + TAPS shifted x tiles carries TAPS * KPIX/16 MMAs per barrier handshake.
+template <int BLOCK_N, int TAPS, int KPIX>
 struct WgradCfg {
-  static constexpr int kChunkBytes = kWgPix * 128;                 // 64 pixels x 64 channels bf16
+  static constexpr int kChunkBytes = KPIX * 128;                   // KPIX pixels x 64 channels bf16
   static constexpr int kAChunks = 2;                               // M = 128 channels of dy
   static constexpr int kBChunks = (BLOCK_N + 63) / 64;
-  static constexpr int kStageBytes = (kAChunks + kBChunks) * kChunkBytes;
+  static constexpr int kTapBytes = kBChunks * kChunkBytes;
+  static constexpr int kStageBytes = kAChunks * kChunkBytes + TAPS * kTapBytes;
   static constexpr int kStages = (208 * 1024) / kStageBytes > 8 ? 8 : (208 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int kAccCols = TAPS * BLOCK_N;
+  static constexpr int kNumAcc = (2 * kAccCols <= 512) ? 2 : 1;    // double-buffer the accumulators when they fit
+  static constexpr int kTmemCols = (kNumAcc * kAccCols <= 128) ? 128 : (kNumAcc * kAccCols <= 256 ? 256 : 512);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(kAccCols <= 512, "accumulators exceed TMEM");
+  static_assert(kStages >= 2, "stage too large");
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1)
+template <int BLOCK_N, int TAPS, int KPIX>
+__global__ void __launch_bounds__(224, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x0,
              const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
              const __grid_constant__ CUtensorMap tm_x3, const WgradParams p) {
-  using Cfg = WgradCfg<BLOCK_N>;
+  using Cfg = WgradCfg<BLOCK_N, TAPS, KPIX>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -462,7 +472,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_items = p.num_taps * p.m_tiles * p.n_tiles;
+  const int total_items = p.tap_groups * p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_dy);
@@ -485,105 +495,130 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
 
   // Stream-K: the (item, pixel-block) space is cut into gridDim.x equal contiguous ranges, so every CTA
   // does the same number of k-blocks; a CTA emits one epilogue per item segment it touches.
-  // item -> (n_tile, m_tile, tap), n fastest.
+  // item -> (n_tile, m_tile, tap group), n fastest.
   const long long total_units = (long long)total_items * p.pix_blocks;
   const long long u_begin = min((long long)blockIdx.x * p.units_per_cta, total_units);
   const long long u_end = min(u_begin + p.units_per_cta, total_units);
-  auto decode = [&](long long u, int& tap, int& m_tile, int& n_tile, int& kb0, int& kb1) {
+  auto decode = [&](long long u, int& group, int& m_tile, int& n_tile, int& kb0, int& kb1) {
     int item = (int)(u / p.pix_blocks);
     kb0 = (int)(u - (long long)item * p.pix_blocks);
     kb1 = (int)min((long long)p.pix_blocks, kb0 + (u_end - u));
     n_tile = item % p.n_tiles;
     item /= p.n_tiles;
     m_tile = item % p.m_tiles;
-    tap = item / p.m_tiles;
+    group = item / p.m_tiles;
   };
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long u = u_begin; u < u_end;) {
-        int tap, m_tile, n_tile, kb0, kb1;
-        decode(u, tap, m_tile, n_tile, kb0, kb1);
-        u += kb1 - kb0;
-        const CUtensorMap* tmx = p.tap_map[tap] == 0 ? &tm_x0 : (p.tap_map[tap] == 1 ? &tm_x1 : (p.tap_map[tap] == 2 ? &tm_x2 : &tm_x3));
-        for (int kb = kb0; kb < kb1; ++kb) {
-          int b = kb;
-          const int w0 = (b % p.tiles_w) * p.box_w;
-          b /= p.tiles_w;
-          const int h0 = (b % p.tiles_h) * p.box_h;
-          const int n0 = (b / p.tiles_h) * p.box_n;
-          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
-          const uint32_t dst = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t bar = smem_u32(&full[stage]);
+  if (warp == 0 || warp == 6) {
+    // Two TMA-issuing warps (a stage is 2 + TAPS * kBChunks small boxes; one elected thread could not issue them
+    // within the stage's MMA time): warp 0 arms the barrier and loads dy + tap 0, warp 6 loads the other taps.
+    const bool leader = elect_one();
+    const bool first = warp == 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long u = u_begin; u < u_end;) {
+      int group, m_tile, n_tile, kb0, kb1;
+      decode(u, group, m_tile, n_tile, kb0, kb1);
+      u += kb1 - kb0;
+      if (!first && TAPS == 1) continue;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        int b = kb;
+        const int w0 = (b % p.tiles_w) * p.box_w;
+        b /= p.tiles_w;
+        const int h0 = (b % p.tiles_h) * p.box_h;
+        const int n0 = (b / p.tiles_h) * p.box_n;
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t dst = smem_base + stage * Cfg::kStageBytes;
+        const uint32_t bar = full0 + 8 * stage;
+        if (leader && first) {
           mbar_expect_tx(bar, Cfg::kStageBytes);
 #pragma unroll
           for (int c = 0; c < Cfg::kAChunks; ++c)
             tma_load_4d(dst + c * Cfg::kChunkBytes, &tm_dy, bar, m_tile * kBlockM + c * 64, w0, h0, n0);
-#pragma unroll
-          for (int c = 0; c < Cfg::kBChunks; ++c)
-            tma_load_4d(dst + (Cfg::kAChunks + c) * Cfg::kChunkBytes, tmx, bar, n_tile * BLOCK_N + c * 64,
-                        w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+#pragma unroll
+        for (int j = 0; j < TAPS; ++j) {
+          if ((j == 0) != first) continue;
+          const int tap = group * TAPS + j;
+          const int map = p.tap_map[tap];
+          const CUtensorMap* tmx = map == 0 ? &tm_x0 : (map == 1 ? &tm_x1 : (map == 2 ? &tm_x2 : &tm_x3));
+          if (leader) {
+#pragma unroll
+            for (int c = 0; c < Cfg::kBChunks; ++c)
+              tma_load_4d(dst + Cfg::kAChunks * Cfg::kChunkBytes + j * Cfg::kTapBytes + c * Cfg::kChunkBytes, tmx, bar,
+                          n_tile * BLOCK_N + c * 64, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0);
+          }
+        }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 1, 1);  // both operands MN-major
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (long long u = u_begin; u < u_end;) {
-        int tap, m_tile, n_tile, kb0, kb1;
-        decode(u, tap, m_tile, n_tile, kb0, kb1);
-        u += kb1 - kb0;
-        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 1, 1);  // both operands MN-major
+    // MN-major tiles: LBO = distance between 64-channel chunks, SBO = 1024 B between 8-pixel groups
+    const uint64_t desc0 = make_smem_desc(smem_base, Cfg::kChunkBytes, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int item_idx = 0;
+    for (long long u = u_begin; u < u_end; ++item_idx) {
+      int group, m_tile, n_tile, kb0, kb1;
+      decode(u, group, m_tile, n_tile, kb0, kb1);
+      u += kb1 - kb0;
+      const int acc = item_idx % Cfg::kNumAcc;
+      const uint32_t acc_phase = (item_idx / Cfg::kNumAcc) & 1;
+      mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols;
+      uint32_t accumulate = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(smem_u32(&full[stage]), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = make_smem_desc(a_addr, Cfg::kChunkBytes, 1024);
-          const uint64_t bdesc = make_smem_desc(a_addr + Cfg::kAChunks * Cfg::kChunkBytes, Cfg::kChunkBytes, 1024);
+        const uint64_t adesc = desc0 + (uint64_t)((stage * Cfg::kStageBytes) >> 4);
+        if (leader) {
 #pragma unroll
-          for (int k = 0; k < kWgPix / 16; ++k) {
-            // K=16 pixels = two 8-pixel swizzle atoms = 2048 bytes (128 descriptor units)
-            umma_bf16(tmem_d, adesc + 128 * k, bdesc + 128 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int j = 0; j < TAPS; ++j) {
+            const uint64_t bdesc = adesc + (uint64_t)((Cfg::kAChunks * Cfg::kChunkBytes + j * Cfg::kTapBytes) >> 4);
+#pragma unroll
+            for (int k = 0; k < KPIX / 16; ++k) {
+              // K=16 pixels = two 8-pixel swizzle atoms = 2048 bytes (128 descriptor units)
+              umma_bf16(tmem_d + j * BLOCK_N, adesc + 128 * k, bdesc + 128 * k, idesc, (k > 0) ? 1u : accumulate);
+            }
           }
-          umma_commit(smem_u32(&empty[stage]));
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          umma_commit(empty0 + 8 * stage);
         }
-        umma_commit(smem_u32(&tmem_full[acc]));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        accumulate = 1;
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(smem_u32(&tmem_full[acc]));
+      __syncwarp();
     }
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (long long u = u_begin; u < u_end;) {
-      int tap, m_tile, n_tile, kb0, kb1;
-      decode(u, tap, m_tile, n_tile, kb0, kb1);
+    int item_idx = 0;
+    for (long long u = u_begin; u < u_end; ++item_idx) {
+      int group, m_tile, n_tile, kb0, kb1;
+      decode(u, group, m_tile, n_tile, kb0, kb1);
       u += kb1 - kb0;
+      const int acc = item_idx % Cfg::kNumAcc;
+      const uint32_t acc_phase = (item_idx / Cfg::kNumAcc) & 1;
       const int co = m_tile * kBlockM + row;
-      float* dst = p.dw + ((long long)tap * p.Cout + co) * p.Cin + n_tile * BLOCK_N;
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
-      if (kb1 > kb0) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::kAccCols;
+#pragma unroll 1
+      for (int j = 0; j < TAPS; ++j) {
+        const int tap = group * TAPS + j;
+        float* dst = p.dw + ((long long)tap * p.Cout + co) * p.Cin + n_tile * BLOCK_N;
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           uint32_t v[32];
-          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_32x32(taddr + j * BLOCK_N + c0, v);
           tmem_ld_wait();
           if (co < p.Cout) {
 #pragma unroll
@@ -595,8 +630,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
@@ -755,18 +788,20 @@ int nbdt_conv2d_wgrad(const void* x, const void* dy, float* dwp, int N, int H, i
         p.tap_map[nt] = ph * 2 + pw; p.tap_dh[nt] = (rr - ph) / 2; p.tap_dw[nt] = (ss - pw) / 2; ++nt;
       }
   }
+  // 3x3: the three taps of one filter row share the dy tile (TAPS = 3, 32-pixel k-blocks); 1x1: TAPS = 1, 64 pixels
+  const int taps_per_group = taps == 9 ? 3 : 1;
+  const int kpix = taps == 9 ? 32 : 64;
   int block_n;
   if (Cin % 160 == 0) block_n = 160;
-  else if (Cin % 256 == 0) block_n = 256;
   else if (Cin % 128 == 0) block_n = 128;
   else if (Cin % 64 == 0) block_n = 64;
   else return nbdt::set_error(NBDT_EINVAL, "wgrad: input channels (%d) must be a multiple of 64", Cin);
-  p.num_taps = taps;
+  p.tap_groups = taps / taps_per_group;
   p.m_tiles = (Cout + kBlockM - 1) / kBlockM;
   p.n_tiles = Cin / block_n;
-  p.box_w = std::min(pow2_ceil(Wo), kWgPix);
-  p.box_h = std::min(pow2_ceil(Ho), kWgPix / p.box_w);
-  p.box_n = kWgPix / (p.box_w * p.box_h);
+  p.box_w = std::min(pow2_ceil(Wo), kpix);
+  p.box_h = std::min(pow2_ceil(Ho), kpix / p.box_w);
+  p.box_n = kpix / (p.box_w * p.box_h);
   p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
   p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
   const int tiles_n = (N + p.box_n - 1) / p.box_n;
@@ -776,7 +811,7 @@ int nbdt_conv2d_wgrad(const void* x, const void* dy, float* dwp, int N, int H, i
   NBDT_CUDA_OK(cudaGetDevice(&dev));
   nbdt::DeviceInfo info;
   if (int rc = nbdt::device_info(dev, &info)) return rc;
-  const int base_items = taps * p.m_tiles * p.n_tiles;
+  const int base_items = p.tap_groups * p.m_tiles * p.n_tiles;
   const long long total_units = (long long)base_items * p.pix_blocks;
   const int grid = (int)std::min<long long>(total_units, info.sm_count);
   p.units_per_cta = (total_units + grid - 1) / grid;
@@ -790,16 +825,21 @@ int nbdt_conv2d_wgrad(const void* x, const void* dy, float* dwp, int N, int H, i
   }
   for (int v = 0; v < 4; ++v)
     if (int rc = view_tmap(&tm_x[v], xviews[v < nv ? v : 0], p.box_w, p.box_h, p.box_n)) return rc;
-#define NBDT_LAUNCH_WG(BN)                                                                                      \
+#define NBDT_LAUNCH_WG(BN, TP, KP)                                                                              \
   {                                                                                                             \
-    auto kern = wgrad_kernel<BN>;                                                                               \
-    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<BN>::kSmemBytes)); \
-    kern<<<grid, 192, WgradCfg<BN>::kSmemBytes, st>>>(tm_dy, tm_x[0], tm_x[1], tm_x[2], tm_x[3], p);             \
+    auto kern = wgrad_kernel<BN, TP, KP>;                                                                       \
+    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<BN, TP, KP>::kSmemBytes)); \
+    kern<<<grid, 224, WgradCfg<BN, TP, KP>::kSmemBytes, st>>>(tm_dy, tm_x[0], tm_x[1], tm_x[2], tm_x[3], p);     \
   }
-  if (block_n == 160) NBDT_LAUNCH_WG(160)
-  else if (block_n == 256) NBDT_LAUNCH_WG(256)
-  else if (block_n == 128) NBDT_LAUNCH_WG(128)
-  else NBDT_LAUNCH_WG(64)
+  if (taps_per_group == 3) {
+    if (block_n == 160) NBDT_LAUNCH_WG(160, 3, 32)
+    else if (block_n == 128) NBDT_LAUNCH_WG(128, 3, 32)
+    else NBDT_LAUNCH_WG(64, 3, 32)
+  } else {
+    if (block_n == 160) NBDT_LAUNCH_WG(160, 1, 64)
+    else if (block_n == 128) NBDT_LAUNCH_WG(128, 1, 64)
+    else NBDT_LAUNCH_WG(64, 1, 64)
+  }
 #undef NBDT_LAUNCH_WG
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
