@@ -143,8 +143,10 @@ int nbdt_conv_unpack_wgrad(const float* dwp, float* dw_oihw, int Cout, int Cin, 
  * (nbdt/models/resnet.py:50-54,70-73,142; main.py:207,239).  c_real <= C marks zero-padded channels.
  * ------------------------------------------------------------------------------------------- */
 
+/* Floats the `sums` / `dsums` scratch buffers below must hold (per-CTA partial sums + the reduced [2][C]). */
+long long nbdt_bn_scratch_floats(int C);
 /* Training-mode batch statistics: mean_invstd[2][C], scale_shift[2][C] (y = x*scale + shift), running-stat
- * update with `momentum` (running_* may be NULL).  sums: [2][C] fp32 scratch. */
+ * update with `momentum` (running_* may be NULL).  sums: fp32 scratch of nbdt_bn_scratch_floats(C). */
 int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, float* sums,
                   float* mean_invstd, float* scale_shift, void* stream);
@@ -156,7 +158,7 @@ int nbdt_bn_apply(const void* x, const void* residual, void* y, long long M, int
                   int relu, void* stream);
 /* Backward of nbdt_bn_stats + nbdt_bn_apply.  act = the forward output when ReLU was applied (else NULL);
  * dx = gradient w.r.t. x (+ extra, may be NULL); dres (may be NULL) = gradient w.r.t. the residual;
- * dsums[2][C] receives (sum g, sum g*xhat) = (dbeta, dgamma). */
+ * dsums: fp32 buffer of nbdt_bn_scratch_floats(C); its first [2][C] receive (sum g, sum g*xhat) = (dbeta, dgamma). */
 int nbdt_bn_backward(const void* x, const void* act, const void* dy, const void* extra, void* dx, void* dres,
                      long long M, int C, int c_real, const float* gamma, const float* mean_invstd, float* dsums,
                      void* stream);

@@ -41,20 +41,24 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // Shared skeleton of the per-channel reductions: thread (r, o) owns channel octet o of rows
 // r, r + R, ... of this CTA's grid-stride share; NACC float accumulators per channel.  `Op` provides
-//   Pack load(row, o)            -- the global loads of one row (issued 4 rows at a time for memory-level parallelism)
+//   Pack load(row, o)            -- the global loads of one row (issued UNROLL rows at a time for memory-level parallelism)
 //   void accum(pack, o, acc)     -- the arithmetic
-template <int NACC, typename Op>
-__device__ __forceinline__ void reduce_rows(long long M, int C, float* __restrict__ out /*[NACC][C]*/, Op op) {
+// Each CTA writes its partial sums to out[blockIdx.x][NACC][C]; a tiny second kernel adds the partials in a fixed
+// order (deterministic, and no same-address atomics: with one atomic per channel per CTA the reduction kernels
+// took ~130 us regardless of tensor size, profiles/r01_bench_launches.md).
+template <int NACC, int UNROLL, typename Op>
+__device__ __forceinline__ void reduce_rows(long long M, int C, float* __restrict__ out, Op op) {
   extern __shared__ float red[];  // [R][NACC][C]  (only when R > 1)
   const int octets = C / 8;
   float acc[NACC][8];
+  float* part = out + (long long)blockIdx.x * NACC * C;
   auto run = [&](long long row, long long stride, int o) {
-    for (; row + 3 * stride < M; row += 4 * stride) {
-      auto p0 = op.load(row, o);
-      auto p1 = op.load(row + stride, o);
-      auto p2 = op.load(row + 2 * stride, o);
-      auto p3 = op.load(row + 3 * stride, o);
-      op.accum(p0, o, acc); op.accum(p1, o, acc); op.accum(p2, o, acc); op.accum(p3, o, acc);
+    for (; row + (UNROLL - 1) * stride < M; row += UNROLL * stride) {
+      decltype(op.load(row, o)) pk[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) pk[u] = op.load(row + u * stride, o);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) op.accum(pk[u], o, acc);
     }
     for (; row < M; row += stride) op.accum(op.load(row, o), o, acc);
   };
@@ -81,14 +85,14 @@ __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restric
           for (int e = 0; e < 8; ++e) {
             float s = 0.f;
             for (int q = 0; q < R; ++q) s += red[((q * NACC + a) * octets + o) * 8 + e];
-            atomicAdd(out + (long long)a * C + o * 8 + e, s);
+            part[(long long)a * C + o * 8 + e] = s;
           }
       }
     } else if (active) {
 #pragma unroll
       for (int a = 0; a < NACC; ++a)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(out + (long long)a * C + o * 8 + e, acc[a][e]);
+        for (int e = 0; e < 8; ++e) part[(long long)a * C + o * 8 + e] = acc[a][e];
     }
   } else {
     for (int o = threadIdx.x; o < octets; o += kThreads) {
@@ -100,9 +104,23 @@ __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restric
 #pragma unroll
       for (int a = 0; a < NACC; ++a)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) atomicAdd(out + (long long)a * C + o * 8 + e, acc[a][e]);
+        for (int e = 0; e < 8; ++e) part[(long long)a * C + o * 8 + e] = acc[a][e];
     }
   }
+}
+
+// out[i] = sum over the nparts per-CTA partials, i < n (fixed order).
+__global__ void sum_partials_kernel(const float* __restrict__ partials, int nparts, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains: the loads are latency bound
+  int b = 0;
+  for (; b + 3 < nparts; b += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] += __ldg(partials + (long long)(b + u) * n + i);
+  }
+  for (; b < nparts; ++b) s[0] += __ldg(partials + (long long)b * n + i);
+  out[i] = (s[0] + s[1]) + (s[2] + s[3]);
 }
 
 struct StatsOp {
@@ -123,11 +141,11 @@ struct StatsOp {
 // sums[0][c] = sum_rows x, sums[1][c] = sum_rows x^2.          bytes: M*C*2 read
 __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const uint4* __restrict__ x, long long M, int C,
                                                             float* __restrict__ sums) {
-  reduce_rows<2>(M, C, sums, StatsOp{x, C / 8});
+  reduce_rows<2, 8>(M, C, sums, StatsOp{x, C / 8});
 }
 
 // mean/invstd, affine scale/shift, running-stat update (momentum, unbiased variance) -- C threads of work.
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, long long M, int C, int c_real,
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nparts, long long M, int C, int c_real,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
                                    float eps, float* __restrict__ mean_invstd /*[2][C]*/,
@@ -138,9 +156,23 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long M, 
     mean_invstd[c] = 0.f; mean_invstd[C + c] = 0.f; scale_shift[c] = 0.f; scale_shift[C + c] = 0.f;
     return;
   }
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (latency-bound loads)
+  int b = 0;
+  for (; b + 3 < nparts; b += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a0[u] += __ldg(partials + (long long)(b + u) * 2 * C + c);
+      a1[u] += __ldg(partials + (long long)(b + u) * 2 * C + C + c);
+    }
+  }
+  for (; b < nparts; ++b) {
+    a0[0] += __ldg(partials + (long long)b * 2 * C + c);
+    a1[0] += __ldg(partials + (long long)b * 2 * C + C + c);
+  }
+  const float s0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
   const double inv_m = 1.0 / (double)M;
-  const double mean = (double)sums[c] * inv_m;
-  double var = (double)sums[C + c] * inv_m - mean * mean;
+  const double mean = (double)s0 * inv_m;
+  double var = (double)s1 * inv_m - mean * mean;
   if (var < 0) var = 0;
   const float invstd = (float)(1.0 / sqrt(var + (double)eps));
   mean_invstd[c] = (float)mean;
@@ -241,7 +273,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const uint4* __
                                                                  const uint4* __restrict__ dy, long long M, int C,
                                                                  const float* __restrict__ mean_invstd,
                                                                  float* __restrict__ dsums) {
-  reduce_rows<2>(M, C, dsums, BwdReduceOp{x, act, dy, mean_invstd, C / 8, C});
+  reduce_rows<2, 4>(M, C, dsums, BwdReduceOp{x, act, dy, mean_invstd, C / 8, C});
 }
 
 // dx = gamma*invstd * (g - dbeta/M - xhat * dgamma/M) (+ extra);  optionally dres = g (masked dy).
@@ -470,17 +502,20 @@ int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* ga
   NBDT_REQUIRE(x && gamma && beta && sums && mean_invstd && scale_shift, "NULL tensor");
   NBDT_REQUIRE(C % 8 == 0 && C <= 8192 && M > 0, "bad shape M=%lld C=%d", M, C);
   cudaStream_t st = (cudaStream_t)stream;
-  NBDT_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), st));
   const int octets = C / 8;
   const int R = std::max(1, kThreads / octets);
-  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 8));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 4));
   const size_t smem = R > 1 ? (size_t)R * 2 * C * sizeof(float) : 0;
   bn_stats_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint4*>(x), M, C, sums);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, M, C, c_real, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, grid, M, C, c_real, gamma, beta, running_mean, running_var,
                                                       momentum, eps, mean_invstd, scale_shift);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }
+
+// Number of floats the `sums` / `dsums` scratch buffers of nbdt_bn_stats / nbdt_bn_backward must hold for C channels
+// (per-CTA partial sums + the reduced result).
+long long nbdt_bn_scratch_floats(int C) { return (long long)(4 * sm_count() + 1) * 2 * C; }
 
 int nbdt_bn_eval_scale(int C, int c_real, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale_shift, void* stream) {
@@ -513,13 +548,14 @@ int nbdt_bn_backward(const void* x, const void* act, const void* dy, const void*
   NBDT_REQUIRE(x && dy && dx && gamma && mean_invstd && dsums, "NULL tensor");
   NBDT_REQUIRE(C % 8 == 0 && C <= 2048 && M > 0, "bad shape M=%lld C=%d", M, C);
   cudaStream_t st = (cudaStream_t)stream;
-  NBDT_CUDA_OK(cudaMemsetAsync(dsums, 0, 2 * C * sizeof(float), st));
   const int octets = C / 8;
   const int R = std::max(1, kThreads / octets);
-  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 8));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 2));
   const size_t smem = R > 1 ? (size_t)R * 2 * C * sizeof(float) : 0;
+  float* partials = dsums + 2 * C;  // dsums: [2][C] result followed by the per-CTA partials
   bn_bwd_reduce_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(act),
-                                                     reinterpret_cast<const uint4*>(dy), M, C, mean_invstd, dsums);
+                                                     reinterpret_cast<const uint4*>(dy), M, C, mean_invstd, partials);
+  sum_partials_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(partials, grid, 2 * C, dsums);
   const long long total = M * octets;
   bn_bwd_apply_kernel<<<grid_for(total, sm_count()), kThreads, 5 * C * sizeof(float), st>>>(
       reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(act), reinterpret_cast<const uint4*>(dy),

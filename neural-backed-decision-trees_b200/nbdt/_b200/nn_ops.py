@@ -95,7 +95,7 @@ class BatchNormActFunction(torch.autograd.Function):
         lib = L.load()
         with torch.cuda.device(dev):
             if training:
-                sums = torch.empty((2, Cp), dtype=torch.float32, device=dev)
+                sums = torch.empty((lib.nbdt_bn_scratch_floats(Cp),), dtype=torch.float32, device=dev)
                 rm = running_mean if running_mean is not None else None
                 rv = running_var if running_var is not None else None
                 L.check(lib.nbdt_bn_stats(_p(x), M, Cp, c_real, _p(g), _p(b), _p(rm), _p(rv), float(momentum), float(eps),
@@ -122,12 +122,12 @@ class BatchNormActFunction(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
-        dsums = torch.empty((2, Cp), dtype=torch.float32, device=x.device)
+        dsums = torch.empty((L.load().nbdt_bn_scratch_floats(Cp),), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             L.check(L.load().nbdt_bn_backward(_p(x), _p(act), _p(dy), None, _p(dx), _p(dres), M, Cp, c_real, _p(g),
                                               _p(mean_invstd), _p(dsums), _stream(x)))
-        _count(2)
-        return dx, dsums[1, :c_real].clone(), dsums[0, :c_real].clone(), None, None, None, None, None, None, dres
+        _count(3)
+        return dx, dsums[Cp:Cp + c_real].clone(), dsums[:c_real].clone(), None, None, None, None, None, None, dres
 
 
 class AvgPoolFunction(torch.autograd.Function):
