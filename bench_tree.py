@@ -22,35 +22,37 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def time_point(tree, kind, rows, C, dtype, iters=10, warmup=3, group=None):
+def time_point(tree, kind, rows, C, dtype, iters=20, warmup=3, group=None):
+    """Average duration of `iters` back-to-back launches (one CUDA-event pair around them, so the launch path of
+    Python is hidden behind the previous kernel) rotating over enough (logits, targets, grad) sets that no launch
+    finds its inputs or the previous owner of its outputs in the 126 MB L2."""
     from nbdt._b200 import ops
 
     dev = torch.device("cuda:0")
     gen = torch.Generator(device=dev).manual_seed(0)
-    x = (3 * torch.randn((rows, C), device=dev, generator=gen)).to(dtype)
-    y = torch.randint(C, (rows,), device=dev, generator=gen)
-    esz = x.element_size()
+    esz = torch.empty((), dtype=dtype).element_size()
     alg_bytes = 2 * rows * C * esz + 8 * rows + 4
-    flush = None
-    if alg_bytes < 300e6:  # working set not safely above L2: flush between iterations
-        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    for _ in range(warmup):
-        ops.tree_loss(tree, x, y, kind, 1.0, 1.0)
+    nsets = min(iters, max(2, int(400e6 // alg_bytes) + 2))
+    sets = []
+    for _ in range(nsets):
+        x = (3 * torch.randn((rows, C), device=dev, generator=gen)).to(dtype)
+        y = torch.randint(C, (rows,), device=dev, generator=gen)
+        sets.append((x, y, (torch.empty((), dtype=torch.float32, device=dev), torch.empty_like(x))))
+    for i in range(warmup):
+        x, y, out = sets[i % nsets]
+        ops.tree_loss(tree, x, y, kind, 1.0, 1.0, out=out)
     torch.cuda.synchronize()
-    times = []
-    for _ in range(iters):
-        if flush is not None:
-            flush.zero_()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        ops.tree_loss(tree, x, y, kind, 1.0, 1.0)
-        e.record()
-        e.synchronize()
-        times.append(s.elapsed_time(e))
-    times.sort()
-    ms = times[len(times) // 2]
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(iters):
+        x, y, out = sets[i % nsets]
+        ops.tree_loss(tree, x, y, kind, 1.0, 1.0, out=out)
+    e.record()
+    e.synchronize()
+    ms = s.elapsed_time(e) / iters
     return {"rows": rows, "C": C, "dtype": str(dtype).replace("torch.", ""), "kind": kind, "ms": ms,
-            "alg_bytes": alg_bytes, "gbs": alg_bytes / ms / 1e6, "l2": "flush" if flush is not None else "inputs>L2"}
+            "alg_bytes": alg_bytes, "gbs": alg_bytes / ms / 1e6,
+            "l2": f"{iters} back-to-back launches rotating over {nsets} buffer sets ({nsets * alg_bytes / 1e6:.0f} MB > L2)"}
 
 
 def main():

@@ -143,7 +143,7 @@ int nbdt_conv_unpack_wgrad(const float* dwp, float* dw_oihw, int Cout, int Cin, 
  * (nbdt/models/resnet.py:50-54,70-73,142; main.py:207,239).  c_real <= C marks zero-padded channels.
  * ------------------------------------------------------------------------------------------- */
 
-/* Floats the `sums` / `dsums` scratch buffers below must hold (per-CTA partial sums + the reduced [2][C]). */
+/* Floats the `sums` / `dsums` scratch buffers below must hold (reduced [2][C] + coefficients [3][C] + per-CTA partial sums). */
 long long nbdt_bn_scratch_floats(int C);
 /* Training-mode batch statistics: mean_invstd[2][C], scale_shift[2][C] (y = x*scale + shift), running-stat
  * update with `momentum` (running_* may be NULL).  sums: fp32 scratch of nbdt_bn_scratch_floats(C). */
@@ -156,12 +156,14 @@ int nbdt_bn_eval_scale(int C, int c_real, const float* gamma, const float* beta,
 /* y = act(x*scale + shift (+ residual)), act = ReLU when relu != 0. */
 int nbdt_bn_apply(const void* x, const void* residual, void* y, long long M, int C, const float* scale_shift,
                   int relu, void* stream);
-/* Backward of nbdt_bn_stats + nbdt_bn_apply.  act = the forward output when ReLU was applied (else NULL);
- * dx = gradient w.r.t. x (+ extra, may be NULL); dres (may be NULL) = gradient w.r.t. the residual;
- * dsums: fp32 buffer of nbdt_bn_scratch_floats(C); its first [2][C] receive (sum g, sum g*xhat) = (dbeta, dgamma). */
-int nbdt_bn_backward(const void* x, const void* act, const void* dy, const void* extra, void* dx, void* dres,
-                     long long M, int C, int c_real, const float* gamma, const float* mean_invstd, float* dsums,
-                     void* stream);
+/* Backward of nbdt_bn_stats + nbdt_bn_apply.  ReLU mask of the forward pass: `act` (the forward output) when
+ * given; else recomputed as x*scale+shift > 0 from `scale_shift` when given (valid when no residual was added before
+ * the ReLU; saves one tensor read per kernel); else no activation.  dx = gradient w.r.t. x (+ extra, may be NULL);
+ * dres (may be NULL) = gradient w.r.t. the residual; dsums: fp32 buffer of nbdt_bn_scratch_floats(C); its first
+ * [2][C] receive (dbeta, dgamma). */
+int nbdt_bn_backward(const void* x, const void* act, const float* scale_shift, const void* dy, const void* extra,
+                     void* dx, void* dres, long long M, int C, int c_real, const float* gamma,
+                     const float* mean_invstd, float* dsums, void* stream);
 /* feat[N][C] (fp32) = mean over the HW rows of each image;  da = dfeat / HW broadcast. */
 int nbdt_avgpool_fwd(const void* a, float* feat, int N, int HW, int C, void* stream);
 int nbdt_avgpool_bwd(const float* dfeat, void* da, int N, int HW, int C, void* stream);

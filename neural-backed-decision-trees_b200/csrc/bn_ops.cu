@@ -39,95 +39,108 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Shared skeleton of the per-channel reductions: thread (r, o) owns channel octet o of rows
-// r, r + R, ... of this CTA's grid-stride share; NACC float accumulators per channel.  `Op` provides
+// Thread mapping shared by every BatchNorm kernel: a CTA of 256 threads covers R = 256/octets consecutive rows x
+// `octets` channel octets (thread -> r = tid / octets, o = tid % octets; active iff r < R), i.e. R*C*2 contiguous
+// bytes per pass, and advances by R*gridDim.x rows.  A thread owns ONE channel octet for its whole life, so the
+// per-channel constants (scale/shift, mean, gradient coefficients) live in registers: no shared-memory reads and no
+// index arithmetic in the streaming loops (the v1 kernels spent their time in a 64-bit `i % octets` per 16-byte
+// access, profiles/r01_bn_kernels.md).  f(o, first_row, row_stride) runs the thread's row loop.
+template <typename F>
+__device__ __forceinline__ void for_octet_rows(int octets, F f) {
+  if (octets <= kThreads) {
+    const int R = kThreads / octets;
+    const int r = threadIdx.x / octets, o = threadIdx.x - r * octets;
+    if (r < R) f(o, (long long)blockIdx.x * R + r, (long long)gridDim.x * R);
+  } else {
+    for (int o = threadIdx.x; o < octets; o += kThreads) f(o, (long long)blockIdx.x, (long long)gridDim.x);
+  }
+}
+
+__device__ __forceinline__ void load8(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// Per-channel reductions on that mapping: NACC float accumulators per channel; `Op` provides
+//   void init(o)                 -- load the thread's per-channel constants
 //   Pack load(row, o)            -- the global loads of one row (issued UNROLL rows at a time for memory-level parallelism)
-//   void accum(pack, o, acc)     -- the arithmetic
-// Each CTA writes its partial sums to out[blockIdx.x][NACC][C]; a tiny second kernel adds the partials in a fixed
-// order (deterministic, and no same-address atomics: with one atomic per channel per CTA the reduction kernels
-// took ~130 us regardless of tensor size, profiles/r01_bench_launches.md).
+//   void accum(pack, acc)        -- the arithmetic
+// Each CTA writes its partial sums to out[blockIdx.x][NACC][C]; reduce_partials() adds them in a fixed order
+// (deterministic; same-address atomics serialise in L2).
 template <int NACC, int UNROLL, typename Op>
 __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restrict__ out, Op op) {
   extern __shared__ float red[];  // [R][NACC][C]  (only when R > 1)
   const int octets = C / 8;
-  float acc[NACC][8];
   float* part = out + (long long)blockIdx.x * NACC * C;
-  auto run = [&](long long row, long long stride, int o) {
+  const int R = octets <= kThreads ? kThreads / octets : 1;
+  for_octet_rows(octets, [&](int o, long long row, long long stride) {
+    float acc[NACC][8];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
+    op.init(o);
     for (; row + (UNROLL - 1) * stride < M; row += UNROLL * stride) {
       decltype(op.load(row, o)) pk[UNROLL];
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) pk[u] = op.load(row + u * stride, o);
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) op.accum(pk[u], o, acc);
+      for (int u = 0; u < UNROLL; ++u) op.accum(pk[u], acc);
     }
-    for (; row < M; row += stride) op.accum(op.load(row, o), o, acc);
-  };
-  if (octets <= kThreads) {
-    const int R = kThreads / octets;
-    const int r = threadIdx.x / octets, o = threadIdx.x % octets;
-    const bool active = r < R;
+    for (; row < M; row += stride) op.accum(op.load(row, o), acc);
+    float* dst = R > 1 ? red + (size_t)(threadIdx.x / octets) * NACC * C : part;
 #pragma unroll
-    for (int a = 0; a < NACC; ++a)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
-    if (active) run((long long)blockIdx.x * R + r, (long long)gridDim.x * R, o);
-    if (R > 1) {
-      if (active)
-#pragma unroll
-        for (int a = 0; a < NACC; ++a)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) red[((r * NACC + a) * octets + o) * 8 + e] = acc[a][e];
-      __syncthreads();
-      if (r == 0) {
-#pragma unroll
-        for (int a = 0; a < NACC; ++a)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float s = 0.f;
-            for (int q = 0; q < R; ++q) s += red[((q * NACC + a) * octets + o) * 8 + e];
-            part[(long long)a * C + o * 8 + e] = s;
-          }
-      }
-    } else if (active) {
-#pragma unroll
-      for (int a = 0; a < NACC; ++a)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) part[(long long)a * C + o * 8 + e] = acc[a][e];
+    for (int a = 0; a < NACC; ++a) {
+      float4* d4 = reinterpret_cast<float4*>(dst + (size_t)a * C + o * 8);
+      d4[0] = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+      d4[1] = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
     }
-  } else {
-    for (int o = threadIdx.x; o < octets; o += kThreads) {
-#pragma unroll
-      for (int a = 0; a < NACC; ++a)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[a][e] = 0.f;
-      run(blockIdx.x, gridDim.x, o);
-#pragma unroll
-      for (int a = 0; a < NACC; ++a)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) part[(long long)a * C + o * 8 + e] = acc[a][e];
+  });
+  if (R > 1) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < NACC * C; i += kThreads) {
+      float s = 0.f;
+      for (int q = 0; q < R; ++q) s += red[(size_t)q * NACC * C + i];
+      part[i] = s;
     }
   }
 }
 
-// out[i] = sum over the nparts per-CTA partials, i < n (fixed order).
-__global__ void sum_partials_kernel(const float* __restrict__ partials, int nparts, int n, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains: the loads are latency bound
-  int b = 0;
-  for (; b + 3 < nparts; b += 4) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) s[u] += __ldg(partials + (long long)(b + u) * n + i);
+// Sum of the per-CTA partials of value index i (fixed order, fp64): a CTA of 256 threads = 32 values x 8 slices of
+// the partial list, so the chain of dependent L2 reads per thread is nparts/8 long with 4 loads in flight (the v1
+// finalize kernels read all partials from one thread per channel: ~20 us of pure latency per BatchNorm).
+// Returns the total in the threads with slice 0 (threadIdx.x < 32); `n` = values per partial.
+__device__ __forceinline__ double reduce_partials(const float* __restrict__ partials, int nparts, int n, int i) {
+  __shared__ double slices[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (i < n) {
+    int b = slice;
+    for (; b + 24 < nparts; b += 32) {
+      s0 += (double)__ldg(partials + (long long)b * n + i);
+      s1 += (double)__ldg(partials + (long long)(b + 8) * n + i);
+      s2 += (double)__ldg(partials + (long long)(b + 16) * n + i);
+      s3 += (double)__ldg(partials + (long long)(b + 24) * n + i);
+    }
+    for (; b < nparts; b += 8) s0 += (double)__ldg(partials + (long long)b * n + i);
   }
-  for (; b < nparts; ++b) s[0] += __ldg(partials + (long long)b * n + i);
-  out[i] = (s[0] + s[1]) + (s[2] + s[3]);
+  slices[slice][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  double total = 0.0;
+  if (slice == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) total += slices[q][lane];
+  }
+  __syncthreads();
+  return total;
 }
 
 struct StatsOp {
   const uint4* x;
   int octets;
+  __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ uint4 load(long long row, int o) const { return __ldg(x + row * octets + o); }
-  __device__ __forceinline__ void accum(const uint4& v, int, float (&acc)[2][8]) const {
+  __device__ __forceinline__ void accum(const uint4& v, float (&acc)[2][8]) const {
     float f[8];
     unpack8(v, f);
 #pragma unroll
@@ -138,41 +151,31 @@ struct StatsOp {
   }
 };
 
-// sums[0][c] = sum_rows x, sums[1][c] = sum_rows x^2.          bytes: M*C*2 read
+// partials[cta][0][c] = sum_rows x, [1][c] = sum_rows x^2.          bytes: M*C*2 read
 __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const uint4* __restrict__ x, long long M, int C,
-                                                            float* __restrict__ sums) {
-  reduce_rows<2, 8>(M, C, sums, StatsOp{x, C / 8});
+                                                            float* __restrict__ partials) {
+  reduce_rows<2, 8>(M, C, partials, StatsOp{x, C / 8});
 }
 
-// mean/invstd, affine scale/shift, running-stat update (momentum, unbiased variance) -- C threads of work.
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nparts, long long M, int C, int c_real,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
-                                   float eps, float* __restrict__ mean_invstd /*[2][C]*/,
-                                   float* __restrict__ scale_shift /*[2][C]*/) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// mean/invstd, affine scale/shift, running-stat update (momentum, unbiased variance).  grid = ceil(C/32) x 256 threads.
+__global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const float* __restrict__ partials, int nparts, long long M,
+                                                               int C, int c_real, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta,
+                                                               float* __restrict__ running_mean,
+                                                               float* __restrict__ running_var, float momentum, float eps,
+                                                               float* __restrict__ mean_invstd /*[2][C]*/,
+                                                               float* __restrict__ scale_shift /*[2][C]*/) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const double s0 = reduce_partials(partials, nparts, 2 * C, c < C ? c : 2 * C);
+  const double s1 = reduce_partials(partials, nparts, 2 * C, c < C ? C + c : 2 * C);
+  if (threadIdx.x >= 32 || c >= C) return;
   if (c >= c_real) {  // zero-padded channel: stays exactly zero
     mean_invstd[c] = 0.f; mean_invstd[C + c] = 0.f; scale_shift[c] = 0.f; scale_shift[C + c] = 0.f;
     return;
   }
-  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};  // independent chains (latency-bound loads)
-  int b = 0;
-  for (; b + 3 < nparts; b += 4) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      a0[u] += __ldg(partials + (long long)(b + u) * 2 * C + c);
-      a1[u] += __ldg(partials + (long long)(b + u) * 2 * C + C + c);
-    }
-  }
-  for (; b < nparts; ++b) {
-    a0[0] += __ldg(partials + (long long)b * 2 * C + c);
-    a1[0] += __ldg(partials + (long long)b * 2 * C + C + c);
-  }
-  const float s0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
   const double inv_m = 1.0 / (double)M;
-  const double mean = (double)s0 * inv_m;
-  double var = (double)s1 * inv_m - mean * mean;
+  const double mean = s0 * inv_m;
+  double var = s1 * inv_m - mean * mean;
   if (var < 0) var = 0;
   const float invstd = (float)(1.0 / sqrt(var + (double)eps));
   mean_invstd[c] = (float)mean;
@@ -200,145 +203,185 @@ __global__ void bn_eval_scale_kernel(int C, int c_real, const float* __restrict_
 }
 
 // y = act(x * scale[c] + shift[c] (+ residual)).            bytes: M*C*2 read (+M*C*2) + M*C*2 written
+template <bool RES>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res,
-                                                            uint4* __restrict__ y, long long total_octets, int C,
+                                                            uint4* __restrict__ y, long long M, int C,
                                                             const float* __restrict__ scale_shift, int relu) {
-  extern __shared__ float ss[];  // [2][C]
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ss[i] = scale_shift[i];
-  __syncthreads();
   const int octets = C / 8;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  auto one = [&](long long i, const uint4& vx, const uint4& vr) {
-    const int c0 = (int)(i % octets) * 8;
-    float f[8], r[8];
-    unpack8(vx, f);
-    unpack8(vr, r);
+  for_octet_rows(octets, [&](int o, long long row, long long stride) {
+    float sc[8], sh[8];
+    load8(scale_shift + o * 8, sc);
+    load8(scale_shift + C + o * 8, sh);
+    auto one = [&](long long rw, const uint4& vx, const uint4& vr) {
+      float f[8], r[8];
+      unpack8(vx, f);
+      if (RES) unpack8(vr, r);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = fmaf(f[e], ss[c0 + e], ss[C + c0 + e]);
-      if (res) v += r[e];
-      f[e] = relu ? fmaxf(v, 0.f) : v;
+      for (int e = 0; e < 8; ++e) {
+        float v = fmaf(f[e], sc[e], sh[e]);
+        if (RES) v += r[e];
+        f[e] = relu ? fmaxf(v, 0.f) : v;
+      }
+      y[rw * octets + o] = pack8(f);
+    };
+    constexpr int U = 4;
+    for (; row + (U - 1) * stride < M; row += U * stride) {
+      uint4 vx[U], vr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        vx[u] = __ldg(x + (row + u * stride) * octets + o);
+        if (RES) vr[u] = __ldg(res + (row + u * stride) * octets + o);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) one(row + u * stride, vx[u], vr[u]);
     }
-    y[i] = pack8(f);
-  };
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + 3 * stride < total_octets; i += 4 * stride) {
-    uint4 vx[4], vr[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      vx[u] = __ldg(x + i + u * stride);
-      vr[u] = res ? __ldg(res + i + u * stride) : zero;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) one(i + u * stride, vx[u], vr[u]);
-  }
-  for (; i < total_octets; i += stride) one(i, __ldg(x + i), res ? __ldg(res + i) : zero);
+    for (; row < M; row += stride)
+      one(row, __ldg(x + row * octets + o), RES ? __ldg(res + row * octets + o) : make_uint4(0, 0, 0, 0));
+  });
 }
+
+// ReLU mask of the forward pass: kMaskNone (no activation), kMaskAct (read the saved forward output: needed when a
+// residual was added before the ReLU), kMaskRecompute (x*scale + shift > 0, bit-identical to the forward's fmaf:
+// saves reading one tensor in each backward kernel).
+enum { kMaskNone = 0, kMaskAct = 1, kMaskRecompute = 2 };
 
 struct BwdPack {
   uint4 x, g, a;
 };
+template <int MASK>
 struct BwdReduceOp {
   const uint4* x;
   const uint4* act;
   const uint4* dy;
   const float* mean_invstd;
+  const float* scale_shift;
   int octets, C;
+  float mean[8], sc[8], sh[8];
+  __device__ __forceinline__ void init(int o) {
+    load8(mean_invstd + o * 8, mean);
+    if (MASK == kMaskRecompute) {
+      load8(scale_shift + o * 8, sc);
+      load8(scale_shift + C + o * 8, sh);
+    }
+  }
   __device__ __forceinline__ BwdPack load(long long row, int o) const {
     BwdPack p;
     p.x = __ldg(x + row * octets + o);
     p.g = __ldg(dy + row * octets + o);
-    p.a = act ? __ldg(act + row * octets + o) : make_uint4(0, 0, 0, 0);
+    if (MASK == kMaskAct) p.a = __ldg(act + row * octets + o);
     return p;
   }
-  __device__ __forceinline__ void accum(const BwdPack& p, int o, float (&acc)[2][8]) const {
+  __device__ __forceinline__ void accum(const BwdPack& p, float (&acc)[2][8]) const {
     float fx[8], fg[8], fa[8];
     unpack8(p.x, fx);
     unpack8(p.g, fg);
-    unpack8(p.a, fa);
+    if (MASK == kMaskAct) unpack8(p.a, fa);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float g = (act && !(fa[e] > 0.f)) ? 0.f : fg[e];
-      const float xhat = (fx[e] - __ldg(mean_invstd + o * 8 + e)) * __ldg(mean_invstd + C + o * 8 + e);
+      bool on = true;
+      if (MASK == kMaskAct) on = fa[e] > 0.f;
+      if (MASK == kMaskRecompute) on = fmaf(fx[e], sc[e], sh[e]) > 0.f;
+      const float g = on ? fg[e] : 0.f;
       acc[0][e] += g;
-      acc[1][e] = fmaf(g, xhat, acc[1][e]);
+      acc[1][e] = fmaf(g, fx[e] - mean[e], acc[1][e]);
     }
   }
 };
 
-// dsums[0][c] = sum g, dsums[1][c] = sum g * xhat, with g = dy * (act > 0) when the forward applied ReLU.
+// partials[cta][0][c] = sum g, [1][c] = sum g * (x - mean), with g = dy masked by the forward ReLU.
 // bytes: M*C*2 * (2 or 3) read
+template <int MASK>
 __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ act,
                                                                  const uint4* __restrict__ dy, long long M, int C,
                                                                  const float* __restrict__ mean_invstd,
-                                                                 float* __restrict__ dsums) {
-  reduce_rows<2, 4>(M, C, dsums, BwdReduceOp{x, act, dy, mean_invstd, C / 8, C});
+                                                                 const float* __restrict__ scale_shift,
+                                                                 float* __restrict__ partials) {
+  BwdReduceOp<MASK> op;
+  op.x = x; op.act = act; op.dy = dy; op.mean_invstd = mean_invstd; op.scale_shift = scale_shift;
+  op.octets = C / 8; op.C = C;
+  reduce_rows<2, 4>(M, C, partials, op);
 }
 
-// dx = gamma*invstd * (g - dbeta/M - xhat * dgamma/M) (+ extra);  optionally dres = g (masked dy).
+// dsums[0][c] = dbeta = sum g, dsums[1][c] = dgamma = invstd * sum g (x - mean); coef[3][C] = (k1, a, b) with
+// dx = k1*g + a*x + b:  k1 = gamma*invstd, a = -k1*invstd*dgamma/M, b = -k1*dbeta/M - a*mean.
+__global__ void __launch_bounds__(kThreads) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, long long M,
+                                                                   int C, int c_real, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ mean_invstd,
+                                                                   float* __restrict__ dsums, float* __restrict__ coef) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const double s0 = reduce_partials(partials, nparts, 2 * C, c < C ? c : 2 * C);
+  const double s1 = reduce_partials(partials, nparts, 2 * C, c < C ? C + c : 2 * C);
+  if (threadIdx.x >= 32 || c >= C) return;
+  const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
+  const float dbeta = (float)s0, dgamma = (float)(s1 * (double)invstd);
+  dsums[c] = dbeta;
+  dsums[C + c] = dgamma;
+  const float inv_m = 1.f / (float)M;
+  const float k1 = c < c_real ? gamma[c] * invstd : 0.f;
+  const float a = -k1 * invstd * dgamma * inv_m;
+  coef[c] = k1;
+  coef[C + c] = a;
+  coef[2 * C + c] = -k1 * dbeta * inv_m - a * mean;
+}
+
+// dx = k1*g + a*x + b (+ extra);  optionally dres = g (masked dy).
 // bytes: M*C*2 * (2..4) read + M*C*2 * (1..2) written
+template <int MASK, bool EXTRA, bool DRES>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ act,
                                                                 const uint4* __restrict__ dy, const uint4* __restrict__ extra,
                                                                 uint4* __restrict__ dx, uint4* __restrict__ dres,
-                                                                long long total_octets, long long M, int C, int c_real,
-                                                                const float* __restrict__ gamma,
-                                                                const float* __restrict__ mean_invstd,
-                                                                const float* __restrict__ dsums) {
-  extern __shared__ float sm[];  // [4][C]: mean, k1 = gamma*invstd, k2 = dbeta/M, k3 = invstd*dgamma/M ... see below
-  const float inv_m = 1.f / (float)M;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float invstd = mean_invstd[C + c];
-    const float g = c < c_real ? gamma[c] : 0.f;
-    sm[c] = mean_invstd[c];
-    sm[C + c] = invstd;
-    sm[2 * C + c] = g * invstd;
-    sm[3 * C + c] = dsums[c] * inv_m;
-  }
-  __syncthreads();
-  float* dg_over_m = sm + 4 * C;  // [C]
-  for (int c = threadIdx.x; c < C; c += blockDim.x) dg_over_m[c] = dsums[C + c] * inv_m;
-  __syncthreads();
+                                                                long long M, int C, const float* __restrict__ coef,
+                                                                const float* __restrict__ scale_shift) {
   const int octets = C / 8;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const uint4 zero = make_uint4(0, 0, 0, 0);
-  auto one = [&](long long i, const uint4& vx, const uint4& vg, const uint4& va, const uint4& ve) {
-    const int c0 = (int)(i % octets) * 8;
-    float fx[8], fg[8], fa[8], fe[8];
-    unpack8(vx, fx);
-    unpack8(vg, fg);
-    unpack8(va, fa);
-    unpack8(ve, fe);
-    float o[8], gm[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = c0 + e;
-      const float g = (act && !(fa[e] > 0.f)) ? 0.f : fg[e];
-      const float xhat = (fx[e] - sm[c]) * sm[C + c];
-      float v = sm[2 * C + c] * (g - sm[3 * C + c] - xhat * dg_over_m[c]);
-      if (extra) v += fe[e];
-      o[e] = v;
-      gm[e] = g;
+  for_octet_rows(octets, [&](int o, long long row, long long stride) {
+    float k1[8], ka[8], kb[8], sc[8], sh[8];
+    load8(coef + o * 8, k1);
+    load8(coef + C + o * 8, ka);
+    load8(coef + 2 * C + o * 8, kb);
+    if (MASK == kMaskRecompute) {
+      load8(scale_shift + o * 8, sc);
+      load8(scale_shift + C + o * 8, sh);
     }
-    dx[i] = pack8(o);
-    if (dres) dres[i] = pack8(gm);
-  };
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + stride < total_octets; i += 2 * stride) {
-    uint4 vx[2], vg[2], va[2], ve[2];
+    auto one = [&](long long rw, const uint4& vx, const uint4& vg, const uint4& va, const uint4& ve) {
+      float fx[8], fg[8], fa[8], fe[8], out[8];
+      unpack8(vx, fx);
+      unpack8(vg, fg);
+      if (MASK == kMaskAct) unpack8(va, fa);
+      if (EXTRA) unpack8(ve, fe);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const long long k = i + u * stride;
-      vx[u] = __ldg(x + k);
-      vg[u] = __ldg(dy + k);
-      va[u] = act ? __ldg(act + k) : zero;
-      ve[u] = extra ? __ldg(extra + k) : zero;
+      for (int e = 0; e < 8; ++e) {
+        bool on = true;
+        if (MASK == kMaskAct) on = fa[e] > 0.f;
+        if (MASK == kMaskRecompute) on = fmaf(fx[e], sc[e], sh[e]) > 0.f;
+        const float g = on ? fg[e] : 0.f;
+        float v = fmaf(k1[e], g, fmaf(ka[e], fx[e], kb[e]));
+        if (EXTRA) v += fe[e];
+        out[e] = v;
+        fg[e] = g;
+      }
+      dx[rw * octets + o] = pack8(out);
+      if (DRES) dres[rw * octets + o] = pack8(fg);
+    };
+    constexpr int U = 2;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (; row + (U - 1) * stride < M; row += U * stride) {
+      uint4 vx[U], vg[U], va[U], ve[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long k = (row + u * stride) * octets + o;
+        vx[u] = __ldg(x + k);
+        vg[u] = __ldg(dy + k);
+        va[u] = MASK == kMaskAct ? __ldg(act + k) : zero;
+        ve[u] = EXTRA ? __ldg(extra + k) : zero;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) one(row + u * stride, vx[u], vg[u], va[u], ve[u]);
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) one(i + u * stride, vx[u], vg[u], va[u], ve[u]);
-  }
-  for (; i < total_octets; i += stride)
-    one(i, __ldg(x + i), __ldg(dy + i), act ? __ldg(act + i) : zero, extra ? __ldg(extra + i) : zero);
+    for (; row < M; row += stride) {
+      const long long k = row * octets + o;
+      one(row, __ldg(x + k), __ldg(dy + k), MASK == kMaskAct ? __ldg(act + k) : zero, EXTRA ? __ldg(extra + k) : zero);
+    }
+  });
 }
 
 // feat[n][c] = mean over HW rows of a[n, :, c]  (fp32 out).      bytes: N*HW*C*2 read
@@ -490,32 +533,43 @@ int sm_count() {
   return info.sm_count;
 }
 
+
+// Launch geometry of the row-octet mapping: CTAs of 256 threads, `per_sm` per SM, never more than one pass of rows.
+int rows_grid(long long M, int C, int per_sm) {
+  const int octets = C / 8;
+  const int R = octets <= kThreads ? kThreads / octets : 1;
+  return (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * per_sm));
+}
+size_t reduce_smem(int C) {
+  const int octets = C / 8;
+  const int R = octets <= kThreads ? kThreads / octets : 1;
+  return R > 1 ? (size_t)R * 2 * C * sizeof(float) : 0;
+}
+constexpr int kReduceCtasPerSm = 2;
+
 }  // namespace
 
 extern "C" {
 
 // Training-mode statistics of x[M][C] (bf16): fills mean_invstd[2][C], scale_shift[2][C], updates the running
-// statistics (may be NULL).  `sums` is a [2][C] fp32 scratch buffer.  c_real <= C: channels beyond are padding.
+// statistics (may be NULL).  `sums`: fp32 scratch of nbdt_bn_scratch_floats(C).  c_real <= C: channels beyond are padding.
 int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, float* sums,
                   float* mean_invstd, float* scale_shift, void* stream) {
   NBDT_REQUIRE(x && gamma && beta && sums && mean_invstd && scale_shift, "NULL tensor");
   NBDT_REQUIRE(C % 8 == 0 && C <= 8192 && M > 0, "bad shape M=%lld C=%d", M, C);
   cudaStream_t st = (cudaStream_t)stream;
-  const int octets = C / 8;
-  const int R = std::max(1, kThreads / octets);
-  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 4));
-  const size_t smem = R > 1 ? (size_t)R * 2 * C * sizeof(float) : 0;
-  bn_stats_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint4*>(x), M, C, sums);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, grid, M, C, c_real, gamma, beta, running_mean, running_var,
-                                                      momentum, eps, mean_invstd, scale_shift);
+  const int grid = rows_grid(M, C, kReduceCtasPerSm);
+  bn_stats_kernel<<<grid, kThreads, reduce_smem(C), st>>>(reinterpret_cast<const uint4*>(x), M, C, sums);
+  bn_finalize_kernel<<<(C + 31) / 32, kThreads, 0, st>>>(sums, grid, M, C, c_real, gamma, beta, running_mean, running_var,
+                                                         momentum, eps, mean_invstd, scale_shift);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }
 
-// Number of floats the `sums` / `dsums` scratch buffers of nbdt_bn_stats / nbdt_bn_backward must hold for C channels
-// (per-CTA partial sums + the reduced result).
-long long nbdt_bn_scratch_floats(int C) { return (long long)(4 * sm_count() + 1) * 2 * C; }
+// Floats the `sums` / `dsums` scratch buffers of nbdt_bn_stats / nbdt_bn_backward must hold for C channels:
+// reduced result [2][C] + gradient coefficients [3][C] + per-CTA partial sums.
+long long nbdt_bn_scratch_floats(int C) { return (long long)(kReduceCtasPerSm * sm_count()) * 2 * C + 5LL * C; }
 
 int nbdt_bn_eval_scale(int C, int c_real, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale_shift, void* stream) {
@@ -530,37 +584,62 @@ int nbdt_bn_eval_scale(int C, int c_real, const float* gamma, const float* beta,
 int nbdt_bn_apply(const void* x, const void* residual, void* y, long long M, int C, const float* scale_shift, int relu,
                   void* stream) {
   NBDT_REQUIRE(x && y && scale_shift, "NULL tensor");
-  NBDT_REQUIRE(C % 8 == 0 && C <= 4096, "bad channel count %d", C);
-  const long long total = M * (C / 8);
-  if (total == 0) return NBDT_OK;
-  bn_apply_kernel<<<grid_for(total, sm_count()), kThreads, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(residual), reinterpret_cast<uint4*>(y), total, C,
-      scale_shift, relu);
+  NBDT_REQUIRE(C % 8 == 0 && C <= 8192, "bad channel count %d", C);
+  if (M == 0) return NBDT_OK;
+  const int grid = rows_grid(M, C, 6);
+  const uint4* xs = reinterpret_cast<const uint4*>(x);
+  const uint4* rs = reinterpret_cast<const uint4*>(residual);
+  uint4* ys = reinterpret_cast<uint4*>(y);
+  if (residual)
+    bn_apply_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(xs, rs, ys, M, C, scale_shift, relu);
+  else
+    bn_apply_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(xs, rs, ys, M, C, scale_shift, relu);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }
 
-// Backward of y = act(bn(x) (+ residual)).  act: the forward OUTPUT y when ReLU was applied, else NULL.
-// dx = d/dx (+ extra); dres (may be NULL) = gradient w.r.t. the residual; dgamma_dbeta[2][C] = (dbeta, dgamma) sums.
-int nbdt_bn_backward(const void* x, const void* act, const void* dy, const void* extra, void* dx, void* dres,
-                     long long M, int C, int c_real, const float* gamma, const float* mean_invstd, float* dsums,
-                     void* stream) {
+// Backward of y = act(bn(x) (+ residual)).  ReLU mask: `act` (the forward OUTPUT y) when given; else recomputed from
+// x and `scale_shift` when given (only valid when no residual was added before the ReLU); else no activation.
+// dx = d/dx (+ extra); dres (may be NULL) = gradient w.r.t. the residual; dsums[0..2C) = (dbeta, dgamma).
+int nbdt_bn_backward(const void* x, const void* act, const float* scale_shift, const void* dy, const void* extra,
+                     void* dx, void* dres, long long M, int C, int c_real, const float* gamma,
+                     const float* mean_invstd, float* dsums, void* stream) {
   NBDT_REQUIRE(x && dy && dx && gamma && mean_invstd && dsums, "NULL tensor");
-  NBDT_REQUIRE(C % 8 == 0 && C <= 2048 && M > 0, "bad shape M=%lld C=%d", M, C);
+  NBDT_REQUIRE(C % 8 == 0 && C <= 8192 && M > 0, "bad shape M=%lld C=%d", M, C);
   cudaStream_t st = (cudaStream_t)stream;
-  const int octets = C / 8;
-  const int R = std::max(1, kThreads / octets);
-  const int grid = (int)std::max<long long>(1, std::min<long long>((M + R - 1) / R, (long long)sm_count() * 2));
-  const size_t smem = R > 1 ? (size_t)R * 2 * C * sizeof(float) : 0;
-  float* partials = dsums + 2 * C;  // dsums: [2][C] result followed by the per-CTA partials
-  bn_bwd_reduce_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(act),
-                                                     reinterpret_cast<const uint4*>(dy), M, C, mean_invstd, partials);
-  sum_partials_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(partials, grid, 2 * C, dsums);
-  const long long total = M * octets;
-  bn_bwd_apply_kernel<<<grid_for(total, sm_count()), kThreads, 5 * C * sizeof(float), st>>>(
-      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(act), reinterpret_cast<const uint4*>(dy),
-      reinterpret_cast<const uint4*>(extra), reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dres), total, M, C,
-      c_real, gamma, mean_invstd, dsums);
+  const int mask = act ? kMaskAct : (scale_shift ? kMaskRecompute : kMaskNone);
+  float* coef = dsums + 2 * C;      // [3][C]
+  float* partials = dsums + 5 * C;  // [grid][2][C]
+  const uint4* xs = reinterpret_cast<const uint4*>(x);
+  const uint4* as = reinterpret_cast<const uint4*>(act);
+  const uint4* gs = reinterpret_cast<const uint4*>(dy);
+  const uint4* es = reinterpret_cast<const uint4*>(extra);
+  uint4* dxs = reinterpret_cast<uint4*>(dx);
+  uint4* drs = reinterpret_cast<uint4*>(dres);
+  const int grid = rows_grid(M, C, kReduceCtasPerSm);
+  const size_t smem = reduce_smem(C);
+  if (mask == kMaskAct)
+    bn_bwd_reduce_kernel<kMaskAct><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
+  else if (mask == kMaskRecompute)
+    bn_bwd_reduce_kernel<kMaskRecompute><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
+  else
+    bn_bwd_reduce_kernel<kMaskNone><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, kThreads, 0, st>>>(partials, grid, M, C, c_real, gamma, mean_invstd, dsums, coef);
+  const int agrid = rows_grid(M, C, 4);
+#define NBDT_BWD_APPLY(MASK, EXTRA, DRES) \
+  bn_bwd_apply_kernel<MASK, EXTRA, DRES><<<agrid, kThreads, 0, st>>>(xs, as, gs, es, dxs, drs, M, C, coef, scale_shift)
+#define NBDT_BWD_APPLY_M(MASK)                       \
+  do {                                               \
+    if (extra && dres) NBDT_BWD_APPLY(MASK, true, true);   \
+    else if (extra) NBDT_BWD_APPLY(MASK, true, false);     \
+    else if (dres) NBDT_BWD_APPLY(MASK, false, true);      \
+    else NBDT_BWD_APPLY(MASK, false, false);               \
+  } while (0)
+  if (mask == kMaskAct) NBDT_BWD_APPLY_M(kMaskAct);
+  else if (mask == kMaskRecompute) NBDT_BWD_APPLY_M(kMaskRecompute);
+  else NBDT_BWD_APPLY_M(kMaskNone);
+#undef NBDT_BWD_APPLY_M
+#undef NBDT_BWD_APPLY
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }

@@ -429,6 +429,7 @@ struct WgradParams {
   long long units_per_cta;           // stream-K: every CTA gets the same number of (item, pixel-block) units
   int pix_blocks;                    // total KPIX-pixel blocks = tiles_w * tiles_h * tiles_n
   int range_len;                     // pixel blocks per range (divides pix_blocks)
+  int teams;                         // > 0: team mode with this many pixel ranges (see wgrad_kernel); 0: stream-K
   int tiles_w, tiles_h;              // pixel-block grid inside one image (box_n images per block when the image is small)
   int box_w, box_h, box_n;
   int Cout, Cin;
@@ -508,17 +509,38 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
   // Unit order: (pixel range, item, k-block within the range).  CTAs with neighbouring unit ranges therefore work on
   // the SAME pixels for different items at the same time and share them through L2 (with item-major order every item
   // re-streamed both tensors from HBM: 1.7 GB of DRAM reads for 0.34 GB of operands, profiles/r01_conv_ncu.md).
-  auto decode = [&](long long u, int& group, int& m_tile, int& n_tile, int& kb0, int& kb1) {
-    const long long seg = u / p.range_len;
-    const int in_seg = (int)(u - seg * p.range_len);
-    int item = (int)(seg % total_items);
-    const int range0 = (int)(seg / total_items) * p.range_len;
-    kb0 = range0 + in_seg;
-    kb1 = (int)min((long long)(range0 + p.range_len), kb0 + (u_end - u));
+  // Team mode (operands larger than L2): the pixel blocks are cut into p.teams ranges and piece q = (team, item)
+  // covers ONE item over ONE range; CTA c runs pieces c, c + gridDim.x, ...  The total_items CTAs of a team start
+  // together and walk the same pixel blocks at the same pace, so each block is fetched from HBM once and the other
+  // items hit it in L2 (with one contiguous unit span per CTA the items of a range ran at different times:
+  // 1.61 GB of DRAM reads for 0.34 GB of operands in the 160->160 layers, profiles/r01_conv_ncu.md).
+  const bool team_mode = p.teams > 0;
+  const long long cur_begin = team_mode ? (long long)blockIdx.x : u_begin;
+  const long long cur_end = team_mode ? (long long)p.teams * total_items : u_end;
+  // decodes the segment at cursor u and returns the cursor of the CTA's next segment
+  auto decode = [&](long long u, int& group, int& m_tile, int& n_tile, int& kb0, int& kb1) -> long long {
+    int item;
+    long long next;
+    if (team_mode) {
+      const int team = (int)(u / total_items);
+      item = (int)(u - (long long)team * total_items);
+      kb0 = (int)((long long)team * p.pix_blocks / p.teams);
+      kb1 = (int)((long long)(team + 1) * p.pix_blocks / p.teams);
+      next = u + gridDim.x;
+    } else {
+      const long long seg = u / p.range_len;
+      const int in_seg = (int)(u - seg * p.range_len);
+      item = (int)(seg % total_items);
+      const int range0 = (int)(seg / total_items) * p.range_len;
+      kb0 = range0 + in_seg;
+      kb1 = (int)min((long long)(range0 + p.range_len), kb0 + (u_end - u));
+      next = u + (kb1 - kb0);
+    }
     n_tile = item % p.n_tiles;
     item /= p.n_tiles;
     m_tile = item % p.m_tiles;
     group = item / p.m_tiles;
+    return next;
   };
 
   if (warp == 0 || warp == 6) {
@@ -528,10 +550,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
     const bool first = warp == 0;
     int stage = 0;
     uint32_t phase = 0;
-    for (long long u = u_begin; u < u_end;) {
+    for (long long u = cur_begin; u < cur_end;) {
       int group, m_tile, n_tile, kb0, kb1;
-      decode(u, group, m_tile, n_tile, kb0, kb1);
-      u += kb1 - kb0;
+      u = decode(u, group, m_tile, n_tile, kb0, kb1);
       if (!first && TAPS == 1) continue;
       for (int kb = kb0; kb < kb1; ++kb) {
         int b = kb;
@@ -572,10 +593,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
     int stage = 0;
     uint32_t phase = 0;
     int item_idx = 0;
-    for (long long u = u_begin; u < u_end; ++item_idx) {
+    for (long long u = cur_begin; u < cur_end; ++item_idx) {
       int group, m_tile, n_tile, kb0, kb1;
-      decode(u, group, m_tile, n_tile, kb0, kb1);
-      u += kb1 - kb0;
+      u = decode(u, group, m_tile, n_tile, kb0, kb1);
       const int acc = item_idx % Cfg::kNumAcc;
       const uint32_t acc_phase = (item_idx / Cfg::kNumAcc) & 1;
       mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
@@ -608,10 +628,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     int item_idx = 0;
-    for (long long u = u_begin; u < u_end; ++item_idx) {
+    for (long long u = cur_begin; u < cur_end; ++item_idx) {
       int group, m_tile, n_tile, kb0, kb1;
-      decode(u, group, m_tile, n_tile, kb0, kb1);
-      u += kb1 - kb0;
+      u = decode(u, group, m_tile, n_tile, kb0, kb1);
       const int acc = item_idx % Cfg::kNumAcc;
       const uint32_t acc_phase = (item_idx / Cfg::kNumAcc) & 1;
       const int co = m_tile * kBlockM + row;
@@ -821,8 +840,23 @@ int nbdt_conv2d_wgrad(const void* x, const void* dy, float* dwp, int N, int H, i
   const int base_items = p.tap_groups * p.m_tiles * p.n_tiles;
   p.range_len = (p.pix_blocks % 256 == 0) ? 256 : p.pix_blocks;
   const long long total_units = (long long)base_items * p.pix_blocks;
-  const int grid = (int)std::min<long long>(total_units, info.sm_count);
+  int grid = (int)std::min<long long>(total_units, info.sm_count);
   p.units_per_cta = (total_units + grid - 1) / grid;
+  // Operands that do not fit in L2 together: team scheduling (each pixel range read from HBM once, see the kernel).
+  // teams = the smallest count whose pieces fill the SMs to >= 94 % (else the best), ranges of >= 64 k-blocks.
+  p.teams = 0;
+  const double operand_bytes = 2.0 * N * ((double)H * W * Cin + (double)Ho * Wo * Cout);
+  if (operand_bytes > 96e6 && base_items <= info.sm_count && !getenv("NBDT_B200_WGRAD_STREAMK")) {
+    double best_eff = 0.0;
+    for (int t = 1; t <= 64 && p.pix_blocks / t >= 64; ++t) {
+      const long long pieces = (long long)t * base_items;
+      const long long rounds = (pieces + info.sm_count - 1) / info.sm_count;
+      const double eff = (double)pieces / (double)(rounds * info.sm_count);
+      if (eff > best_eff + 1e-9) { best_eff = eff; p.teams = t; }
+      if (eff >= 0.94) break;
+    }
+    if (p.teams > 0) grid = (int)std::min<long long>((long long)p.teams * base_items, info.sm_count);
+  }
   CUtensorMap tm_dy, tm_x[4];
   {
     View4 dyv = dense_view(dy, N, Ho, Wo, Cout);

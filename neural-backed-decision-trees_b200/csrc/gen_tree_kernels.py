@@ -65,6 +65,14 @@ def fnv1a(C, children, root):
 
 
 def emit_kernel(name, C, children, root):
+    """Straight-line kernel for one hierarchy.
+
+    Soft modes work in the PROBABILITY domain like the reference's traverse_tree (model.py:207-242: products of
+    per-node softmax probabilities): a binary node costs two MUFU ops (ex2, rcp), leaves none, and
+    exp(class_prob) for the second cross-entropy is a degree-6 polynomial on [0, 1] on the FMA pipe (the v1
+    kernel was bound by the MUFU pipe at 70 %, profiles/r01_tree_spec_ncu.md).  The hard loss needs log path
+    probabilities that must not underflow (per-node log-softmax, loss.py:212-257) and stays in the log2 domain.
+    """
     N = len(children)
     NV = C + N
     parent = [-1] * NV
@@ -72,34 +80,51 @@ def emit_kernel(name, C, children, root):
         for c in ch:
             parent[c] = C + i
     cnt = [1] * C + [0] * N
-    depth = [0] * NV
     order = [C + root]
     for v in order:
         if v >= C:
-            for c in children[v - C]:
-                depth[c] = depth[v] + 1
-                order.append(c)
+            order.extend(children[v - C])
     for v in reversed(order):
         if parent[v] >= 0:
             cnt[parent[v]] += cnt[v]
+    depth = [0] * NV
+    for v in order:
+        if parent[v] >= 0:
+            depth[v] = depth[parent[v]] + 1
     inner_bottom_up = [v for v in reversed(order) if v >= C]
     inner_top_down = [v for v in order if v >= C]
+    rootv = C + root
 
     L = []
     w = L.append
+
+    def S(vv):
+        return f"x{vv}" if vv < C else f"S{vv}"
+
+    def G(vv):
+        return f"g{vv}" if vv < C else f"G{vv}"
+
+    def k2(c):  # log2(e) / #leaves: node logit of child c in log2 units = S(c) * k2(c)
+        return f"{1.4426950408889634 / cnt[c]!r}f"
+
+    def onehot(c):
+        return f"oh{c}"
+
     w(f"// hierarchy {name}: {C} leaves, {N} inner nodes, max depth {max(depth[:C])}")
     w("template <typename T, int MODE>")
-    w(f"__global__ void __launch_bounds__(128) {name}(const SpecParams p) {{")
+    w(f"__global__ void __launch_bounds__(128, 6) {name}(const SpecParams p) {{")
     w("  const T* __restrict__ x = reinterpret_cast<const T*>(p.x);")
     w("  T* __restrict__ gout = reinterpret_cast<T*>(p.grad);")
     w("  float loss_acc = 0.f;")
+    w("  const float kx = p.w_xent * p.inv_rows, kt = p.w_tree * p.inv_rows;")
+    w("  const float kg = kt * p.grad_scale, kgx = kx * p.grad_scale;")
     w("  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < p.B; row += (long long)gridDim.x * blockDim.x) {")
     w("    const T* xr = x + row * p.ld;")
     w(f"    float v[{C}];")
     w(f"    load_row<T, {C}>(xr, v);")
     for c in range(C):
-        w(f"    const float x{c} = v[{c}] * kLog2e;")
-    # plain CE statistics
+        w(f"    const float x{c} = v[{c}];")
+    # plain cross-entropy statistics of the raw logits
     w("    float lse1 = 0.f, inv_s1 = 0.f, xy = 0.f; int y = 0;")
     for c in range(C):
         w(f"    float e{c} = 0.f;")
@@ -108,87 +133,122 @@ def emit_kernel(name, C, children, root):
     w("      float m1 = x0;")
     for c in range(1, C):
         w(f"      m1 = fmaxf(m1, x{c});")
+    w("      const float nm = -m1 * kLog2e;")
     for c in range(C):
-        w(f"      e{c} = ex2(x{c} - m1);")
-    w("      float s1 = " + " + ".join(f"e{c}" for c in range(C)) + ";")
-    w("      lse1 = m1 + lg2(s1); inv_s1 = __fdividef(1.f, s1);")
-    w("      xy = to_f<T>(xr[y]) * kLog2e;")
+        w(f"      e{c} = ex2(fmaf(x{c}, kLog2e, nm));")
+    w("      const float s1 = " + " + ".join(f"e{c}" for c in range(C)) + ";")
+    w("      lse1 = fmaf(lg2(s1), kLn2, m1); inv_s1 = rcp(s1);")
+    w("      xy = to_f<T>(xr[y]);")
     w("    }")
-    # up sweep
-    def S(vv):
-        return f"x{vv}" if vv < C else f"S{vv}"
+    for c in range(C):
+        w(f"    const float oh{c} = (y == {c}) ? 1.f : 0.f;")
+    # up sweep: subtree sums
     for vv in inner_bottom_up:
         w(f"    const float S{vv} = " + " + ".join(S(c) for c in children[vv - C]) + ";")
-    # down sweep
-    w(f"    const float LP{C + root} = 0.f;")
-    for vv in inner_top_down:
-        ch = children[vv - C]
-        a = []
-        for c in ch:
-            if cnt[c] == 1:
-                a.append(S(c))
-            else:
-                w(f"    const float a{c} = {S(c)} * {1.0 / cnt[c]!r}f;")
-                a.append(f"a{c}")
-        if len(ch) == 2:
-            w(f"    const float lse{vv} = fmaxf({a[0]}, {a[1]}) + lg2(1.f + ex2(-fabsf({a[0]} - {a[1]})));")
-        else:
-            w(f"    float m{vv} = {a[0]};")
-            for t in a[1:]:
-                w(f"    m{vv} = fmaxf(m{vv}, {t});")
-            w(f"    const float lse{vv} = m{vv} + lg2(" + " + ".join(f"ex2({t} - m{vv})" for t in a) + ");")
-        for c, t in zip(ch, a):
-            w(f"    const float lp{c} = {t} - lse{vv};")
-            w(f"    const float LP{c} = LP{vv} + lp{c};")
-    for c in range(C):
-        w(f"    const float p{c} = ex2(LP{c});")
-    w("    if (MODE == kSpecSoftFwd) {")
-    w(f"      float o[{C}] = {{" + ", ".join(f"p{c}" for c in range(C)) + "};")
-    w(f"      store_row<float, {C}>(p.class_probs + row * {C}, o);")
-    w("      continue;")
-    w("    }")
-    # leaf stage
+    # down sweep.  pr{c}: probability of child c at its parent; soft: P{c} path probability; hard: LP{c} log2 path prob.
     for c in range(C):
         w(f"    float g{c};")
-    w("    const float kx = p.w_xent * p.inv_rows, kt = p.w_tree * p.inv_rows;")
-    w("    if (MODE == kSpecSoftLoss) {")
-    for c in range(C):
-        w(f"      const float q{c} = ex2(p{c} * kLog2e);")
-    w("      const float s2 = " + " + ".join(f"q{c}" for c in range(C)) + ";")
-    w("      const float inv_s2 = __fdividef(1.f, s2);")
-    w("      const float py = " + "".join(f"y == {c} ? p{c} : " for c in range(C - 1)) + f"p{C - 1};")
-    w("      loss_acc += kx * kLn2 * (lse1 - xy) + kt * (kLn2 * lg2(s2) - py);")
-    w("      const float kg = kt * p.grad_scale;")
-    for c in range(C):
-        w(f"      g{c} = kg * (q{c} * inv_s2 - (y == {c} ? 1.f : 0.f)) * p{c};")
-    w("    } else {")
-    w("      const float LPy = " + "".join(f"y == {c} ? LP{c} : " for c in range(C - 1)) + f"LP{C - 1};")
-    w("      loss_acc += kx * kLn2 * (lse1 - xy) - kt * kLn2 * LPy;")
-    w("      const float kg = kt * p.grad_scale;")
-    for c in range(C):
-        w(f"      g{c} = (y == {c}) ? -kg : 0.f;")
-    w("    }")
-    w("    if (gout == nullptr) continue;")
-    # up sweep of G
-    def G(vv):
-        return f"g{vv}" if vv < C else f"G{vv}"
-    for vv in inner_bottom_up:
-        w(f"    const float G{vv} = " + " + ".join(G(c) for c in children[vv - C]) + ";")
-    # down sweep of A
-    w(f"    const float A{C + root} = 0.f;")
+    for vv in range(NV):
+        if vv != rootv:
+            w(f"    float pr{vv};")
+    w("    if (MODE != kSpecHardLoss) {")
     for vv in inner_top_down:
         ch = children[vv - C]
-        for j, c in enumerate(ch):
-            if len(ch) == 2 and j == 1:
-                w(f"    const float pr{c} = 1.f - pr{ch[0]};")
+        if len(ch) == 2:
+            c0, c1 = ch
+            w(f"      {{ const float d = fmaf({S(c0)}, {k2(c0)}, -({S(c1)} * {k2(c1)}));")
+            w("        const float t = ex2(-fabsf(d)); const float r = rcp(1.f + t); const float lo = t * r;")
+            w(f"        pr{c0} = d >= 0.f ? r : lo; pr{c1} = d >= 0.f ? lo : r; }}")
+        else:
+            w("      {")
+            for c in ch:
+                w(f"        const float a{c} = {S(c)} * {k2(c)};")
+            w(f"        float m = a{ch[0]};")
+            for c in ch[1:]:
+                w(f"        m = fmaxf(m, a{c});")
+            for c in ch:
+                w(f"        const float q{c} = ex2(a{c} - m);")
+            w("        const float r = rcp(" + " + ".join(f"q{c}" for c in ch) + ");")
+            for c in ch:
+                w(f"        pr{c} = q{c} * r;")
+            w("      }")
+    for vv in inner_top_down:
+        for c in children[vv - C]:
+            if vv == rootv:
+                w(f"      const float P{c} = pr{c};")
             else:
-                w(f"    const float pr{c} = ex2(lp{c});")
-            scale = "" if cnt[c] == 1 else f" * {1.0 / cnt[c]!r}f"
-            w(f"    const float A{c} = A{vv} + ({G(c)} - pr{c} * G{vv}){scale};")
-    w("    const float kgx = kx * p.grad_scale;")
+                w(f"      const float P{c} = P{vv} * pr{c};")
+    w("      if (MODE == kSpecSoftFwd) {")
+    w(f"        float o[{C}] = {{" + ", ".join(f"P{c}" for c in range(C)) + "};")
+    w(f"        store_row<float, {C}>(p.class_probs + row * {C}, o);")
+    w("        continue;")
+    w("      }")
+    for c in range(C):
+        w(f"      const float q{c} = exp01(P{c});")
+    w("      const float s2 = " + " + ".join(f"q{c}" for c in range(C)) + ";")
+    w("      const float inv_s2 = rcp(s2);")
+    w("      float py = oh0 * P0;")
+    for c in range(1, C):
+        w(f"      py = fmaf(oh{c}, P{c}, py);")
+    w("      loss_acc += kx * (lse1 - xy) + kt * (kLn2 * lg2(s2) - py);")
+    for c in range(C):
+        w(f"      g{c} = kg * (q{c} * inv_s2 - {onehot(c)}) * P{c};")
+    w("    } else {")
+    for vv in inner_top_down:
+        ch = children[vv - C]
+        if len(ch) == 2:
+            c0, c1 = ch
+            w(f"      float lp{c0}, lp{c1};")
+            w(f"      {{ const float d = fmaf({S(c0)}, {k2(c0)}, -({S(c1)} * {k2(c1)}));")
+            w("        const float t = ex2(-fabsf(d)); const float l = -lg2(1.f + t); const float ll = l - fabsf(d);")
+            w(f"        lp{c0} = d >= 0.f ? l : ll; lp{c1} = d >= 0.f ? ll : l;")
+            w("        const float r = rcp(1.f + t); const float lo = t * r;")
+            w(f"        pr{c0} = d >= 0.f ? r : lo; pr{c1} = d >= 0.f ? lo : r; }}")
+        else:
+            for c in ch:
+                w(f"      float lp{c};")
+            w("      {")
+            for c in ch:
+                w(f"        const float a{c} = {S(c)} * {k2(c)};")
+            w(f"        float m = a{ch[0]};")
+            for c in ch[1:]:
+                w(f"        m = fmaxf(m, a{c});")
+            for c in ch:
+                w(f"        const float q{c} = ex2(a{c} - m);")
+            w("        const float s = " + " + ".join(f"q{c}" for c in ch) + ";")
+            w("        const float lse = m + lg2(s); const float r = rcp(s);")
+            for c in ch:
+                w(f"        lp{c} = a{c} - lse; pr{c} = q{c} * r;")
+            w("      }")
+    for vv in inner_top_down:
+        for c in children[vv - C]:
+            if vv == rootv:
+                w(f"      const float LP{c} = lp{c};")
+            else:
+                w(f"      const float LP{c} = LP{vv} + lp{c};")
+    w("      float LPy = oh0 * LP0;")
+    for c in range(1, C):
+        w(f"      LPy = fmaf(oh{c}, LP{c}, LPy);")
+    w("      loss_acc += kx * (lse1 - xy) - kt * kLn2 * LPy;")
+    for c in range(C):
+        w(f"      g{c} = -kg * oh{c};")
+    w("    }")
+    w("    if (gout == nullptr) continue;")
+    # up sweep of the leaf gradients, down sweep of the accumulated logit gradient
+    for vv in inner_bottom_up:
+        w(f"    const float G{vv} = " + " + ".join(G(c) for c in children[vv - C]) + ";")
+    for vv in inner_top_down:
+        for c in children[vv - C]:
+            term = f"fmaf(-pr{c}, G{vv}, {G(c)})"
+            if vv == rootv:
+                w(f"    const float A{c} = {term}" + ("" if cnt[c] == 1 else f" * {1.0 / cnt[c]!r}f") + ";")
+            elif cnt[c] == 1:
+                w(f"    const float A{c} = A{vv} + {term};")
+            else:
+                w(f"    const float A{c} = fmaf({term}, {1.0 / cnt[c]!r}f, A{vv});")
     w(f"    float o[{C}];")
     for c in range(C):
-        w(f"    o[{c}] = A{c} + kgx * (e{c} * inv_s1 - (y == {c} ? 1.f : 0.f));")
+        w(f"    o[{c}] = fmaf(kgx, fmaf(e{c}, inv_s1, -{onehot(c)}), A{c});")
     w(f"    store_row<T, {C}>(gout + row * p.ld, o);")
     w("  }")
     w("  block_loss_reduce(loss_acc, p.loss, MODE != kSpecSoftFwd);")
@@ -211,6 +271,18 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 __device__ __forceinline__ float ex2(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 __device__ __forceinline__ float lg2(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+// exp(t) for t in [0, 1] (a class probability): degree-6 Chebyshev-node interpolant, max rel. error 1.5e-7 --
+// six FMA-pipe instructions instead of a MUFU op.
+__device__ __forceinline__ float exp01(float t) {
+  float r = 0.002307842718437314f;
+  r = fmaf(r, t, 0.0069595566019415855f);
+  r = fmaf(r, t, 0.04264117032289505f);
+  r = fmaf(r, t, 0.16631804406642914f);
+  r = fmaf(r, t, 0.5000588297843933f);
+  r = fmaf(r, t, 0.9999963045120239f);
+  return fmaf(r, t, 1.0f);
+}
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }

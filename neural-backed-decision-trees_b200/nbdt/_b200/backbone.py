@@ -37,8 +37,10 @@ def conv(x, conv_mod, residual=None):
     return ConvFunction.apply(x, conv_mod.weight, stride, residual)
 
 
-def bn_act(x, bn, relu=True, residual=None):
-    return BatchNormActFunction.apply(x, *_bn_args(bn), relu, residual)
+def bn_act(x, bn, relu=True, residual=None, want_skip=False):
+    """act(bn(x) (+ residual)).  want_skip=True returns (y, x_skip): use x_skip as the identity branch so that its
+    gradient is added inside the BN-backward kernel."""
+    return BatchNormActFunction.apply(x, *_bn_args(bn), relu, residual, want_skip)
 
 
 def conv_bn_act(x, conv_mod, bn, relu=True, residual=None):

@@ -52,7 +52,7 @@ SIGNATURES = {
     "nbdt_bn_stats": (ctypes.c_int, [c_ptr, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nbdt_bn_eval_scale": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_ptr]),
     "nbdt_bn_apply": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, ctypes.c_longlong, ctypes.c_int, c_ptr, ctypes.c_int, c_ptr]),
-    "nbdt_bn_backward": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nbdt_bn_backward": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nbdt_avgpool_fwd": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_ptr]),
     "nbdt_avgpool_bwd": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_ptr]),
     "nbdt_stem_fwd": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 5 + [c_ptr]),

@@ -53,7 +53,11 @@ class StemFunction(torch.autograd.Function):
 
 
 class ConvFunction(torch.autograd.Function):
-    """y = conv(x, weight) (+ residual) on tcgen05 tensor cores; backward = dgrad + wgrad kernels."""
+    """y = conv(x, weight) (+ residual) on tcgen05 tensor cores; backward = dgrad + wgrad kernels.
+
+    When the weight's gradient lives in a FusedSGD flat buffer (`weight._nbdt_direct_grad`), the weight-gradient
+    unpack kernel accumulates straight into it and autograd gets no weight gradient (one pass over the gradient
+    instead of unpack + autograd's accumulate)."""
 
     @staticmethod
     def forward(ctx, x, weight, stride, residual):
@@ -64,6 +68,7 @@ class ConvFunction(torch.autograd.Function):
         y = C.conv_fwd(x, wp, k, stride, residual)
         ctx.save_for_backward(x, wpt)
         ctx.meta = (tuple(weight.shape), k, stride, residual is not None)
+        ctx.direct_grad = weight.grad if getattr(weight, "_nbdt_direct_grad", False) else None
         return y
 
     @staticmethod
@@ -75,15 +80,23 @@ class ConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = C.conv_dgrad(dy, wpt, (x.shape[1], x.shape[2]), k, stride)
         if ctx.needs_input_grad[1]:
-            dw = C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride), wshape)
+            dwp = C.conv_wgrad(x, dy, k, stride)
+            if ctx.direct_grad is not None:
+                C.unpack_wgrad(dwp, wshape, out=ctx.direct_grad, accumulate=True)
+            else:
+                dw = C.unpack_wgrad(dwp, wshape)
         return dx, dw, None, (dy if has_res else None)
 
 
 class BatchNormActFunction(torch.autograd.Function):
-    """y = act(batch_norm(x) (+ residual)); training mode uses batch statistics and updates the running ones."""
+    """y = act(batch_norm(x) (+ residual)); training mode uses batch statistics and updates the running ones.
+
+    `want_skip`: also return x itself as a second output (the identity branch of a pre-activation residual unit):
+    its gradient then arrives in backward() and is added inside the BN-backward kernel instead of by a separate
+    autograd accumulation pass over the tensor."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual, want_skip=False):
         C._check_act(x, "batch norm input")
         N, H, W, Cp = x.shape
         M = N * H * W
@@ -110,24 +123,34 @@ class BatchNormActFunction(torch.autograd.Function):
             _count()
         ctx.training = training
         ctx.meta = (M, Cp, c_real, relu, residual is not None)
-        ctx.save_for_backward(x, y if relu else None, g, mean_invstd)
+        # ReLU mask in backward: recomputed from x and scale/shift (bit-identical fmaf) unless a residual was added
+        # before the activation, in which case the saved output is needed
+        mask_from_act = relu and residual is not None
+        ctx.save_for_backward(x, y if mask_from_act else None, scale_shift if (relu and not mask_from_act) else None,
+                              g, mean_invstd)
+        ctx.set_materialize_grads(False)
+        if want_skip:
+            return y, x
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         if not ctx.training:
             raise NotImplementedError("backward through eval-mode batch norm is not implemented on the B200 path")
-        x, act, g, mean_invstd = ctx.saved_tensors
+        x, act, scale_shift, g, mean_invstd = ctx.saved_tensors
         M, Cp, c_real, relu, has_res = ctx.meta
+        if dy is None:
+            return (dskip,) + (None,) * 10
         dy = dy.contiguous()
+        extra = dskip.contiguous() if dskip is not None else None
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if has_res else None
         dsums = torch.empty((L.load().nbdt_bn_scratch_floats(Cp),), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            L.check(L.load().nbdt_bn_backward(_p(x), _p(act), _p(dy), None, _p(dx), _p(dres), M, Cp, c_real, _p(g),
-                                              _p(mean_invstd), _p(dsums), _stream(x)))
+            L.check(L.load().nbdt_bn_backward(_p(x), _p(act), _p(scale_shift), _p(dy), _p(extra), _p(dx), _p(dres), M, Cp,
+                                              c_real, _p(g), _p(mean_invstd), _p(dsums), _stream(x)))
         _count(3)
-        return dx, dsums[Cp:Cp + c_real].clone(), dsums[:c_real].clone(), None, None, None, None, None, None, dres
+        return dx, dsums[Cp:Cp + c_real], dsums[:c_real], None, None, None, None, None, None, dres, None
 
 
 class AvgPoolFunction(torch.autograd.Function):

@@ -108,8 +108,9 @@ def node_outputs(tree, logits):
     return nl, pr, preds, ent, dt
 
 
-def tree_loss(tree, logits, targets, kind, w_xent, w_tree, tsw=1.0, batch_rows=0, want_grad=True):
-    """Fused loss (+ gradient w.r.t. logits).  Returns (loss fp32 scalar tensor, grad or None)."""
+def tree_loss(tree, logits, targets, kind, w_xent, w_tree, tsw=1.0, batch_rows=0, want_grad=True, out=None):
+    """Fused loss (+ gradient w.r.t. logits).  Returns (loss fp32 scalar tensor, grad or None).
+    `out` = (loss, grad) preallocated outputs (benchmarks: no allocation inside the timed region)."""
     logits, ld = _rows(logits, "tree-supervision loss")
     L.require_cuda(targets, "tree-supervision loss targets")
     dt = tree.device_tree(logits.device)
@@ -118,8 +119,11 @@ def tree_loss(tree, logits, targets, kind, w_xent, w_tree, tsw=1.0, batch_rows=0
     if targets.shape != (B,):
         raise ValueError(f"targets must have shape ({B},), got {tuple(targets.shape)}")
     targets = targets.to(device=dev, dtype=torch.int64).contiguous()
-    loss = torch.empty((), dtype=torch.float32, device=dev)
-    grad = torch.empty_strided(logits.shape, (ld, 1), dtype=logits.dtype, device=dev) if want_grad else None
+    if out is not None:
+        loss, grad = out
+    else:
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        grad = torch.empty_strided(logits.shape, (ld, 1), dtype=logits.dtype, device=dev) if want_grad else None
     lib = L.load()
     with torch.cuda.device(dev):
         if kind == "soft":

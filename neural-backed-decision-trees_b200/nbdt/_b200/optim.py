@@ -32,6 +32,7 @@ class FusedSGD(torch.optim.Optimizer):
             self.flat_param[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + n].view_as(p)
             p.grad = self.flat_grad[off:off + n].view_as(p)
+            p._nbdt_direct_grad = True  # conv weight gradients are accumulated into the flat buffer by the kernel
             off += n
         self._steps = 0
         self.grad_scale = 1.0

@@ -57,8 +57,11 @@ class PreResUnit(nn.Module):
             self.identity_conv = nn.Conv2d(cin, cout, kernel_size=1, stride=stride, bias=False)
 
     def forward(self, x):
-        a = B.bn_act(x, self.body.conv1.bn, relu=True)  # pre-activation, shared with identity_conv
-        identity = B.conv(a, self.identity_conv) if self.resize_identity else x
+        if self.resize_identity:
+            a = B.bn_act(x, self.body.conv1.bn, relu=True)  # pre-activation, shared with identity_conv
+            identity = B.conv(a, self.identity_conv)
+        else:  # the identity branch re-enters through the BN function so its gradient is fused into BN backward
+            a, identity = B.bn_act(x, self.body.conv1.bn, relu=True, want_skip=True)
         y = B.conv(a, self.body.conv1.conv)
         y = B.bn_act(y, self.body.conv2.bn, relu=True)
         return B.conv(y, self.body.conv2.conv, residual=identity)
