@@ -153,7 +153,7 @@ int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* ga
 /* Eval mode: scale_shift from the running statistics. */
 int nbdt_bn_eval_scale(int C, int c_real, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale_shift, void* stream);
-/* y = act(x*scale + shift (+ residual)), act = ReLU when relu != 0. */
+/* y = act(x*scale + shift (+ residual)); relu: activation code 0 none, 1 ReLU, 2 SiLU (SiLU: inference only). */
 int nbdt_bn_apply(const void* x, const void* residual, void* y, long long M, int C, const float* scale_shift,
                   int relu, void* stream);
 /* Backward of nbdt_bn_stats + nbdt_bn_apply.  ReLU mask of the forward pass: `act` (the forward output) when
@@ -170,11 +170,28 @@ int nbdt_avgpool_bwd(const float* dfeat, void* da, int N, int HW, int C, void* s
 /* 3-channel 3x3 stem conv: x NCHW fp32 [N,3,H,W], w fp32 [cout][3][3][3] -> y NHWC bf16 [N,H,W,c_phys]
  * (channels >= cout are written as zero); and its weight gradient. */
 int nbdt_stem_fwd(const float* x, const float* w, void* y, int N, int H, int W, int cout, int c_phys, void* stream);
+/* same with stride 1 or 2 (y [N,ceil(H/s),ceil(W/s),c_phys]): the EfficientNet stem (torchvision efficientnet.py: Conv2d(3,32,3,stride=2)). */
+int nbdt_stem_fwd_strided(const float* x, const float* w, void* y, int N, int H, int W, int cout, int c_phys, int stride,
+                          void* stream);
 int nbdt_stem_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int cout, int c_phys,
                     void* stream);
 /* Fused SGD over a flat fp32 buffer: m = momentum*m + (g*grad_scale + wd*p); p -= lr*m (first_step: m = g'). */
 int nbdt_sgd_step(float* params, const float* grads, float* momentum_buf, long long n, float lr, float momentum,
                   float weight_decay, float grad_scale, int first_step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backbone: MBConv kernels (csrc/mbconv_ops.cu) for the EfficientNet backbones the reference pulls in with
+ * `from torchvision.models import *` / `from pytorchcv.models.efficientnet import *` (nbdt/models/__init__.py:3-4).
+ * Inference path (folded BatchNorm).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Depthwise conv (groups = C) + folded BatchNorm + activation: y = act(dwconv(x; w)*scale + shift).
+ * x bf16 [N,H,W,C]; w fp32 [ksize*ksize][C] (tap-major); scale_shift fp32 [2][C] or NULL; act 0 none / 1 ReLU / 2 SiLU;
+ * y bf16 [N,ceil(H/stride),ceil(W/stride),C]; ksize in {3,5}, padding ksize/2, stride in {1,2}. */
+int nbdt_dwconv_fwd(const void* x, const float* w, const float* scale_shift, void* y, int N, int H, int W, int C,
+                    int ksize, int stride, int act, void* stream);
+/* Squeeze-excitation scaling y[n,p,c] = x[n,p,c]*s[n][c]; x, y bf16 [N][HW][C] (may alias), s fp32 [N][C]. */
+int nbdt_se_scale(const void* x, const float* s, void* y, int N, int HW, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,7 +65,7 @@ __device__ __forceinline__ void load8(const float* __restrict__ p, float (&f)[8]
 //   void init(o)                 -- load the thread's per-channel constants
 //   Pack load(row, o)            -- the global loads of one row (issued UNROLL rows at a time for memory-level parallelism)
 //   void accum(pack, acc)        -- the arithmetic
-// Each CTA writes its partial sums to out[blockIdx.x][NACC][C]; reduce_partials() adds them in a fixed order
+// Each CTA writes its partial sums to out[blockIdx.x][NACC][C]; reduce_partials2() adds them in a fixed order
 // (deterministic; same-address atomics serialise in L2).
 template <int NACC, int UNROLL, typename Op>
 __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restrict__ out, Op op) {
@@ -106,33 +106,42 @@ __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restric
   }
 }
 
-// Sum of the per-CTA partials of value index i (fixed order, fp64): a CTA of 256 threads = 32 values x 8 slices of
-// the partial list, so the chain of dependent L2 reads per thread is nparts/8 long with 4 loads in flight (the v1
-// finalize kernels read all partials from one thread per channel: ~20 us of pure latency per BatchNorm).
-// Returns the total in the threads with slice 0 (threadIdx.x < 32); `n` = values per partial.
-__device__ __forceinline__ double reduce_partials(const float* __restrict__ partials, int nparts, int n, int i) {
-  __shared__ double slices[8][33];
+// Totals of the per-CTA partials [nparts][2][C] for channel c (fixed order, fp64).  CTA = 1024 threads = 32 channels
+// (lanes) x 32 slices of the partial list (warps): a thread's chain of dependent L2 reads is nparts/64 iterations
+// with four loads in flight (the v1 finalize kernels read all partials from one thread per channel: ~20 us of pure
+// latency per BatchNorm).  The totals are returned to the threads of warp 0.
+constexpr int kFinalizeThreads = 1024;
+__device__ __forceinline__ void reduce_partials2(const float* __restrict__ partials, int nparts, int C, int c,
+                                                 double& t0, double& t1) {
+  __shared__ double slices[2][32][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  if (i < n) {
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  if (c < C) {
+    const long long n = 2LL * C;
     int b = slice;
-    for (; b + 24 < nparts; b += 32) {
-      s0 += (double)__ldg(partials + (long long)b * n + i);
-      s1 += (double)__ldg(partials + (long long)(b + 8) * n + i);
-      s2 += (double)__ldg(partials + (long long)(b + 16) * n + i);
-      s3 += (double)__ldg(partials + (long long)(b + 24) * n + i);
+    for (; b + 32 < nparts; b += 64) {
+      a0 += (double)__ldg(partials + b * n + c);
+      b0 += (double)__ldg(partials + b * n + C + c);
+      a1 += (double)__ldg(partials + (b + 32) * n + c);
+      b1 += (double)__ldg(partials + (b + 32) * n + C + c);
     }
-    for (; b < nparts; b += 8) s0 += (double)__ldg(partials + (long long)b * n + i);
+    for (; b < nparts; b += 32) {
+      a0 += (double)__ldg(partials + b * n + c);
+      b0 += (double)__ldg(partials + b * n + C + c);
+    }
   }
-  slices[slice][lane] = (s0 + s1) + (s2 + s3);
+  slices[0][slice][lane] = a0 + a1;
+  slices[1][slice][lane] = b0 + b1;
   __syncthreads();
-  double total = 0.0;
+  t0 = 0.0;
+  t1 = 0.0;
   if (slice == 0) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) total += slices[q][lane];
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+      t0 += slices[0][q][lane];
+      t1 += slices[1][q][lane];
+    }
   }
-  __syncthreads();
-  return total;
 }
 
 struct StatsOp {
@@ -152,13 +161,13 @@ struct StatsOp {
 };
 
 // partials[cta][0][c] = sum_rows x, [1][c] = sum_rows x^2.          bytes: M*C*2 read
-__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const uint4* __restrict__ x, long long M, int C,
+__global__ void __launch_bounds__(kThreads, 4) bn_stats_kernel(const uint4* __restrict__ x, long long M, int C,
                                                             float* __restrict__ partials) {
   reduce_rows<2, 8>(M, C, partials, StatsOp{x, C / 8});
 }
 
-// mean/invstd, affine scale/shift, running-stat update (momentum, unbiased variance).  grid = ceil(C/32) x 256 threads.
-__global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const float* __restrict__ partials, int nparts, long long M,
+// mean/invstd, affine scale/shift, running-stat update (momentum, unbiased variance).  grid = ceil(C/32) x 1024 threads.
+__global__ void __launch_bounds__(kFinalizeThreads) bn_finalize_kernel(const float* __restrict__ partials, int nparts, long long M,
                                                                int C, int c_real, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta,
                                                                float* __restrict__ running_mean,
@@ -166,8 +175,8 @@ __global__ void __launch_bounds__(kThreads) bn_finalize_kernel(const float* __re
                                                                float* __restrict__ mean_invstd /*[2][C]*/,
                                                                float* __restrict__ scale_shift /*[2][C]*/) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const double s0 = reduce_partials(partials, nparts, 2 * C, c < C ? c : 2 * C);
-  const double s1 = reduce_partials(partials, nparts, 2 * C, c < C ? C + c : 2 * C);
+  double s0, s1;
+  reduce_partials2(partials, nparts, C, c, s0, s1);
   if (threadIdx.x >= 32 || c >= C) return;
   if (c >= c_real) {  // zero-padded channel: stays exactly zero
     mean_invstd[c] = 0.f; mean_invstd[C + c] = 0.f; scale_shift[c] = 0.f; scale_shift[C + c] = 0.f;
@@ -220,7 +229,8 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const uint4* __restr
       for (int e = 0; e < 8; ++e) {
         float v = fmaf(f[e], sc[e], sh[e]);
         if (RES) v += r[e];
-        f[e] = relu ? fmaxf(v, 0.f) : v;
+        // activation code: 0 none, 1 ReLU, 2 SiLU (inference path of the MBConv backbones)
+        f[e] = relu == 1 ? fmaxf(v, 0.f) : (relu == 2 ? __fdividef(v, 1.f + __expf(-v)) : v);
       }
       y[rw * octets + o] = pack8(f);
     };
@@ -291,7 +301,7 @@ struct BwdReduceOp {
 // partials[cta][0][c] = sum g, [1][c] = sum g * (x - mean), with g = dy masked by the forward ReLU.
 // bytes: M*C*2 * (2 or 3) read
 template <int MASK>
-__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ act,
+__global__ void __launch_bounds__(kThreads, 4) bn_bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ act,
                                                                  const uint4* __restrict__ dy, long long M, int C,
                                                                  const float* __restrict__ mean_invstd,
                                                                  const float* __restrict__ scale_shift,
@@ -304,13 +314,13 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const uint4* __
 
 // dsums[0][c] = dbeta = sum g, dsums[1][c] = dgamma = invstd * sum g (x - mean); coef[3][C] = (k1, a, b) with
 // dx = k1*g + a*x + b:  k1 = gamma*invstd, a = -k1*invstd*dgamma/M, b = -k1*dbeta/M - a*mean.
-__global__ void __launch_bounds__(kThreads) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, long long M,
+__global__ void __launch_bounds__(kFinalizeThreads) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, long long M,
                                                                    int C, int c_real, const float* __restrict__ gamma,
                                                                    const float* __restrict__ mean_invstd,
                                                                    float* __restrict__ dsums, float* __restrict__ coef) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const double s0 = reduce_partials(partials, nparts, 2 * C, c < C ? c : 2 * C);
-  const double s1 = reduce_partials(partials, nparts, 2 * C, c < C ? C + c : 2 * C);
+  double s0, s1;
+  reduce_partials2(partials, nparts, C, c, s0, s1);
   if (threadIdx.x >= 32 || c >= C) return;
   const float mean = mean_invstd[c], invstd = mean_invstd[C + c];
   const float dbeta = (float)s0, dgamma = (float)(s1 * (double)invstd);
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_finalize_kernel(const float* 
 // dx = k1*g + a*x + b (+ extra);  optionally dres = g (masked dy).
 // bytes: M*C*2 * (2..4) read + M*C*2 * (1..2) written
 template <int MASK, bool EXTRA, bool DRES>
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ act,
+__global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ act,
                                                                 const uint4* __restrict__ dy, const uint4* __restrict__ extra,
                                                                 uint4* __restrict__ dx, uint4* __restrict__ dres,
                                                                 long long M, int C, const float* __restrict__ coef,
@@ -362,7 +372,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const uint4* __r
       dx[rw * octets + o] = pack8(out);
       if (DRES) dres[rw * octets + o] = pack8(fg);
     };
-    constexpr int U = 2;
+    // rows in flight per thread: ~8 x 16-byte loads whatever the number of tensors read
+    constexpr int U = (MASK == kMaskAct || EXTRA) ? ((MASK == kMaskAct && EXTRA) ? 2 : 3) : 4;
     const uint4 zero = make_uint4(0, 0, 0, 0);
     for (; row + (U - 1) * stride < M; row += U * stride) {
       uint4 vx[U], vg[U], va[U], ve[U];
@@ -419,17 +430,18 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dfeat, uint4* __res
 // c_phys >= cout physical channels, padding channels zero).  One thread per output pixel.
 __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        __nv_bfloat16* __restrict__ y, int N, int H, int W, int cout,
-                                                       int c_phys) {
+                                                       int c_phys, int stride) {
   extern __shared__ float ws[];  // [27][cout]
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
     const int co = i % cout, k = i / cout;  // k = ci*9 + r*3 + s
     ws[i] = w[co * 27 + k];
   }
   __syncthreads();
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= (long long)N * H * W) return;
-  const int wq = (int)(pix % W), hq = (int)((pix / W) % H);
-  const long long n = pix / ((long long)W * H);
+  if (pix >= (long long)N * Ho * Wo) return;
+  const int wq = (int)(pix % Wo) * stride, hq = (int)((pix / Wo) % Ho) * stride;
+  const long long n = pix / ((long long)Wo * Ho);
   float in[27];
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci)
@@ -465,20 +477,22 @@ __global__ void __launch_bounds__(kThreads) stem_wgrad_kernel(const float* __res
   extern __shared__ float sm[];  // patch[P][27] | g[P][cout]
   float* patch = sm;
   float* g = sm + P * 27;
-  const long long total = (long long)N * H * W;
+  // 32-bit pixel arithmetic (the launcher checks N*H*W < 2^31): the 64-bit divisions of the first version cost more
+  // than the multiply-adds (0.44 ms per step, profiles/r01_bench_launches.md)
+  const unsigned total = (unsigned)N * H * W;
   const int nout = cout * 27;
   float acc[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-  for (long long p0 = (long long)blockIdx.x * P; p0 < total; p0 += (long long)gridDim.x * P) {
+  for (unsigned p0 = blockIdx.x * P; p0 < total; p0 += gridDim.x * P) {
     __syncthreads();
     for (int i = threadIdx.x; i < P * 27; i += blockDim.x) {
       const int pp = i / 27, k = i % 27;
-      const long long pix = p0 + pp;
+      const unsigned pix = p0 + pp;
       float v = 0.f;
       if (pix < total) {
-        const int wq = (int)(pix % W), hq = (int)((pix / W) % H);
-        const long long n = pix / ((long long)W * H);
+        const int wq = (int)(pix % (unsigned)W), hq = (int)((pix / (unsigned)W) % (unsigned)H);
+        const long long n = pix / ((unsigned)W * (unsigned)H);
         const int ci = k / 9, r = (k % 9) / 3, s = k % 3;
         const int hh = hq + r - 1, ww = wq + s - 1;
         if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((n * 3 + ci) * H + hh) * W + ww);
@@ -487,8 +501,8 @@ __global__ void __launch_bounds__(kThreads) stem_wgrad_kernel(const float* __res
     }
     for (int i = threadIdx.x; i < P * cout; i += blockDim.x) {
       const int pp = i / cout, co = i % cout;
-      const long long pix = p0 + pp;
-      g[i] = pix < total ? __bfloat162float(dy[pix * c_phys + co]) : 0.f;
+      const unsigned pix = p0 + pp;
+      g[i] = pix < total ? __bfloat162float(dy[(long long)pix * c_phys + co]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -545,7 +559,7 @@ size_t reduce_smem(int C) {
   const int R = octets <= kThreads ? kThreads / octets : 1;
   return R > 1 ? (size_t)R * 2 * C * sizeof(float) : 0;
 }
-constexpr int kReduceCtasPerSm = 2;
+constexpr int kReduceCtasPerSm = 4;
 
 }  // namespace
 
@@ -561,7 +575,7 @@ int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* ga
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = rows_grid(M, C, kReduceCtasPerSm);
   bn_stats_kernel<<<grid, kThreads, reduce_smem(C), st>>>(reinterpret_cast<const uint4*>(x), M, C, sums);
-  bn_finalize_kernel<<<(C + 31) / 32, kThreads, 0, st>>>(sums, grid, M, C, c_real, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<(C + 31) / 32, kFinalizeThreads, 0, st>>>(sums, grid, M, C, c_real, gamma, beta, running_mean, running_var,
                                                          momentum, eps, mean_invstd, scale_shift);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
@@ -624,7 +638,7 @@ int nbdt_bn_backward(const void* x, const void* act, const float* scale_shift, c
     bn_bwd_reduce_kernel<kMaskRecompute><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
   else
     bn_bwd_reduce_kernel<kMaskNone><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, kThreads, 0, st>>>(partials, grid, M, C, c_real, gamma, mean_invstd, dsums, coef);
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinalizeThreads, 0, st>>>(partials, grid, M, C, c_real, gamma, mean_invstd, dsums, coef);
   const int agrid = rows_grid(M, C, 4);
 #define NBDT_BWD_APPLY(MASK, EXTRA, DRES) \
   bn_bwd_apply_kernel<MASK, EXTRA, DRES><<<agrid, kThreads, 0, st>>>(xs, as, gs, es, dxs, drs, M, C, coef, scale_shift)
@@ -663,22 +677,28 @@ int nbdt_avgpool_bwd(const float* dfeat, void* da, int N, int HW, int C, void* s
   return NBDT_OK;
 }
 
-// 3-channel 3x3 stride-1 stem: x NCHW fp32 [N,3,H,W], w fp32 [cout][3][3][3], y NHWC bf16 [N,H,W,c_phys].
-int nbdt_stem_fwd(const float* x, const float* w, void* y, int N, int H, int W, int cout, int c_phys, void* stream) {
+// 3-channel 3x3 stem (padding 1): x NCHW fp32 [N,3,H,W], w fp32 [cout][3][3][3], y NHWC bf16 [N,Ho,Wo,c_phys].
+int nbdt_stem_fwd_strided(const float* x, const float* w, void* y, int N, int H, int W, int cout, int c_phys, int stride,
+                          void* stream) {
   NBDT_REQUIRE(x && w && y, "NULL tensor");
   NBDT_REQUIRE(c_phys % 8 == 0 && c_phys >= cout && cout <= 256, "bad stem channels %d/%d", cout, c_phys);
-  const long long pix = (long long)N * H * W;
+  NBDT_REQUIRE(stride == 1 || stride == 2, "stem stride %d is not supported", stride);
+  const long long pix = (long long)N * ((H + stride - 1) / stride) * ((W + stride - 1) / stride);
   if (pix == 0) return NBDT_OK;
   stem_fwd_kernel<<<(unsigned)((pix + 127) / 128), 128, 27 * cout * sizeof(float), (cudaStream_t)stream>>>(
-      x, w, reinterpret_cast<__nv_bfloat16*>(y), N, H, W, cout, c_phys);
+      x, w, reinterpret_cast<__nv_bfloat16*>(y), N, H, W, cout, c_phys, stride);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
+}
+int nbdt_stem_fwd(const float* x, const float* w, void* y, int N, int H, int W, int cout, int c_phys, void* stream) {
+  return nbdt_stem_fwd_strided(x, w, y, N, H, W, cout, c_phys, 1, stream);
 }
 
 // dw fp32 [cout][3][3][3] (overwritten) from x NCHW fp32 and dy NHWC bf16 [N,H,W,c_phys].
 int nbdt_stem_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int cout, int c_phys, void* stream) {
   NBDT_REQUIRE(x && dy && dw, "NULL tensor");
   NBDT_REQUIRE(cout * 27 <= 8 * kThreads, "stem with %d output channels is not supported", cout);
+  NBDT_REQUIRE((long long)N * H * W < (1LL << 31) - 64 * 4096, "stem: too many pixels (%lld)", (long long)N * H * W);
   cudaStream_t st = (cudaStream_t)stream;
   NBDT_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)cout * 27 * sizeof(float), st));
   const long long pix = (long long)N * H * W;

@@ -112,7 +112,8 @@ def emit_kernel(name, C, children, root):
 
     w(f"// hierarchy {name}: {C} leaves, {N} inner nodes, max depth {max(depth[:C])}")
     w("template <typename T, int MODE>")
-    w(f"__global__ void __launch_bounds__(128, 6) {name}(const SpecParams p) {{")
+    # registers: ~8 per leaf live at the widest point; cap at 80 (6 CTAs/SM) for <= 12 leaves, 128 (4 CTAs/SM) above
+    w(f"__global__ void __launch_bounds__(128, {6 if C <= 12 else 4}) {name}(const SpecParams p) {{")
     w("  const T* __restrict__ x = reinterpret_cast<const T*>(p.x);")
     w("  T* __restrict__ gout = reinterpret_cast<T*>(p.grad);")
     w("  float loss_acc = 0.f;")

@@ -1,6 +1,7 @@
 from .resnet import *
 from .wideresnet import *
 from torchvision.models import *
+from .efficientnet import *  # B200-kernel EfficientNet-B0 replaces torchvision's eager efficientnet_b0
 
 
 def get_model_choices():

@@ -133,3 +133,20 @@ def test_resnet18_seeded_init_matches_reference():
     assert [k for k, _ in net.named_parameters()] == list(g["param_names"])
     norms = np.array([float(p.detach().double().norm()) for _, p in net.named_parameters()])
     np.testing.assert_allclose(norms, g["weight_norms_before"], rtol=1e-12)
+
+
+def test_efficientnet_b0_keeps_torchvision_layout():
+    """a18: same module tree / state_dict keys as torchvision's efficientnet_b0 (what the reference star-imports)."""
+    import torchvision
+    from nbdt.models import efficientnet_b0
+    from nbdt.models.efficientnet import EfficientNet
+
+    ours = efficientnet_b0(num_classes=1000)
+    assert isinstance(ours, EfficientNet)
+    theirs = torchvision.models.efficientnet_b0(weights=None)
+    a, b = ours.state_dict(), theirs.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    assert all(a[k].shape == b[k].shape for k in a)
+    ours.load_state_dict(b, strict=True)
+    assert sum(p.numel() for p in ours.parameters()) == 5288548
+    assert efficientnet_b0(num_classes=10).classifier[1].out_features == 10
