@@ -45,13 +45,46 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------------
+def usable_cores():
+    """Host threads the CPU arm should use: the cores this process may actually run on (affinity mask and cgroup CPU
+    quota), then a 1-second calibration -- on a box whose container is throttled below os.cpu_count() an
+    oversubscribed intra-op pool runs the convolutions ~10x slower, which would flatter the GPU arm."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    import torch.nn.functional as F
+
+    x, w = torch.randn(8, 160, 32, 32), torch.randn(160, 160, 3, 3)  # the dominant WRN-28-10 layer shape
+    best, best_t = n, None
+    cand = sorted({c for c in (n, n // 2, n // 4, 32, 16, 8) if 1 <= c <= n}, reverse=True)
+    for c in cand:
+        torch.set_num_threads(c)
+        F.conv2d(x, w, padding=1)
+        t0 = time.time()
+        for _ in range(3):
+            F.conv2d(x, w, padding=1)
+        dt = time.time() - t0
+        if best_t is None or dt < 0.9 * best_t:
+            best, best_t = c, dt
+    return best
+
+
 def cpu_reference_run(steps, warmup, batch, budget_s=120.0):
     """Returns (images/sec, cores, sample description).  Bounded: stops early past `budget_s`."""
     import torch.nn as nn
     from oracle import torch_port as P
     from oracle.tree_oracle import OracleTree
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     pkg = os.path.join(ROOT, "neural-backed-decision-trees_b200", "nbdt")
     tree = OracleTree(os.path.join(pkg, "hierarchies/CIFAR10/graph-induced-wrn28_10_cifar10.json"),

@@ -468,59 +468,51 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
   }
 }
 
-// Stem weight gradient: dw[co][k] = sum_pixels dy[pix][co] * patch[pix][k];  CTA = tile of 64 pixels staged in
-// shared memory, thread t owns outputs t, t + 256, ... of the cout*27; one atomic per output per CTA.
-__global__ void __launch_bounds__(kThreads) stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
-                                                              float* __restrict__ dw, int N, int H, int W, int cout,
-                                                              int c_phys) {
-  constexpr int P = 64;
-  extern __shared__ float sm[];  // patch[P][27] | g[P][cout]
-  float* patch = sm;
-  float* g = sm + P * 27;
-  // 32-bit pixel arithmetic (the launcher checks N*H*W < 2^31): the 64-bit divisions of the first version cost more
-  // than the multiply-adds (0.44 ms per step, profiles/r01_bench_launches.md)
+// Stem weight gradient: dw[co][k] = sum_pixels dy[pix][co] * patch[pix][k]  (k = ci*9 + r*3 + s; a 16 x 27 x #pixels GEMM
+// with a tiny output).  Thread (lane, g) walks a stream of pixels and keeps the 4 x 27 outputs of channels 4g..4g+3
+// in registers: 27 patch loads (L1-resident NCHW gathers) + one 8-byte dy load feed 108 FMAs.  A warp has one g, so
+// the end-of-kernel reduction is a shuffle tree + 108 atomics per warp.  (The first version staged 64-pixel tiles in
+// shared memory between two __syncthreads with 8 warps per SM: latency-bound, 0.4 ms per step.)
+__global__ void __launch_bounds__(128) stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                         float* __restrict__ dw, int N, int H, int W, int cout,
+                                                         int c_phys) {
+  const int lane = threadIdx.x;                         // pixel lane
+  const int co0 = (blockIdx.y * 4 + threadIdx.y) * 4;   // first of this thread's 4 output channels
+  if (co0 >= cout) return;                              // whole warp (one threadIdx.y per warp)
   const unsigned total = (unsigned)N * H * W;
-  const int nout = cout * 27;
-  float acc[8];
+  float acc[4][27];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-  for (unsigned p0 = blockIdx.x * P; p0 < total; p0 += gridDim.x * P) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < P * 27; i += blockDim.x) {
-      const int pp = i / 27, k = i % 27;
-      const unsigned pix = p0 + pp;
-      float v = 0.f;
-      if (pix < total) {
-        const int wq = (int)(pix % (unsigned)W), hq = (int)((pix / (unsigned)W) % (unsigned)H);
-        const long long n = pix / ((unsigned)W * (unsigned)H);
-        const int ci = k / 9, r = (k % 9) / 3, s = k % 3;
-        const int hh = hq + r - 1, ww = wq + s - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + ((n * 3 + ci) * H + hh) * W + ww);
-      }
-      patch[i] = v;
-    }
-    for (int i = threadIdx.x; i < P * cout; i += blockDim.x) {
-      const int pp = i / cout, co = i % cout;
-      const unsigned pix = p0 + pp;
-      g[i] = pix < total ? __bfloat162float(dy[(long long)pix * c_phys + co]) : 0.f;
-    }
-    __syncthreads();
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int o = threadIdx.x + q * kThreads;
-      if (o < nout) {
-        const int co = o / 27, k = o % 27;
-        float s = 0.f;
-        for (int pp = 0; pp < P; ++pp) s = fmaf(g[pp * cout + co], patch[pp * 27 + k], s);
-        acc[q] += s;
-      }
-    }
+    for (int k = 0; k < 27; ++k) acc[c][k] = 0.f;
+  for (unsigned pix = blockIdx.x * 32 + lane; pix < total; pix += gridDim.x * 32) {
+    const int wq = (int)(pix % (unsigned)W), hq = (int)((pix / (unsigned)W) % (unsigned)H);
+    const unsigned n = pix / ((unsigned)W * (unsigned)H);
+    const uint2 gv = __ldg(reinterpret_cast<const uint2*>(dy + (size_t)pix * c_phys + co0));
+    const float g[4] = {__uint_as_float(gv.x << 16), __uint_as_float(gv.x & 0xffff0000u),
+                        __uint_as_float(gv.y << 16), __uint_as_float(gv.y & 0xffff0000u)};
+    const float* xb = x + (size_t)n * 3 * H * W;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int hh = hq + r - 1, ww = wq + s - 1;
+          const float v = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xb + ((size_t)ci * H + hh) * W + ww) : 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[c][ci * 9 + r * 3 + s] = fmaf(g[c], v, acc[c][ci * 9 + r * 3 + s]);
+        }
   }
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int o = threadIdx.x + q * kThreads;
-    if (o < nout) atomicAdd(dw + o, acc[q]);
-  }
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      float v = acc[c][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && co0 + c < cout) atomicAdd(dw + (co0 + c) * 27 + k, v);
+    }
 }
 
 // p -= lr * (m = momentum*m + g + wd*p)   (torch.optim.SGD, dampening 0, no nesterov; first step m = g + wd*p)
@@ -703,9 +695,10 @@ int nbdt_stem_wgrad(const float* x, const void* dy, float* dw, int N, int H, int
   NBDT_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)cout * 27 * sizeof(float), st));
   const long long pix = (long long)N * H * W;
   if (pix == 0) return NBDT_OK;
-  const int grid = (int)std::min<long long>((pix + 63) / 64, (long long)sm_count() * 4);
-  stem_wgrad_kernel<<<grid, kThreads, (64 * 27 + 64 * cout) * sizeof(float), st>>>(
-      x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, N, H, W, cout, c_phys);
+  NBDT_REQUIRE(c_phys % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7) == 0, "stem wgrad: dy must be 8-byte aligned");
+  const int gx = (int)std::min<long long>((pix + 31) / 32, (long long)sm_count() * 4);
+  stem_wgrad_kernel<<<dim3(gx, (cout + 15) / 16), dim3(32, 4), 0, st>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, N,
+                                                                         H, W, cout, c_phys);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }

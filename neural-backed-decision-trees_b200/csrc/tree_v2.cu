@@ -45,7 +45,9 @@ struct TreeV2 {
   const int4* node;        // [N] BFS order: {first edge, parent edge (-1: root), #children, unused}
   const unsigned* be;      // [S] per edge: beg | end << 16  (DFS leaf positions of the child's subtree)
   const float* inv;        // [S] 1 / #leaves under the child
-  const int* level_ptr;    // [D+1] into the BFS node order
+  const int* level_ptr;    // [D+1] into the BFS EDGE order (edges of depth d+1 are consecutive)
+  const int* eparent;      // [S] edge that ends in the edge's parent node (-1: child of the root)
+  const unsigned* pbe;     // [S] beg | end << 16 of the edge's PARENT node
   const int* class_pos;    // [C] DFS position of class c
   const int* class_edge;   // [C] edge that ends in the leaf of class c
   const int* pos_edge;     // [C] edge that ends in the leaf at DFS position i
@@ -62,6 +64,8 @@ struct Tab {
   const unsigned* be;
   const float* inv;
   const int* level_ptr;
+  const int* eparent;
+  const unsigned* pbe;
   const int* class_pos;
   const int* class_edge;
   const int* pos_edge;
@@ -120,7 +124,7 @@ template <int G, typename V> __device__ __forceinline__ V group_exclusive_scan(V
 
 // G lanes per row, EPT = ceil(C / G) elements per lane (compile-time bound), MODE = kSpec{SoftLoss,HardLoss,SoftFwd}.
 template <int G, int EPT, int MODE, typename T>
-__global__ void __launch_bounds__(256) tree_v2_kernel(const V2Params q) {
+__global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Tab& t = q.t;
   const SpecParams& p = q.p;
@@ -187,76 +191,79 @@ __global__ void __launch_bounds__(256) tree_v2_kernel(const V2Params q) {
 
     // ---- 2. fp64 prefix sums over the DFS-ordered logits: PS[i] = sum of positions < i ----
     {
-      double local[EPT];
+      // two passes over the lane's positions (sum, then running prefix) instead of EPT fp64 registers
       double run = 0.0;
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
         const int i = j * per + k;
         if (k < per && i < C) run += (double)P[i];
-        local[k] = run;
       }
-      const double off = group_exclusive_scan<G, double>(run, j);
-      __syncwarp();  // every lane has read its staged logits before P is overwritten below
+      double acc = group_exclusive_scan<G, double>(run, j);
+      if (j == 0) PS[0] = 0.0;
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
         const int i = j * per + k;
-        if (k < per && i < C) PS[i + 1] = local[k] + off;
+        if (k < per && i < C) {
+          acc += (double)P[i];
+          PS[i + 1] = acc;
+        }
       }
-      if (j == 0) PS[0] = 0.0;
     }
     __syncwarp();
 
-    // ---- 3. top-down over the levels: child probabilities and path probabilities ----
-    for (int d = 0; d < t.D; ++d) {
-      const int n1 = __ldg(t.level_ptr + d + 1);
-      for (int n = __ldg(t.level_ptr + d) + j; n < n1; n += G) {
-        const int4 nd = __ldg(t.node + n);
-        const int e0 = nd.x, K = nd.z;
-        float base;  // path probability (soft) / log2 path probability (hard) of this node
-        if (MODE == kSpecHardLoss) base = nd.y < 0 ? 0.f : P[nd.y];
-        else base = nd.y < 0 ? 1.f : P[nd.y];
-        if (K == 2) {
-          const unsigned be0 = __ldg(t.be + e0), be1 = __ldg(t.be + e0 + 1);
-          const double p0 = PS[be0 & 0xffffu], p1 = PS[be0 >> 16], p2 = PS[be1 >> 16];
-          const float a0 = (float)(p1 - p0) * (__ldg(t.inv + e0) * kLog2e);
-          const float a1 = (float)(p2 - p1) * (__ldg(t.inv + e0 + 1) * kLog2e);
-          const float dlt = a0 - a1;
-          const float tt = ex2(-fabsf(dlt));
-          const float rr = rcp(1.f + tt), lo = tt * rr;
-          const bool first = dlt >= 0.f;
-          pr[e0] = first ? rr : lo;
-          pr[e0 + 1] = first ? lo : rr;
-          if (MODE == kSpecHardLoss) {
-            const float l = -lg2(1.f + tt), ll = l - fabsf(dlt);
-            P[e0] = base + (first ? l : ll);
-            P[e0 + 1] = base + (first ? ll : l);
-          } else {
-            P[e0] = base * (first ? rr : lo);
-            P[e0 + 1] = base * (first ? lo : rr);
-          }
-        } else {
-          float mx = -INFINITY;
-          for (int e = e0; e < e0 + K; ++e) {
-            const unsigned b = __ldg(t.be + e);
-            const float a = (float)(PS[b >> 16] - PS[b & 0xffffu]) * (__ldg(t.inv + e) * kLog2e);
-            pr[e] = a;
-            mx = fmaxf(mx, a);
-          }
-          float s = 0.f;
-          for (int e = e0; e < e0 + K; ++e) {
-            const float ee = ex2(pr[e] - mx);
-            if (MODE == kSpecHardLoss) P[e] = pr[e] - mx;  // a - max, completed below
-            pr[e] = ee;
-            s += ee;
-          }
-          const float rs = rcp(s), ls = lg2(s);
-          for (int e = e0; e < e0 + K; ++e) {
-            const float pe = pr[e] * rs;
-            pr[e] = pe;
-            if (MODE == kSpecHardLoss) P[e] = base + (P[e] - ls);
-            else P[e] = base * pe;
-          }
+    // ---- 3a. child softmax of every inner node (no dependency between nodes: no synchronisation, the loop
+    //          iterations overlap).  pr[e] = child probability; hard loss: P[e] = log2 child probability ----
+#pragma unroll 2
+    for (int n = j; n < t.N; n += G) {
+      const int4 nd = __ldg(t.node + n);
+      const int e0 = nd.x, K = nd.z;
+      if (K == 2) {
+        const unsigned be0 = __ldg(t.be + e0), be1 = __ldg(t.be + e0 + 1);
+        const double p0 = PS[be0 & 0xffffu], p1 = PS[be0 >> 16], p2 = PS[be1 >> 16];
+        const float a0 = (float)(p1 - p0) * (__ldg(t.inv + e0) * kLog2e);
+        const float a1 = (float)(p2 - p1) * (__ldg(t.inv + e0 + 1) * kLog2e);
+        const float dlt = a0 - a1;
+        const float tt = ex2(-fabsf(dlt));
+        const float rr = rcp(1.f + tt), lo = tt * rr;
+        const bool first = dlt >= 0.f;
+        pr[e0] = first ? rr : lo;
+        pr[e0 + 1] = first ? lo : rr;
+        if (MODE == kSpecHardLoss) {
+          const float l = -lg2(1.f + tt), ll = l - fabsf(dlt);
+          P[e0] = first ? l : ll;
+          P[e0 + 1] = first ? ll : l;
         }
+      } else {
+        float mx = -INFINITY;
+        for (int e = e0; e < e0 + K; ++e) {
+          const unsigned b = __ldg(t.be + e);
+          const float a = (float)(PS[b >> 16] - PS[b & 0xffffu]) * (__ldg(t.inv + e) * kLog2e);
+          pr[e] = a;
+          mx = fmaxf(mx, a);
+        }
+        float sum = 0.f;
+        for (int e = e0; e < e0 + K; ++e) {
+          const float a = pr[e] - mx;
+          const float ee = ex2(a);
+          if (MODE == kSpecHardLoss) P[e] = a;  // completed with -lg2(sum) below
+          pr[e] = ee;
+          sum += ee;
+        }
+        const float rs = rcp(sum), ls = lg2(sum);
+        for (int e = e0; e < e0 + K; ++e) {
+          pr[e] *= rs;
+          if (MODE == kSpecHardLoss) P[e] -= ls;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- 3b. path (log-)probabilities, one level of edges at a time: P[e] = P[parent edge] (*|+) child value ----
+    for (int d = 0; d < t.D; ++d) {
+      const int e1 = __ldg(t.level_ptr + d + 1);
+      for (int e = __ldg(t.level_ptr + d) + j; e < e1; e += G) {
+        const int ep = __ldg(t.eparent + e);
+        if (MODE == kSpecHardLoss) P[e] = (ep < 0 ? 0.f : P[ep]) + P[e];
+        else P[e] = (ep < 0 ? 1.f : P[ep]) * pr[e];
       }
       __syncwarp();
     }
@@ -318,24 +325,28 @@ __global__ void __launch_bounds__(256) tree_v2_kernel(const V2Params q) {
     }
     __syncwarp();
 
-    // ---- 5. top-down again: A[e] = A[parent] + (G[e] - pr[e] * G[node]) / #leaves(e)  (A overwrites P) ----
+    // ---- 5a. per-edge gradient term t[e] = (G[e] - pr[e] * G[parent node]) / #leaves(e), G = range sums of the leaf
+    //          gradients (prefix-sum differences); independent per edge, overwrites pr[e] ----
+#pragma unroll 2
+    for (int e = j; e < S; e += G) {
+      const unsigned b = __ldg(t.be + e), pb = __ldg(t.pbe + e);
+      float Ge, Gn;
+      if (MODE == kSpecSoftLoss) {
+        Ge = PG[b >> 16] - PG[b & 0xffffu];
+        Gn = PG[pb >> 16] - PG[pb & 0xffffu];
+      } else {
+        Ge = ((int)(b & 0xffffu) <= pos_y && pos_y < (int)(b >> 16)) ? -kg : 0.f;
+        Gn = ((int)(pb & 0xffffu) <= pos_y && pos_y < (int)(pb >> 16)) ? -kg : 0.f;
+      }
+      pr[e] = fmaf(-pr[e], Gn, Ge) * __ldg(t.inv + e);
+    }
+    __syncwarp();
+    // ---- 5b. A[e] = A[parent edge] + t[e], one level of edges at a time (A overwrites P) ----
     for (int d = 0; d < t.D; ++d) {
-      const int n1 = __ldg(t.level_ptr + d + 1);
-      for (int n = __ldg(t.level_ptr + d) + j; n < n1; n += G) {
-        const int4 nd = __ldg(t.node + n);
-        const int e0 = nd.x, K = nd.z;
-        const float An = nd.y < 0 ? 0.f : P[nd.y];
-        const unsigned bfirst = __ldg(t.be + e0), blast = __ldg(t.be + e0 + K - 1);
-        float Gn;
-        if (MODE == kSpecSoftLoss) Gn = PG[blast >> 16] - PG[bfirst & 0xffffu];
-        else Gn = ((int)(bfirst & 0xffffu) <= pos_y && pos_y < (int)(blast >> 16)) ? -kg : 0.f;
-        for (int e = e0; e < e0 + K; ++e) {
-          const unsigned b = __ldg(t.be + e);
-          float Ge;
-          if (MODE == kSpecSoftLoss) Ge = PG[b >> 16] - PG[b & 0xffffu];
-          else Ge = ((int)(b & 0xffffu) <= pos_y && pos_y < (int)(b >> 16)) ? -kg : 0.f;
-          P[e] = fmaf(fmaf(-pr[e], Gn, Ge), __ldg(t.inv + e), An);
-        }
+      const int e1 = __ldg(t.level_ptr + d + 1);
+      for (int e = __ldg(t.level_ptr + d) + j; e < e1; e += G) {
+        const int ep = __ldg(t.eparent + e);
+        P[e] = (ep < 0 ? 0.f : P[ep]) + pr[e];
       }
       __syncwarp();
     }
@@ -442,16 +453,15 @@ int tree_v2_create(const nbdt_tree_desc* d, int device, int sm_count, int max_sm
       }
     }
   }
-  // BFS numbering of the inner nodes, consecutive edges per node
-  std::vector<int> bfs, depth(N, 0), level_ptr, parent_edge(N, -1);
+  // BFS numbering of the inner nodes, consecutive edges per node; BFS order makes the edges of one depth consecutive
+  std::vector<int> bfs, depth(N, 0), parent_edge(N, -1);
   bfs.push_back(d->root);
   std::vector<int4> node;
-  std::vector<unsigned> be;
+  std::vector<unsigned> be, pbe;
   std::vector<float> inv;
-  std::vector<int> class_edge(C, 0), pos_edge(C, 0);
+  std::vector<int> class_edge(C, 0), pos_edge(C, 0), eparent, edepth;
   for (size_t qi = 0; qi < bfs.size(); ++qi) {
     const int i = bfs[qi];
-    if (level_ptr.empty() || depth[i] + 1 > (int)level_ptr.size()) level_ptr.push_back((int)qi);
     const int e0 = (int)be.size();
     const int K = d->child_ptr[i + 1] - d->child_ptr[i];
     node.push_back(make_int4(e0, parent_edge[i], K, 0));
@@ -459,7 +469,10 @@ int tree_v2_create(const nbdt_tree_desc* d, int device, int sm_count, int max_sm
       const int ch = d->child_node[k];
       const int e = (int)be.size();
       be.push_back((unsigned)beg[ch] | ((unsigned)end[ch] << 16));
+      pbe.push_back((unsigned)beg[C + i] | ((unsigned)end[C + i] << 16));
       inv.push_back(1.0f / (float)(end[ch] - beg[ch]));
+      eparent.push_back(parent_edge[i]);
+      edepth.push_back(depth[i]);
       if (ch < C) {
         class_edge[ch] = e;
         pos_edge[class_pos[ch]] = e;
@@ -471,8 +484,11 @@ int tree_v2_create(const nbdt_tree_desc* d, int device, int sm_count, int max_sm
     }
   }
   if ((int)bfs.size() != N || (int)be.size() != S) return NBDT_OK;  // malformed: tree.cu has already validated; be safe
+  std::vector<int> level_ptr;  // edges grouped by the depth of their parent node (non-decreasing in BFS order)
+  for (int e = 0; e < S; ++e)
+    if (e == 0 || edepth[e] != edepth[e - 1]) level_ptr.push_back(e);
   const int D = (int)level_ptr.size();
-  level_ptr.push_back(N);
+  level_ptr.push_back(S);
 
   TreeV2* t = new (std::nothrow) TreeV2();
   NBDT_REQUIRE(t != nullptr, "out of host memory");
@@ -484,7 +500,9 @@ int tree_v2_create(const nbdt_tree_desc* d, int device, int sm_count, int max_sm
   const size_t o_be = align16(o_node + node.size() * sizeof(int4));
   const size_t o_inv = align16(o_be + be.size() * 4);
   const size_t o_lvl = align16(o_inv + inv.size() * 4);
-  const size_t o_cpos = align16(o_lvl + level_ptr.size() * 4);
+  const size_t o_epar = align16(o_lvl + level_ptr.size() * 4);
+  const size_t o_pbe = align16(o_epar + eparent.size() * 4);
+  const size_t o_cpos = align16(o_pbe + pbe.size() * 4);
   const size_t o_cedge = align16(o_cpos + class_pos.size() * 4);
   const size_t o_pedge = align16(o_cedge + class_edge.size() * 4);
   const size_t bytes = align16(o_pedge + pos_edge.size() * 4);
@@ -493,6 +511,8 @@ int tree_v2_create(const nbdt_tree_desc* d, int device, int sm_count, int max_sm
   memcpy(host.data() + o_be, be.data(), be.size() * 4);
   memcpy(host.data() + o_inv, inv.data(), inv.size() * 4);
   memcpy(host.data() + o_lvl, level_ptr.data(), level_ptr.size() * 4);
+  memcpy(host.data() + o_epar, eparent.data(), eparent.size() * 4);
+  memcpy(host.data() + o_pbe, pbe.data(), pbe.size() * 4);
   memcpy(host.data() + o_cpos, class_pos.data(), class_pos.size() * 4);
   memcpy(host.data() + o_cedge, class_edge.data(), class_edge.size() * 4);
   memcpy(host.data() + o_pedge, pos_edge.data(), pos_edge.size() * 4);
@@ -513,6 +533,8 @@ int tree_v2_create(const nbdt_tree_desc* d, int device, int sm_count, int max_sm
   t->be = reinterpret_cast<const unsigned*>(base + o_be);
   t->inv = reinterpret_cast<const float*>(base + o_inv);
   t->level_ptr = reinterpret_cast<const int*>(base + o_lvl);
+  t->eparent = reinterpret_cast<const int*>(base + o_epar);
+  t->pbe = reinterpret_cast<const unsigned*>(base + o_pbe);
   t->class_pos = reinterpret_cast<const int*>(base + o_cpos);
   t->class_edge = reinterpret_cast<const int*>(base + o_cedge);
   t->pos_edge = reinterpret_cast<const int*>(base + o_pedge);
@@ -536,6 +558,7 @@ int tree_v2_launch(const TreeV2* t, int mode, int dtype, const SpecParams& p, vo
   if (!t) return -1;
   V2Params q;
   q.t.node = t->node; q.t.be = t->be; q.t.inv = t->inv; q.t.level_ptr = t->level_ptr;
+  q.t.eparent = t->eparent; q.t.pbe = t->pbe;
   q.t.class_pos = t->class_pos; q.t.class_edge = t->class_edge; q.t.pos_edge = t->pos_edge;
   q.t.C = t->C; q.t.N = t->N; q.t.S = t->S; q.t.D = t->D;
   q.p = p;

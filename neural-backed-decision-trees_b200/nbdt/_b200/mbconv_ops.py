@@ -56,11 +56,12 @@ def folded_scale_shift(bn, c_phys):
     def build():
         dev = bn.weight.device
         ss = torch.empty((2, c_phys), dtype=torch.float32, device=dev)
+        # keep the padded copies alive across the launch (a temporary's storage would be recycled for the next one)
+        g, b = _pad_vec(bn.weight, c_phys, 1.0), _pad_vec(bn.bias, c_phys)
+        rm, rv = _pad_vec(bn.running_mean, c_phys), _pad_vec(bn.running_var, c_phys, 1.0)
         with torch.cuda.device(dev):
-            L.check(L.load().nbdt_bn_eval_scale(c_phys, bn.num_features, _p(_pad_vec(bn.weight, c_phys, 1.0)),
-                                                _p(_pad_vec(bn.bias, c_phys)), _p(_pad_vec(bn.running_mean, c_phys)),
-                                                _p(_pad_vec(bn.running_var, c_phys, 1.0)), float(bn.eps), _p(ss),
-                                                L.stream_ptr(dev)))
+            L.check(L.load().nbdt_bn_eval_scale(c_phys, bn.num_features, _p(g), _p(b), _p(rm), _p(rv), float(bn.eps),
+                                                _p(ss), L.stream_ptr(dev)))
         _count()
         return ss
     return cached(bn, f"ss{c_phys}", (bn.weight, bn.bias, bn.running_mean, bn.running_var), build)
