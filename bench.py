@@ -392,14 +392,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-    if world == 1 and args.gpus > 1:
+    if args.impl == "b200" and world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    # Exactly ONE line on stdout: libraries that write to fd 1 from C (NCCL prints its version banner there when
+    # NCCL_DEBUG is set) are sent to stderr for the whole run; the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
     run_b200(args, rank, world, local_rank)
 
 

@@ -55,7 +55,9 @@ struct TreeV2 {
 
 namespace {
 
-constexpr int kMaxLeaves = 1024;
+// Measured (profiles/r01_tree_sweep_v6.jsonl): 15-25 % faster than the first-generation kernel at 100-200 leaves, 20 % slower
+// at 1000 (one row per warp, 24 KB of shared memory per row): used up to 512 leaves.
+constexpr int kMaxLeaves = 512;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -125,7 +127,11 @@ template <int G, typename V> __device__ __forceinline__ V group_exclusive_scan(V
 // G lanes per row, EPT = ceil(C / G) elements per lane (compile-time bound), MODE = kSpec{SoftLoss,HardLoss,SoftFwd}.
 template <int G, int EPT, int MODE, typename T>
 __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // Rows are addressed as integer offsets into the __shared__ array (not through per-row generic pointers): the
+  // compiler then emits plain LDS/STS with 32-bit offsets instead of re-deriving the shared window base for every
+  // predicated access (profiles/r01_tree_v2_ncu.md).
+  extern __shared__ __align__(16) float smf[];
+  double* const smd = reinterpret_cast<double*>(smf);
   const Tab& t = q.t;
   const SpecParams& p = q.p;
   constexpr int RPW = 32 / G;
@@ -133,11 +139,12 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
   const int r = lane / G, j = lane % G;
   const int C = t.C, S = t.S;
   // row layout: [PS: (C+1) doubles][P: S floats][pr: S floats]  (row_floats includes the doubles as 2 floats each)
-  float* rowbase = reinterpret_cast<float*>(smem_raw) + (size_t)(warp * RPW + r) * q.row_floats;
-  double* PS = reinterpret_cast<double*>(rowbase);
-  float* PG = rowbase;                    // gradient prefix sums reuse the PS storage
-  float* P = rowbase + 2 * (C + 1);       // staging for the logits, then path (log-)probabilities, then A
-  float* pr = P + S;
+  const int ro = (warp * RPW + r) * q.row_floats;  // even: the fp64 prefix sums stay 8-byte aligned
+  const int oP = ro + 2 * (C + 1), oR = oP + S;
+#define PS_(i) smd[(ro >> 1) + (i)]   /* fp64 prefix sums of the DFS-ordered logits */
+#define PG_(i) smf[ro + (i)]          /* fp32 gradient prefix sums (reuse the PS storage) */
+#define P_(i) smf[oP + (i)]           /* staging for the logits, then path (log-)probabilities, then A */
+#define PR_(i) smf[oR + (i)]          /* child probabilities, then the per-edge gradient terms */
   const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
   T* __restrict__ gout = reinterpret_cast<T*>(p.grad);
   const int per = (C + G - 1) / G;        // positions owned by one lane in the scans: [j*per, min(C, (j+1)*per))
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
       float v = 0.f;
       if (c < C) {
         if (valid) v = to_f<T>(xr[c]);
-        P[__ldg(t.class_pos + c)] = v;
+        P_(__ldg(t.class_pos + c)) = v;
         m1 = fmaxf(m1, v);
       }
       ev[k] = v;
@@ -189,81 +196,81 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
     }
     __syncwarp();
 
-    // ---- 2. fp64 prefix sums over the DFS-ordered logits: PS[i] = sum of positions < i ----
+    // ---- 2. fp64 prefix sums over the DFS-ordered logits: PS_(i) = sum of positions < i ----
     {
       // two passes over the lane's positions (sum, then running prefix) instead of EPT fp64 registers
       double run = 0.0;
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
         const int i = j * per + k;
-        if (k < per && i < C) run += (double)P[i];
+        if (k < per && i < C) run += (double)P_(i);
       }
       double acc = group_exclusive_scan<G, double>(run, j);
-      if (j == 0) PS[0] = 0.0;
+      if (j == 0) PS_(0) = 0.0;
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
         const int i = j * per + k;
         if (k < per && i < C) {
-          acc += (double)P[i];
-          PS[i + 1] = acc;
+          acc += (double)P_(i);
+          PS_(i + 1) = acc;
         }
       }
     }
     __syncwarp();
 
     // ---- 3a. child softmax of every inner node (no dependency between nodes: no synchronisation, the loop
-    //          iterations overlap).  pr[e] = child probability; hard loss: P[e] = log2 child probability ----
+    //          iterations overlap).  PR_(e) = child probability; hard loss: P_(e) = log2 child probability ----
 #pragma unroll 2
     for (int n = j; n < t.N; n += G) {
       const int4 nd = __ldg(t.node + n);
       const int e0 = nd.x, K = nd.z;
       if (K == 2) {
         const unsigned be0 = __ldg(t.be + e0), be1 = __ldg(t.be + e0 + 1);
-        const double p0 = PS[be0 & 0xffffu], p1 = PS[be0 >> 16], p2 = PS[be1 >> 16];
+        const double p0 = PS_(be0 & 0xffffu), p1 = PS_(be0 >> 16), p2 = PS_(be1 >> 16);
         const float a0 = (float)(p1 - p0) * (__ldg(t.inv + e0) * kLog2e);
         const float a1 = (float)(p2 - p1) * (__ldg(t.inv + e0 + 1) * kLog2e);
         const float dlt = a0 - a1;
         const float tt = ex2(-fabsf(dlt));
         const float rr = rcp(1.f + tt), lo = tt * rr;
         const bool first = dlt >= 0.f;
-        pr[e0] = first ? rr : lo;
-        pr[e0 + 1] = first ? lo : rr;
+        PR_(e0) = first ? rr : lo;
+        PR_(e0 + 1) = first ? lo : rr;
         if (MODE == kSpecHardLoss) {
           const float l = -lg2(1.f + tt), ll = l - fabsf(dlt);
-          P[e0] = first ? l : ll;
-          P[e0 + 1] = first ? ll : l;
+          P_(e0) = first ? l : ll;
+          P_(e0 + 1) = first ? ll : l;
         }
       } else {
         float mx = -INFINITY;
         for (int e = e0; e < e0 + K; ++e) {
           const unsigned b = __ldg(t.be + e);
-          const float a = (float)(PS[b >> 16] - PS[b & 0xffffu]) * (__ldg(t.inv + e) * kLog2e);
-          pr[e] = a;
+          const float a = (float)(PS_(b >> 16) - PS_(b & 0xffffu)) * (__ldg(t.inv + e) * kLog2e);
+          PR_(e) = a;
           mx = fmaxf(mx, a);
         }
         float sum = 0.f;
         for (int e = e0; e < e0 + K; ++e) {
-          const float a = pr[e] - mx;
+          const float a = PR_(e) - mx;
           const float ee = ex2(a);
-          if (MODE == kSpecHardLoss) P[e] = a;  // completed with -lg2(sum) below
-          pr[e] = ee;
+          if (MODE == kSpecHardLoss) P_(e) = a;  // completed with -lg2(sum) below
+          PR_(e) = ee;
           sum += ee;
         }
         const float rs = rcp(sum), ls = lg2(sum);
         for (int e = e0; e < e0 + K; ++e) {
-          pr[e] *= rs;
-          if (MODE == kSpecHardLoss) P[e] -= ls;
+          PR_(e) *= rs;
+          if (MODE == kSpecHardLoss) P_(e) -= ls;
         }
       }
     }
     __syncwarp();
-    // ---- 3b. path (log-)probabilities, one level of edges at a time: P[e] = P[parent edge] (*|+) child value ----
+    // ---- 3b. path (log-)probabilities, one level of edges at a time: P_(e) = P_(parent edge) (*|+) child value ----
     for (int d = 0; d < t.D; ++d) {
       const int e1 = __ldg(t.level_ptr + d + 1);
       for (int e = __ldg(t.level_ptr + d) + j; e < e1; e += G) {
         const int ep = __ldg(t.eparent + e);
-        if (MODE == kSpecHardLoss) P[e] = (ep < 0 ? 0.f : P[ep]) + P[e];
-        else P[e] = (ep < 0 ? 1.f : P[ep]) * pr[e];
+        if (MODE == kSpecHardLoss) P_(e) = (ep < 0 ? 0.f : P_(ep)) + P_(e);
+        else P_(e) = (ep < 0 ? 1.f : P_(ep)) * PR_(e);
       }
       __syncwarp();
     }
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
         const int c = j + k * G;
-        if (c < C && valid) p.class_probs[row * C + c] = P[__ldg(t.class_edge + c)];
+        if (c < C && valid) p.class_probs[row * C + c] = P_(__ldg(t.class_edge + c));
       }
       __syncwarp();
       continue;
@@ -288,7 +295,7 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
         const int i = j * per + k;
         float pv = 0.f, qv = 0.f;
         if (k < per && i < C) {
-          pv = P[__ldg(t.pos_edge + i)];
+          pv = P_(__ldg(t.pos_edge + i));
           qv = exp01(pv);
           if (i == pos_y) py = pv;
         }
@@ -311,11 +318,11 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
 #pragma unroll
       for (int k = 0; k < EPT; ++k) {
         const int i = j * per + k;
-        if (k < per && i < C) PG[i + 1] = pl[k] + off;
+        if (k < per && i < C) PG_(i + 1) = pl[k] + off;
       }
-      if (j == 0) PG[0] = 0.f;
+      if (j == 0) PG_(0) = 0.f;
     } else {  // hard loss: tree term = -log(path probability of the target's leaf)
-      const float lpy = P[__ldg(t.class_edge + y)];
+      const float lpy = P_(__ldg(t.class_edge + y));
       row_loss = kx * (lse1 - xy) - kt * kLn2 * lpy;
     }
     if (j == 0 && valid) loss_acc += row_loss;
@@ -325,20 +332,20 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
     }
     __syncwarp();
 
-    // ---- 5a. per-edge gradient term t[e] = (G[e] - pr[e] * G[parent node]) / #leaves(e), G = range sums of the leaf
-    //          gradients (prefix-sum differences); independent per edge, overwrites pr[e] ----
+    // ---- 5a. per-edge gradient term t[e] = (G[e] - PR_(e) * G[parent node]) / #leaves(e), G = range sums of the leaf
+    //          gradients (prefix-sum differences); independent per edge, overwrites PR_(e) ----
 #pragma unroll 2
     for (int e = j; e < S; e += G) {
       const unsigned b = __ldg(t.be + e), pb = __ldg(t.pbe + e);
       float Ge, Gn;
       if (MODE == kSpecSoftLoss) {
-        Ge = PG[b >> 16] - PG[b & 0xffffu];
-        Gn = PG[pb >> 16] - PG[pb & 0xffffu];
+        Ge = PG_(b >> 16) - PG_(b & 0xffffu);
+        Gn = PG_(pb >> 16) - PG_(pb & 0xffffu);
       } else {
         Ge = ((int)(b & 0xffffu) <= pos_y && pos_y < (int)(b >> 16)) ? -kg : 0.f;
         Gn = ((int)(pb & 0xffffu) <= pos_y && pos_y < (int)(pb >> 16)) ? -kg : 0.f;
       }
-      pr[e] = fmaf(-pr[e], Gn, Ge) * __ldg(t.inv + e);
+      PR_(e) = fmaf(-PR_(e), Gn, Ge) * __ldg(t.inv + e);
     }
     __syncwarp();
     // ---- 5b. A[e] = A[parent edge] + t[e], one level of edges at a time (A overwrites P) ----
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
       const int e1 = __ldg(t.level_ptr + d + 1);
       for (int e = __ldg(t.level_ptr + d) + j; e < e1; e += G) {
         const int ep = __ldg(t.eparent + e);
-        P[e] = (ep < 0 ? 0.f : P[ep]) + pr[e];
+        P_(e) = (ep < 0 ? 0.f : P_(ep)) + PR_(e);
       }
       __syncwarp();
     }
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
     for (int k = 0; k < EPT; ++k) {
       const int c = j + k * G;
       if (c < C && valid)
-        gout[row * p.ld + c] = from_f<T>(fmaf(kgx, fmaf(ev[k], inv_s1, c == y ? -1.f : 0.f), P[__ldg(t.class_edge + c)]));
+        gout[row * p.ld + c] = from_f<T>(fmaf(kgx, fmaf(ev[k], inv_s1, c == y ? -1.f : 0.f), P_(__ldg(t.class_edge + c))));
     }
     __syncwarp();
   }
@@ -375,6 +382,10 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
     }
   }
 }
+#undef PS_
+#undef PG_
+#undef P_
+#undef PR_
 
 template <int G, int EPT, int MODE, typename T>
 int launch_cfg(const TreeV2* t, const V2Params& q, cudaStream_t stream) {
@@ -407,8 +418,7 @@ int launch_mode(const TreeV2* t, const V2Params& q, cudaStream_t stream) {
   if (C <= 64) return launch_cfg<4, 16, MODE, T>(t, q, stream);
   if (C <= 128) return launch_cfg<8, 16, MODE, T>(t, q, stream);
   if (C <= 256) return launch_cfg<16, 16, MODE, T>(t, q, stream);
-  if (C <= 512) return launch_cfg<32, 16, MODE, T>(t, q, stream);
-  return launch_cfg<32, 32, MODE, T>(t, q, stream);
+  return launch_cfg<32, 16, MODE, T>(t, q, stream);
 }
 
 template <typename T>

@@ -197,3 +197,51 @@ def coerce_tensor(x, is_label=False):
 def uncoerce_tensor(x, original_shape):
     n, c, h, w = original_shape
     return x.reshape(n, h, w, c).permute(0, 3, 1, 2)
+
+
+def load_image_from_path(path):
+    """PIL image from a local path or an http(s) URL (reference: nbdt/utils.py:100-110)."""
+    import io
+    from urllib.request import Request, urlopen
+
+    from PIL import Image
+
+    if "http" in path:
+        request = Request(path, headers={"User-Agent": "Mozilla/5.0 (nbdt-b200)"})
+        return Image.open(io.BytesIO(urlopen(request).read()))
+    return Image.open(path)
+
+
+def get_mean_and_std(dataset):
+    """Per-channel mean and std of a dataset of (image tensor, label) pairs (reference: nbdt/utils.py:139-156:
+    the mean over the samples of each image's per-channel mean / std)."""
+    import torch
+
+    loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=0)
+    mean, std, n = torch.zeros(3), torch.zeros(3), 0
+    for inputs, _ in loader:
+        for i in range(3):
+            mean[i] += inputs[:, i, :, :].mean()
+            std[i] += inputs[:, i, :, :].std()
+        n += 1
+    return mean / max(n, 1), std / max(n, 1)
+
+
+def init_params(net):
+    """Kaiming / constant / small-normal initialisation of conv / batch-norm / linear layers
+    (reference: nbdt/utils.py:159-172)."""
+    import torch.nn as nn
+    import torch.nn.init as init
+
+    for m in net.modules():
+        if isinstance(m, nn.Conv2d):
+            init.kaiming_normal_(m.weight, mode="fan_out")
+            if m.bias is not None:
+                init.constant_(m.bias, 0)
+        elif isinstance(m, nn.BatchNorm2d):
+            init.constant_(m.weight, 1)
+            init.constant_(m.bias, 0)
+        elif isinstance(m, nn.Linear):
+            init.normal_(m.weight, std=1e-3)
+            if m.bias is not None:
+                init.constant_(m.bias, 0)
