@@ -274,6 +274,235 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant: two CTAs (one cluster, one TPC) work on two neighbouring 128-pixel tiles with ONE
+// tcgen05.mma.cta_group::2 of M = 256 per K step.  Each CTA stages its own A tile and only HALF of the weight tile
+// (the tensor core reads B's N columns half from each CTA's shared memory), so a (tap, k-block) unit costs
+// 16 KB + BLOCK_N/2 x 128 B of TMA fill per SM instead of 16 KB + BLOCK_N x 128 B: 26 KB instead of 36 KB at
+// BLOCK_N = 160.  ncu had the single-CTA kernel at 59-71 % l1tex / 14-20 TB/s of L2->SM traffic with the tensor pipe
+// only 41 % busy on the 160-channel layers (profiles/r01_conv_ncu.md): shared-memory fill was the limiter.
+//
+// Protocol: the leader (even) CTA's elected thread issues every MMA.  "Stage full" lives in the leader: both CTAs' TMA
+// loads complete_tx on it (expect_tx = both halves).  "Stage empty" and "accumulator full" are multicast by
+// tcgen05.commit to both CTAs; "accumulator empty" is counted in the leader (4 epilogue warps x 2 CTAs).
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct TapGemm2Cfg {
+  static constexpr int kUnits = 2;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;  // this CTA's half of the weight tile
+  static constexpr int kUnitBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = kUnits * kUnitBytes;
+  static constexpr int kStages = (216 * 1024) / kStageBytes > 6 ? 6 : (216 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static_assert(kUnitBytes % 1024 == 0 && kABytes % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+tap_gemm2_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constant__ CUtensorMap tm_in1,
+                 const __grid_constant__ CUtensorMap tm_in2, const __grid_constant__ CUtensorMap tm_in3,
+                 const __grid_constant__ CUtensorMap tm_w, const TapGemmParams p) {
+  using Cfg = TapGemm2Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                         // [kStages]  (used in the leader CTA only)
+  uint64_t* empty = bars + Cfg::kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]        (used in the leader CTA only)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int total_pairs = m_pairs * p.n_tiles;   // pair tile -> (m pair, n tile), n fastest
+  const int units = p.num_taps * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_in0);
+    prefetch_tmap(&tm_w);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full[a]), 1);
+      mbar_init(smem_u32(&tmem_empty[a]), 8);  // 4 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  cluster_sync();  // barriers of both CTAs are initialised before anyone signals across the pair
+  if (warp == 1) {
+    tmem2_alloc(smem_u32(tmem_base_slot), Cfg::kTmemCols);
+    tmem2_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+
+  // this CTA's 128-pixel tile of pair tile `pt`
+  auto tile_origin = [&](int pt, int& n_tile, int& w0, int& h0, int& n0) {
+    n_tile = pt % p.n_tiles;
+    int m = (pt / p.n_tiles) * 2 + (int)rank;
+    w0 = (m % p.tiles_w) * p.box_w;
+    m /= p.tiles_w;
+    h0 = (m % p.tiles_h) * p.box_h;
+    n0 = (m / p.tiles_h) * p.box_n;  // >= N_img for the odd tile out: TMA zero fill, no stores
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    const bool leader_lane = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = pair; pt < total_pairs; pt += num_pairs) {
+      int n_tile, w0, h0, n0;
+      tile_origin(pt, n_tile, w0, h0, n0);
+      int t = 0, kb = 0;
+      for (int u = 0; u < units; u += Cfg::kUnits) {
+        const int nu = min(Cfg::kUnits, units - u);
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t bar = full0 + 8 * stage;  // same offset in the leader
+        const uint32_t dst = smem_base + stage * Cfg::kStageBytes;
+        if (leader_lane && rank == 0) mbar_expect_tx(bar, 2 * nu * Cfg::kUnitBytes);
+#pragma unroll
+        for (int j = 0; j < Cfg::kUnits; ++j) {
+          if (j < nu) {
+            const int map = p.tap_map[t];
+            const CUtensorMap* tm = map == 0 ? &tm_in0 : (map == 1 ? &tm_in1 : (map == 2 ? &tm_in2 : &tm_in3));
+            if (leader_lane) {
+              tma2_load_4d(dst + j * Cfg::kUnitBytes, tm, bar, kb * kBlockK, w0 + p.tap_dw[t], h0 + p.tap_dh[t], n0);
+              tma2_load_2d(dst + j * Cfg::kUnitBytes + Cfg::kABytes, &tm_w, bar, kb * kBlockK,
+                           p.tap_wrow[t] + n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
+            }
+            if (++kb == p.kblocks) { kb = 0; ++t; }
+          }
+        }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      const bool leader_lane = elect_one();
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, BLOCK_N, 0, 0);
+      const uint64_t desc0 = make_smem_desc(smem_base, 16, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int pt = pair; pt < total_pairs; pt += num_pairs) {
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        int kb = 0;
+        uint32_t accumulate = 0;
+        for (int u = 0; u < units; u += Cfg::kUnits) {
+          const int nu = min(Cfg::kUnits, units - u);
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t sdesc = desc0 + (uint64_t)((stage * Cfg::kStageBytes) >> 4);
+#pragma unroll
+          for (int j = 0; j < Cfg::kUnits; ++j) {
+            if (j < nu) {
+              const int ksteps = (kb == p.kblocks - 1) ? p.last_ksteps : kBlockK / 16;
+              const uint64_t adesc = sdesc + (uint64_t)((j * Cfg::kUnitBytes) >> 4);
+              const uint64_t bdesc = adesc + (uint64_t)(Cfg::kABytes >> 4);
+              if (leader_lane) {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  if (k < ksteps) umma2_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              accumulate = 1;
+              if (++kb == p.kblocks) kb = 0;
+            }
+          }
+          if (leader_lane) umma2_commit(empty0 + 8 * stage);  // frees the stage in both CTAs
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (leader_lane) umma2_commit(smem_u32(&tmem_full[acc]));  // accumulator ready in both CTAs
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs; each CTA holds its own 128 rows) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pt = pair; pt < total_pairs; pt += num_pairs) {
+      int n_tile, w0, h0, n0;
+      tile_origin(pt, n_tile, w0, h0, n0);
+      const int pw = w0 + row % p.box_w;
+      const int ph = h0 + (row / p.box_w) % p.box_h;
+      const int pn = n0 + row / (p.box_w * p.box_h);
+      const bool in_range = pw < p.W_out && ph < p.H_out && pn < p.N_img;
+      const long long off = pn * p.out_sn + ph * p.out_sh + pw * p.out_sw + (long long)n_tile * BLOCK_N;
+
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (in_range) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
+          const uint4* res = p.residual ? reinterpret_cast<const uint4*>(p.residual + off + c0) : nullptr;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+            if (res) {
+              const uint4 r = res[q];  // plain load: residual may alias out (in-place accumulate)
+              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+                f[2 * e] += __bfloat162float(b.x);
+                f[2 * e + 1] += __bfloat162float(b.y);
+              }
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              o[e] = *reinterpret_cast<const uint32_t*>(&b);
+            }
+            dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(smem_u32(&tmem_empty[acc]));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();  // no CTA may exit (or free TMEM) while its peer still reads its shared memory / signals its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem2_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -381,6 +610,31 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
     if (int rc = make_tmap(&tm_w, wpack, 2, dims, strides, box)) return rc;
   }
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  // CTA-pair kernel (cta_group::2) when there is at least one pair tile per SM pair; NBDT_B200_CONV_PAIR=0 disables it
+  static const bool pair_enabled = !(getenv("NBDT_B200_CONV_PAIR") && atoi(getenv("NBDT_B200_CONV_PAIR")) == 0);
+  const int total_pairs = ((p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2) * p.n_tiles;
+  if (pair_enabled && p.exp == 0 && total_pairs >= info.sm_count / 2) {
+    CUtensorMap tm_w2;
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)w_rows};
+      cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+      cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(block_n / 2)};
+      if (int rc = make_tmap(&tm_w2, wpack, 2, dims, strides, box)) return rc;
+    }
+    const int grid2 = std::min(total_pairs, info.sm_count / 2) * 2;
+#define NBDT_LAUNCH_TAP2(BN)                                                                                    \
+  {                                                                                                             \
+    auto kern = tap_gemm2_kernel<BN>;                                                                           \
+    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemm2Cfg<BN>::kSmemBytes)); \
+    kern<<<grid2, 192, TapGemm2Cfg<BN>::kSmemBytes, stream>>>(tm_in[0], tm_in[1], tm_in[2], tm_in[3], tm_w2, p); \
+  }
+    if (block_n == 160) NBDT_LAUNCH_TAP2(160)
+    else if (block_n == 128) NBDT_LAUNCH_TAP2(128)
+    else NBDT_LAUNCH_TAP2(64)
+#undef NBDT_LAUNCH_TAP2
+    NBDT_CUDA_OK(cudaGetLastError());
+    return NBDT_OK;
+  }
   const int grid = std::min(total_tiles, info.sm_count);
 #define NBDT_LAUNCH_TAP(BN)                                                                                     \
   {                                                                                                             \
