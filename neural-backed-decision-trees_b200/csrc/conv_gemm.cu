@@ -53,6 +53,10 @@ struct TapGemmParams {
   int tap_dw[kMaxTaps];
   int tap_wrow[kMaxTaps];  // first row of this tap's [Cout x Cin] slice in the packed weight matrix
   int exp;  // perf experiments only (env NBDT_B200_CONV_EXP): 1 skip B loads, 2 skip A loads, 4 skip stores, 8 one MMA per stage
+  // H-halo pair kernel (tap_gemm2h_kernel): the 9 taps as 3 column groups (same dw) of 3 taps (dh = -1, 0, +1 in any order)
+  int grp_dw[3];
+  int grp_dh[3][3];
+  int grp_wrow[3][3];
 };
 
 // One pipeline stage holds kUnits consecutive (tap, 64-channel k-block) units: the MMA thread's per-stage
@@ -503,6 +507,222 @@ tap_gemm2_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair kernel with H-halo activation tiles (stride-1 3x3 convolutions on maps 16 or 32 pixels wide).
+// The three taps of a filter COLUMN (same dw, dh = -1 / 0 / +1) read the same pixels shifted by whole image rows, and a
+// 128-pixel tile is box_w x box_h pixels of ONE image: a tile with one halo row above and below
+// ({64 ch x box_w x (box_h + 2)} box, zero-filled outside the image) holds all three views as row ranges starting
+// (1 + dh) * box_w pixel rows into it -- for a K-major operand a pixel is one 128-byte row, and the tensor core
+// un-swizzles by absolute address, so the A descriptor simply starts there.  One stage = one (column, k-block) unit:
+// 24 KB of activations + 3 half weight tiles (30 KB at BLOCK_N = 160) for 12 MMAs = 57 B per tensor-pipe cycle per SM,
+// against 83 B/cycle for tap_gemm2_kernel (which ran at the 12 TB/s L2->SM limit, not at the tensor pipe's).
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct TapGemm2hCfg {
+  static constexpr int kAHaloBytes = 192 * 128;                // 32 x (4+2) or 16 x (8+2) pixel rows of 64 channels
+  static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;  // this CTA's half of one tap's weight tile
+  static constexpr int kStageBytes = kAHaloBytes + 3 * kBBytes;
+  static constexpr int kStages = (216 * 1024) / kStageBytes > 6 ? 6 : (216 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(kStageBytes % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+tap_gemm2h_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
+                  const TapGemmParams p) {
+  using Cfg = TapGemm2hCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                         // [kStages]  (leader CTA only)
+  uint64_t* empty = bars + Cfg::kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]        (leader CTA only)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int total_pairs = m_pairs * p.n_tiles;
+  const int units = 3 * p.kblocks;               // (column group, k-block), group-major
+  const uint32_t a_tx = (uint32_t)(p.box_w * (p.box_h + 2) * 128);  // bytes of one halo box
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_in);
+    prefetch_tmap(&tm_w);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full[a]), 1);
+      mbar_init(smem_u32(&tmem_empty[a]), 8);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync();
+  if (warp == 1) {
+    tmem2_alloc(smem_u32(tmem_base_slot), Cfg::kTmemCols);
+    tmem2_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+
+  auto tile_origin = [&](int pt, int& n_tile, int& w0, int& h0, int& n0) {
+    n_tile = pt % p.n_tiles;
+    int m = (pt / p.n_tiles) * 2 + (int)rank;
+    w0 = (m % p.tiles_w) * p.box_w;
+    m /= p.tiles_w;
+    h0 = (m % p.tiles_h) * p.box_h;
+    n0 = m / p.tiles_h;  // box_n == 1; >= N_img for the odd tile out: TMA zero fill, no stores
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    const bool leader_lane = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = pair; pt < total_pairs; pt += num_pairs) {
+      int n_tile, w0, h0, n0;
+      tile_origin(pt, n_tile, w0, h0, n0);
+      int g = 0, kb = 0;
+      for (int u = 0; u < units; ++u) {
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t bar = full0 + 8 * stage;
+        const uint32_t dst = smem_base + stage * Cfg::kStageBytes;
+        if (leader_lane && rank == 0) mbar_expect_tx(bar, 2 * (a_tx + 3 * Cfg::kBBytes));
+        if (leader_lane) {
+          tma2_load_4d(dst, &tm_in, bar, kb * kBlockK, w0 + p.grp_dw[g], h0 - 1, n0);
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+            tma2_load_2d(dst + Cfg::kAHaloBytes + r * Cfg::kBBytes, &tm_w, bar, kb * kBlockK,
+                         p.grp_wrow[g][r] + n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
+        }
+        if (++kb == p.kblocks) { kb = 0; ++g; }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      const bool leader_lane = elect_one();
+      constexpr uint32_t idesc = make_idesc_bf16(2 * kBlockM, BLOCK_N, 0, 0);
+      const uint64_t desc0 = make_smem_desc(smem_base, 16, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int pt = pair; pt < total_pairs; pt += num_pairs) {
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        int g = 0, kb = 0;
+        uint32_t accumulate = 0;
+        for (int u = 0; u < units; ++u) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t sdesc = desc0 + (uint64_t)((stage * Cfg::kStageBytes) >> 4);
+          const int ksteps = (kb == p.kblocks - 1) ? p.last_ksteps : kBlockK / 16;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            // tap (dh, dw_g): its 128 pixel rows start (1 + dh) * box_w rows into the halo tile (128 B = 8 descriptor units per row)
+            const uint64_t adesc = sdesc + (uint64_t)((1 + p.grp_dh[g][r]) * p.box_w * 8);
+            const uint64_t bdesc = sdesc + (uint64_t)((Cfg::kAHaloBytes + r * Cfg::kBBytes) >> 4);
+            if (leader_lane) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                if (k < ksteps) umma2_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            accumulate = 1;
+          }
+          if (leader_lane) umma2_commit(empty0 + 8 * stage);
+          if (++kb == p.kblocks) { kb = 0; ++g; }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (leader_lane) umma2_commit(smem_u32(&tmem_full[acc]));
+        __syncwarp();
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pt = pair; pt < total_pairs; pt += num_pairs) {
+      int n_tile, w0, h0, n0;
+      tile_origin(pt, n_tile, w0, h0, n0);
+      const int pw = w0 + row % p.box_w;
+      const int ph = h0 + row / p.box_w;
+      const int pn = n0;
+      const bool in_range = pw < p.W_out && ph < p.H_out && pn < p.N_img;
+      const long long off = pn * p.out_sn + ph * p.out_sh + pw * p.out_sw + (long long)n_tile * BLOCK_N;
+
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        if (in_range) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
+          const uint4* res = p.residual ? reinterpret_cast<const uint4*>(p.residual + off + c0) : nullptr;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+            if (res) {
+              const uint4 rv = res[q];  // plain load: residual may alias out (in-place accumulate)
+              const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&rw[e]);
+                f[2 * e] += __bfloat162float(b.x);
+                f[2 * e + 1] += __bfloat162float(b.y);
+              }
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 b = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              o[e] = *reinterpret_cast<const uint32_t*>(&b);
+            }
+            dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(smem_u32(&tmem_empty[acc]));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem2_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -613,6 +833,49 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
   // CTA-pair kernel (cta_group::2) when there is at least one pair tile per SM pair; NBDT_B200_CONV_PAIR=0 disables it
   static const bool pair_enabled = !(getenv("NBDT_B200_CONV_PAIR") && atoi(getenv("NBDT_B200_CONV_PAIR")) == 0);
   const int total_pairs = ((p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2) * p.n_tiles;
+  // H-halo variant: 3x3 taps on ONE dense view, tiles = box_w x box_h pixels of one image with box_w in {16, 32}
+  bool halo = pair_enabled && p.exp == 0 && total_pairs >= info.sm_count / 2 && num_taps == 9 && num_views == 1 &&
+              p.box_n == 1 && (p.box_w == 16 || p.box_w == 32) && p.box_w * (p.box_h + 2) <= 192 &&
+              !getenv("NBDT_B200_CONV_NOHALO");
+  if (halo) {  // group the taps by dw; every group must hold dh = -1, 0, +1
+    int ng = 0, cnt[3] = {0, 0, 0};
+    for (int t = 0; t < num_taps && halo; ++t) {
+      int g = 0;
+      while (g < ng && p.grp_dw[g] != taps[t].dw) ++g;
+      if (g == ng) {
+        if (ng == 3) { halo = false; break; }
+        p.grp_dw[ng++] = taps[t].dw;
+      }
+      if (cnt[g] == 3 || taps[t].dh < -1 || taps[t].dh > 1 || taps[t].map != 0) { halo = false; break; }
+      p.grp_dh[g][cnt[g]] = taps[t].dh;
+      p.grp_wrow[g][cnt[g]] = taps[t].wrow;
+      ++cnt[g];
+    }
+    halo = halo && ng == 3 && cnt[0] == 3 && cnt[1] == 3 && cnt[2] == 3;
+  }
+  if (halo) {
+    CUtensorMap tm_a, tm_w2;
+    if (int rc = view_tmap(&tm_a, in_views[0], p.box_w, p.box_h + 2, 1)) return rc;
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)w_rows};
+      cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+      cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)(block_n / 2)};
+      if (int rc = make_tmap(&tm_w2, wpack, 2, dims, strides, box)) return rc;
+    }
+    const int grid2 = std::min(total_pairs, info.sm_count / 2) * 2;
+#define NBDT_LAUNCH_TAP2H(BN)                                                                                   \
+  {                                                                                                             \
+    auto kern = tap_gemm2h_kernel<BN>;                                                                          \
+    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TapGemm2hCfg<BN>::kSmemBytes)); \
+    kern<<<grid2, 192, TapGemm2hCfg<BN>::kSmemBytes, stream>>>(tm_a, tm_w2, p);                                  \
+  }
+    if (block_n == 160) NBDT_LAUNCH_TAP2H(160)
+    else if (block_n == 128) NBDT_LAUNCH_TAP2H(128)
+    else NBDT_LAUNCH_TAP2H(64)
+#undef NBDT_LAUNCH_TAP2H
+    NBDT_CUDA_OK(cudaGetLastError());
+    return NBDT_OK;
+  }
   if (pair_enabled && p.exp == 0 && total_pairs >= info.sm_count / 2) {
     CUtensorMap tm_w2;
     {
@@ -684,6 +947,7 @@ struct WgradParams {
   int pix_blocks;                    // total KPIX-pixel blocks = tiles_w * tiles_h * tiles_n
   int range_len;                     // pixel blocks per range (divides pix_blocks)
   int teams;                         // > 0: team mode with this many pixel ranges (see wgrad_kernel); 0: stream-K
+  int stage_tx_bytes;                // halo mode: TMA bytes per stage (dy tile + the halo boxes, without the atom padding)
   int tiles_w, tiles_h;              // pixel-block grid inside one image (box_n images per block when the image is small)
   int box_w, box_h, box_n;
   int Cout, Cin;
@@ -695,13 +959,28 @@ struct WgradParams {
 
 // TAPS taps that share the dy tile are accumulated side by side in TMEM (TAPS x BLOCK_N columns), so one
 // stage = 1 dy tile + TAPS shifted x tiles carries TAPS * KPIX/16 MMAs per barrier handshake.
-template <int BLOCK_N, int TAPS, int KPIX>
+// HALO (stride-1 3x3 convs on maps at least 16 pixels wide): the three taps of a filter row are the same pixels
+// shifted by -1 / 0 / +1 along W, so ONE x tile with a one-pixel halo on each side ({64 ch x (box_w+2) x box_h}
+// boxes, zero-filled outside the image) serves all three -- the MMA descriptors of tap dw start (1 + dw) pixel rows
+// into the tile (a pixel is one 128-byte row of an MN-major tile; the descriptor's base-offset field carries the
+// start row's phase inside the 8-row swizzle atom).  TMA fill per 32-pixel k-block: 8 KB + 3 x 34 x 128 B = 21 KB
+// instead of 8 + 3 x 12 = 44 KB.  The kernel ran at the L2->SM limit (11.7 TB/s, profiles/r01_conv_ncu.md).
+// The tensor core un-swizzles by ABSOLUTE shared-memory address bits, so a descriptor may start at any 128-byte row of a
+// TMA-written tile with base offset 0 (verified on B200; setting the base-offset field to the row phase is wrong here).
+// HALO == 2 (maps narrower than 16 pixels: 8x8, 4x4): the taps of a filter COLUMN are shifts along H; a tile with a
+// one-row halo above and below ({64 ch x box_w x (box_h+2)} boxes) serves the three of them at row offsets (1+dh)*box_w
+// -- 8 + 3 x 48 x 128 B = 26 KB per k-block.
+template <int BLOCK_N, int TAPS, int KPIX, int HALO = 0>
 struct WgradCfg {
   static constexpr int kChunkBytes = KPIX * 128;                   // KPIX pixels x 64 channels bf16
   static constexpr int kAChunks = 2;                               // M = 128 channels of dy
   static constexpr int kBChunks = (BLOCK_N + 63) / 64;
+  // mode 1: (32+2) x 1 or (16+2) x 2 pixel rows padded to 8-row atoms; mode 2: 8 x (4+2) or 2 x 4 x (4+2) pixel rows
+  static constexpr int kHaloRows = HALO == 2 ? 48 : 40;
+  static constexpr int kHaloChunkBytes = kHaloRows * 128;
   static constexpr int kTapBytes = kBChunks * kChunkBytes;
-  static constexpr int kStageBytes = kAChunks * kChunkBytes + TAPS * kTapBytes;
+  static constexpr int kBBytes = HALO ? kBChunks * kHaloChunkBytes : TAPS * kTapBytes;
+  static constexpr int kStageBytes = kAChunks * kChunkBytes + kBBytes;
   static constexpr int kStages = (208 * 1024) / kStageBytes > 8 ? 8 : (208 * 1024) / kStageBytes;
   static constexpr int kAccCols = TAPS * BLOCK_N;
   static constexpr int kNumAcc = (2 * kAccCols <= 512) ? 2 : 1;    // double-buffer the accumulators when they fit
@@ -709,14 +988,16 @@ struct WgradCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
   static_assert(kStages >= 2, "stage too large");
+  static_assert(!HALO || (TAPS == 3 && KPIX == 32), "halo tiles are for the three taps of a 3x3 filter row");
+  static_assert(kStageBytes % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
 };
 
-template <int BLOCK_N, int TAPS, int KPIX>
+template <int BLOCK_N, int TAPS, int KPIX, int HALO>
 __global__ void __launch_bounds__(224, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x0,
              const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
              const __grid_constant__ CUtensorMap tm_x3, const WgradParams p) {
-  using Cfg = WgradCfg<BLOCK_N, TAPS, KPIX>;
+  using Cfg = WgradCfg<BLOCK_N, TAPS, KPIX, HALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -729,6 +1010,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_items = p.tap_groups * p.m_tiles * p.n_tiles;
+  // j-th tap of a group: filter row `group` (taps along W) except in H-halo mode, where a group is a filter column
+  auto tap_of = [](int group, int j) { return HALO == 2 ? j * 3 + group : group * TAPS + j; };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_dy);
@@ -818,13 +1101,26 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
         const uint32_t dst = smem_base + stage * Cfg::kStageBytes;
         const uint32_t bar = full0 + 8 * stage;
         if (leader && first) {
-          mbar_expect_tx(bar, Cfg::kStageBytes);
+          mbar_expect_tx(bar, HALO ? p.stage_tx_bytes : Cfg::kStageBytes);
 #pragma unroll
           for (int c = 0; c < Cfg::kAChunks; ++c)
             tma_load_4d(dst + c * Cfg::kChunkBytes, &tm_dy, bar, m_tile * kBlockM + c * 64, w0, h0, n0);
+          if (HALO == 1) {  // one halo tile for the whole tap row: box {64, box_w + 2, box_h, box_n} from (w0 - 1, h0 + dh)
+#pragma unroll
+            for (int c = 0; c < Cfg::kBChunks; ++c)
+              tma_load_4d(dst + Cfg::kAChunks * Cfg::kChunkBytes + c * Cfg::kHaloChunkBytes, &tm_x0, bar,
+                          n_tile * BLOCK_N + c * 64, w0 - 1, h0 + p.tap_dh[tap_of(group, 0)], n0);
+          }
+          if (HALO == 2) {  // tap column: box {64, box_w, box_h + 2, box_n} from (w0 + dw, h0 - 1)
+#pragma unroll
+            for (int c = 0; c < Cfg::kBChunks; ++c)
+              tma_load_4d(dst + Cfg::kAChunks * Cfg::kChunkBytes + c * Cfg::kHaloChunkBytes, &tm_x0, bar,
+                          n_tile * BLOCK_N + c * 64, w0 + p.tap_dw[tap_of(group, 0)], h0 - 1, n0);
+          }
         }
 #pragma unroll
         for (int j = 0; j < TAPS; ++j) {
+          if (HALO) continue;
           if ((j == 0) != first) continue;
           const int tap = group * TAPS + j;
           const int map = p.tap_map[tap];
@@ -844,6 +1140,23 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 1, 1);  // both operands MN-major
     // MN-major tiles: LBO = distance between 64-channel chunks, SBO = 1024 B between 8-pixel groups
     const uint64_t desc0 = make_smem_desc(smem_base, Cfg::kChunkBytes, 1024);
+    // halo mode: B descriptors (chunk stride = padded halo tile) + per (tap, K step) start row inside the tile
+    const uint64_t descb0 = make_smem_desc(smem_base + Cfg::kAChunks * Cfg::kChunkBytes, Cfg::kHaloChunkBytes, 1024);
+    uint64_t bdelta[TAPS][KPIX / 16];
+#pragma unroll
+    for (int j = 0; j < TAPS; ++j)
+#pragma unroll
+      for (int k = 0; k < KPIX / 16; ++k) {
+        const int pix = k * 16;  // first pixel of the K step, in box order (w fastest, then h, then n)
+        int row;
+        if (HALO == 2) {
+          const int per_img = p.box_w * p.box_h;
+          row = (pix / per_img) * p.box_w * (p.box_h + 2) + ((pix % per_img) / p.box_w + j) * p.box_w + pix % p.box_w;
+        } else {
+          row = (pix / p.box_w) * (p.box_w + 2) + (pix % p.box_w) + 1 + (j - 1);
+        }
+        bdelta[j][k] = (uint64_t)(row * 8);  // + row * 128 bytes on the start address, base offset 0 (see above)
+      }
     int stage = 0;
     uint32_t phase = 0;
     int item_idx = 0;
@@ -864,10 +1177,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < TAPS; ++j) {
             const uint64_t bdesc = adesc + (uint64_t)((Cfg::kAChunks * Cfg::kChunkBytes + j * Cfg::kTapBytes) >> 4);
+            const uint64_t hdesc = descb0 + (uint64_t)((stage * Cfg::kStageBytes) >> 4);
 #pragma unroll
             for (int k = 0; k < KPIX / 16; ++k) {
               // K=16 pixels = two 8-pixel swizzle atoms = 2048 bytes (128 descriptor units)
-              umma_bf16(tmem_d + j * BLOCK_N, adesc + 128 * k, bdesc + 128 * k, idesc, (k > 0) ? 1u : accumulate);
+              umma_bf16(tmem_d + j * BLOCK_N, adesc + 128 * k, HALO ? hdesc + bdelta[j][k] : bdesc + 128 * k, idesc,
+                        (k > 0) ? 1u : accumulate);
             }
           }
           umma_commit(empty0 + 8 * stage);
@@ -893,7 +1208,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * Cfg::kAccCols;
 #pragma unroll 1
       for (int j = 0; j < TAPS; ++j) {
-        const int tap = group * TAPS + j;
+        const int tap = tap_of(group, j);
         float* dst = p.dw + ((long long)tap * p.Cout + co) * p.Cin + n_tile * BLOCK_N;
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -1121,20 +1436,42 @@ int nbdt_conv2d_wgrad(const void* x, const void* dy, float* dwp, int N, int H, i
   }
   for (int v = 0; v < 4; ++v)
     if (int rc = view_tmap(&tm_x[v], xviews[v < nv ? v : 0], p.box_w, p.box_h, p.box_n)) return rc;
-#define NBDT_LAUNCH_WG(BN, TP, KP)                                                                              \
-  {                                                                                                             \
-    auto kern = wgrad_kernel<BN, TP, KP>;                                                                       \
-    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<BN, TP, KP>::kSmemBytes)); \
-    kern<<<grid, 224, WgradCfg<BN, TP, KP>::kSmemBytes, st>>>(tm_dy, tm_x[0], tm_x[1], tm_x[2], tm_x[3], p);     \
+  // halo tiles for stride-1 3x3: mode 1 when the pixel boxes are whole 16-pixel runs of an image row, mode 2 (tap columns)
+  // for narrower maps whose box holds 16 or 32 pixels of one image
+  int halo = 0;
+  if (taps_per_group == 3 && stride == 1 && !getenv("NBDT_B200_WGRAD_NOHALO")) {
+    if (p.box_w == 16 || p.box_w == 32) halo = 1;
+    else if (p.box_w * p.box_h * p.box_n == 32 && (p.box_w * p.box_h) % 16 == 0 && p.box_w * (p.box_h + 2) * p.box_n <= 48) halo = 2;
   }
-  if (taps_per_group == 3) {
-    if (block_n == 160) NBDT_LAUNCH_WG(160, 3, 32)
-    else if (block_n == 128) NBDT_LAUNCH_WG(128, 3, 32)
-    else NBDT_LAUNCH_WG(64, 3, 32)
+  if (halo == 1) {
+    if (int rc = view_tmap(&tm_x[0], xviews[0], p.box_w + 2, p.box_h, p.box_n)) return rc;
+    p.stage_tx_bytes = 2 * kpix * 128 + ((block_n + 63) / 64) * (p.box_w + 2) * p.box_h * p.box_n * 128;
+  } else if (halo == 2) {
+    if (int rc = view_tmap(&tm_x[0], xviews[0], p.box_w, p.box_h + 2, p.box_n)) return rc;
+    p.stage_tx_bytes = 2 * kpix * 128 + ((block_n + 63) / 64) * p.box_w * (p.box_h + 2) * p.box_n * 128;
+  }
+#define NBDT_LAUNCH_WG(BN, TP, KP, HL)                                                                          \
+  {                                                                                                             \
+    auto kern = wgrad_kernel<BN, TP, KP, HL>;                                                                   \
+    NBDT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WgradCfg<BN, TP, KP, HL>::kSmemBytes)); \
+    kern<<<grid, 224, WgradCfg<BN, TP, KP, HL>::kSmemBytes, st>>>(tm_dy, tm_x[0], tm_x[1], tm_x[2], tm_x[3], p); \
+  }
+  if (halo == 1) {
+    if (block_n == 160) NBDT_LAUNCH_WG(160, 3, 32, 1)
+    else if (block_n == 128) NBDT_LAUNCH_WG(128, 3, 32, 1)
+    else NBDT_LAUNCH_WG(64, 3, 32, 1)
+  } else if (halo == 2) {
+    if (block_n == 160) NBDT_LAUNCH_WG(160, 3, 32, 2)
+    else if (block_n == 128) NBDT_LAUNCH_WG(128, 3, 32, 2)
+    else NBDT_LAUNCH_WG(64, 3, 32, 2)
+  } else if (taps_per_group == 3) {
+    if (block_n == 160) NBDT_LAUNCH_WG(160, 3, 32, 0)
+    else if (block_n == 128) NBDT_LAUNCH_WG(128, 3, 32, 0)
+    else NBDT_LAUNCH_WG(64, 3, 32, 0)
   } else {
-    if (block_n == 160) NBDT_LAUNCH_WG(160, 1, 64)
-    else if (block_n == 128) NBDT_LAUNCH_WG(128, 1, 64)
-    else NBDT_LAUNCH_WG(64, 1, 64)
+    if (block_n == 160) NBDT_LAUNCH_WG(160, 1, 64, 0)
+    else if (block_n == 128) NBDT_LAUNCH_WG(128, 1, 64, 0)
+    else NBDT_LAUNCH_WG(64, 1, 64, 0)
   }
 #undef NBDT_LAUNCH_WG
   NBDT_CUDA_OK(cudaGetLastError());
