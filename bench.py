@@ -204,7 +204,7 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch  # per GPU (weak scaling)
-    from nbdt._b200 import conv_ops
+    from nbdt._b200 import conv_ops, nn_ops
     from nbdt._b200.optim import FusedSGD
 
     torch.manual_seed(0)
@@ -235,6 +235,7 @@ def run_b200(args, rank, world, local_rank):
             e1.record()
             tree_ev.append((e0, e1))
         loss.backward()
+        nn_ops.join_wgrad_streams(dev)  # weight-gradient kernels run on a side stream: join before capture ends / SGD
         return loss
 
     def finish():

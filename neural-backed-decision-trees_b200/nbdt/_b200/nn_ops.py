@@ -1,6 +1,8 @@
 """Autograd functions of the B200 backbone: every forward/backward is a hand-written kernel behind the
 C ABI (csrc/conv_gemm.cu, csrc/bn_ops.cu).  Activations are NHWC bf16 tensors (N, H, W, C); parameters stay
 fp32 `nn.Parameter`s in their PyTorch layouts, so state_dicts, optimizers and checkpoints are unchanged."""
+import os
+
 import torch
 
 from . import conv_ops as C
@@ -10,6 +12,30 @@ from .ops import _count, _p
 
 def _stream(t):
     return L.stream_ptr(t.device)
+
+
+# Weight-gradient kernels are off the critical path of backward (nothing downstream reads dW before the optimizer
+# step), and they are tensor-bound while the BatchNorm backward kernels that follow the data-gradient are HBM-bound:
+# they run on a side stream and overlap (the wgrad CTAs leave enough shared memory for the BN CTAs to co-reside).
+# Only when the gradient goes straight into a FusedSGD flat buffer -- the optimizer step joins the side stream.
+_SIDE_STREAMS = {}
+_OVERLAP_WGRAD = os.environ.get("NBDT_B200_WGRAD_STREAM", "1") != "0"
+
+
+def wgrad_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
+
+
+def join_wgrad_streams(device=None):
+    """Make the current stream wait for every weight-gradient kernel launched so far (optimizer step, all-reduce,
+    end of a CUDA-graph capture)."""
+    for key, st in _SIDE_STREAMS.items():
+        if device is None or torch.device(device).index in (None, key):
+            torch.cuda.current_stream(key).wait_stream(st)
 
 
 def _pad_vec(v, n, fill=0.0):
@@ -80,11 +106,18 @@ class ConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = C.conv_dgrad(dy, wpt, (x.shape[1], x.shape[2]), k, stride)
         if ctx.needs_input_grad[1]:
-            dwp = C.conv_wgrad(x, dy, k, stride)
-            if ctx.direct_grad is not None:
-                C.unpack_wgrad(dwp, wshape, out=ctx.direct_grad, accumulate=True)
+            if ctx.direct_grad is not None and _OVERLAP_WGRAD:
+                main, side = torch.cuda.current_stream(x.device), wgrad_stream(x.device)
+                side.wait_stream(main)  # x and dy are complete on the main stream at this point
+                with torch.cuda.stream(side):
+                    dwp = C.conv_wgrad(x, dy, k, stride)
+                    C.unpack_wgrad(dwp, wshape, out=ctx.direct_grad, accumulate=True)
+                x.record_stream(side)
+                dy.record_stream(side)
+            elif ctx.direct_grad is not None:
+                C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride), wshape, out=ctx.direct_grad, accumulate=True)
             else:
-                dw = C.unpack_wgrad(dwp, wshape)
+                dw = C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride), wshape)
         return dx, dw, None, (dy if has_res else None)
 
 

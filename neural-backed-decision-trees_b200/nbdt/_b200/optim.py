@@ -60,6 +60,9 @@ class FusedSGD(torch.optim.Optimizer):
                 self.flat_grad[off:off + n].copy_(p.grad.reshape(-1))
                 p.grad = self.flat_grad[off:off + n].view_as(p)
             off += n
+        from .nn_ops import join_wgrad_streams
+
+        join_wgrad_streams(self.flat_param.device)  # weight-gradient kernels run on a side stream
         with torch.cuda.device(self.flat_param.device):
             L.check(L.load().nbdt_sgd_step(_p(self.flat_param), _p(self.flat_grad), _p(self.flat_momentum),
                                            self.flat_param.numel(), float(g["lr"]), float(g["momentum"]),

@@ -69,6 +69,9 @@ class FlatGradientAllReduce:
 
     def reduce(self):
         if self.world_size > 1:
+            from .nn_ops import join_wgrad_streams
+
+            join_wgrad_streams(self.optimizer.flat_grad.device)  # weight gradients are written on a side stream
             dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
 
 
