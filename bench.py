@@ -271,8 +271,11 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    loss_first = None
     for _ in range(max(args.warmup, 3)):
-        step(dev_x, dev_y)
+        l = step(dev_x, dev_y)
+        if loss_first is None:
+            loss_first = float(l)
     launches0 = ops.launch_count()
     step(dev_x, dev_y)
     launches_per_step = ops.launch_count() - launches0
@@ -334,6 +337,9 @@ def run_b200(args, rank, world, local_rank):
     e2e_step()
     e2e_ms = timed(e2e_step, args.steps)
 
+    loss_last = float(run_step())
+    if not (loss_last == loss_last and abs(loss_last) < 1e4):  # NaN / blow-up: the timed work was not a valid train step
+        raise SystemExit(f"bench.py: training diverged on the synthetic batch (loss {loss_first} -> {loss_last})")
     if rank != 0:
         return
     peaks, peak_src = load_peaks()
@@ -346,6 +352,12 @@ def run_b200(args, rank, world, local_rank):
     conv_ms = sum(v[1] for v in conv_stats.values())
     conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"]
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tpath):  # DRAM bytes per launch from the committed `ncu --set full` capture of the same kernels
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["mean_bytes_per_launch"], tj["source"]
     line = {
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -358,9 +370,9 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": host_x.numel() * 4 + host_y.numel() * 8,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "roofline": {"kernel": "tap_gemm_kernel / wgrad_kernel (tcgen05 implicit-GEMM conv fwd + dgrad + wgrad, all launches of the timed steps)",
+        "roofline": {"kernel": "tap_gemm2h / tap_gemm2 / tap_gemm / wgrad kernels (tcgen05 implicit-GEMM conv fwd + dgrad + wgrad, all 81 launches of a step)",
                      "bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": conv_tflops / peak_tf, "traffic": None, "peak_source": peak_src + " (bf16_tflops_sustained)",
+                     "frac": conv_tflops / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src + " (bf16_tflops_sustained)",
                      "per_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms_per_step": v[1] / prof_steps,
                                       "launches_per_step": v[2] / prof_steps} for k, v in conv_stats.items()},
                      "conv_share_of_step": (conv_ms / prof_steps) / ms_per_step,
@@ -370,6 +382,7 @@ def run_b200(args, rank, world, local_rank):
                           "frac": tree_bytes / (tree_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_us": tree_ms * 1e3,
                           "note": "45 KB per launch at the BASELINE batch: latency-bound; saturating sweep in profiles/"},
         "step_tflops": FLOPS_PER_IMAGE * B * world / (ms_per_step / 1e3) / 1e12,
+        "loss": {"first_step": loss_first, "after_timed_steps": loss_last},  # sanity: the same synthetic batch is being fitted
     }
     if world == 1 and not args.no_cpu_baseline:
         val, cores, sample, _ = cpu_reference_run(3, 1, args.cpu_batch, budget_s=60.0)

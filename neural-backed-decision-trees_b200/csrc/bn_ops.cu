@@ -396,19 +396,54 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(const uint4* 
 }
 
 // feat[n][c] = mean over HW rows of a[n, :, c]  (fp32 out).      bytes: N*HW*C*2 read
-__global__ void avgpool_fwd_kernel(const uint4* __restrict__ a, float* __restrict__ feat, int HW, int C) {
+// CTA (slice s, image n) reduces pixels [s*pix_per_cta, ...) on the row-octet mapping; with one slice per image the
+// result is written directly (deterministic: the 8x8 maps of the CIFAR backbones), with several slices (the 112x112 ...
+// 7x7 maps of EfficientNet's squeeze-excitation, where one CTA per image was 42 % of the forward time) the slices are
+// combined with fp32 atomics into a zeroed output.
+__global__ void __launch_bounds__(kThreads) avgpool_fwd_kernel(const uint4* __restrict__ a, float* __restrict__ feat, int HW,
+                                                               int C, int pix_per_cta, int use_atomics) {
+  __shared__ float red[kThreads * 8];
   const int octets = C / 8;
-  const int n = blockIdx.x;
-  for (int o = threadIdx.x; o < octets; o += blockDim.x) {
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const float inv = 1.f / (float)HW;
+  const uint4* img = a + (size_t)n * HW * octets;
+  if (octets <= kThreads) {
+    const int R = kThreads / octets;
+    const int r = threadIdx.x / octets, o = threadIdx.x - r * octets;
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int p = 0; p < HW; ++p) {
-      float f[8];
-      unpack8(__ldg(a + ((long long)n * HW + p) * octets + o), f);
+    if (r < R) {
+      for (int p = p0 + r; p < p1; p += R) {
+        float f[8];
+        unpack8(__ldg(img + (size_t)p * octets + o), f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] += f[e];
+        for (int e = 0; e < 8; ++e) s[e] += f[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[(r * octets + o) * 8 + e] = s[e];
     }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      float t = 0.f;
+      for (int q = 0; q < R; ++q) t += red[q * C + c];
+      if (use_atomics) atomicAdd(feat + (size_t)n * C + c, t * inv);
+      else feat[(size_t)n * C + c] = t * inv;
+    }
+  } else {
+    for (int o = threadIdx.x; o < octets; o += kThreads) {
+      float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int p = p0; p < p1; ++p) {
+        float f[8];
+        unpack8(__ldg(img + (size_t)p * octets + o), f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) feat[(long long)n * C + o * 8 + e] = s[e] / (float)HW;
+        for (int e = 0; e < 8; ++e) s[e] += f[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (use_atomics) atomicAdd(feat + (size_t)n * C + o * 8 + e, s[e] * inv);
+        else feat[(size_t)n * C + o * 8 + e] = s[e] * inv;
+      }
+    }
   }
 }
 // da[n, p, c] = dfeat[n][c] / HW
@@ -651,10 +686,16 @@ int nbdt_bn_backward(const void* x, const void* act, const float* scale_shift, c
 }
 
 int nbdt_avgpool_fwd(const void* a, float* feat, int N, int HW, int C, void* stream) {
-  NBDT_REQUIRE(a && feat && C % 8 == 0, "bad arguments");
+  NBDT_REQUIRE(a && feat && C % 8 == 0 && N <= 65535, "bad arguments");
   if (N == 0) return NBDT_OK;
-  avgpool_fwd_kernel<<<N, std::min(kThreads, std::max(32, C / 8)), 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint4*>(a), feat, HW, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  // slices per image: enough CTAs to fill the GPU (~4 per SM), at least 64 pixels each
+  const int want = std::max(1, (4 * sm_count() + N - 1) / N);
+  const int slices = std::max(1, std::min(want, (HW + 63) / 64));
+  const int pix_per_cta = (HW + slices - 1) / slices;
+  const int gx = (HW + pix_per_cta - 1) / pix_per_cta;
+  if (gx > 1) NBDT_CUDA_OK(cudaMemsetAsync(feat, 0, (size_t)N * C * sizeof(float), st));
+  avgpool_fwd_kernel<<<dim3(gx, N), kThreads, 0, st>>>(reinterpret_cast<const uint4*>(a), feat, HW, C, pix_per_cta, gx > 1);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }

@@ -833,8 +833,10 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
   // CTA-pair kernel (cta_group::2) when there is at least one pair tile per SM pair; NBDT_B200_CONV_PAIR=0 disables it
   static const bool pair_enabled = !(getenv("NBDT_B200_CONV_PAIR") && atoi(getenv("NBDT_B200_CONV_PAIR")) == 0);
   const int total_pairs = ((p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2) * p.n_tiles;
+  // pair kernels from this many pair tiles on (default: one per SM pair); NBDT_B200_CONV_PAIR_MIN lowers it for tests
+  const int pair_min = getenv("NBDT_B200_CONV_PAIR_MIN") ? atoi(getenv("NBDT_B200_CONV_PAIR_MIN")) : info.sm_count / 2;
   // H-halo variant: 3x3 taps on ONE dense view, tiles = box_w x box_h pixels of one image with box_w in {16, 32}
-  bool halo = pair_enabled && p.exp == 0 && total_pairs >= info.sm_count / 2 && num_taps == 9 && num_views == 1 &&
+  bool halo = pair_enabled && p.exp == 0 && total_pairs >= pair_min && num_taps == 9 && num_views == 1 &&
               p.box_n == 1 && (p.box_w == 16 || p.box_w == 32) && p.box_w * (p.box_h + 2) <= 192 &&
               !getenv("NBDT_B200_CONV_NOHALO");
   if (halo) {  // group the taps by dw; every group must hold dh = -1, 0, +1
@@ -876,7 +878,7 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
     NBDT_CUDA_OK(cudaGetLastError());
     return NBDT_OK;
   }
-  if (pair_enabled && p.exp == 0 && total_pairs >= info.sm_count / 2) {
+  if (pair_enabled && p.exp == 0 && total_pairs >= pair_min) {
     CUtensorMap tm_w2;
     {
       cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)w_rows};
@@ -981,7 +983,10 @@ struct WgradCfg {
   static constexpr int kTapBytes = kBChunks * kChunkBytes;
   static constexpr int kBBytes = HALO ? kBChunks * kHaloChunkBytes : TAPS * kTapBytes;
   static constexpr int kStageBytes = kAChunks * kChunkBytes + kBBytes;
-  static constexpr int kStages = (208 * 1024) / kStageBytes > 8 ? 8 : (208 * 1024) / kStageBytes;
+  // at most ~190 KB of the SM's shared memory: the HBM-bound BatchNorm-backward CTAs that follow the data gradient on the
+  // main stream must be able to co-reside with this kernel's CTAs (it runs on a side stream, nn_ops.ConvFunction)
+  static constexpr int kMaxStages = (190 * 1024) / kStageBytes;
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kAccCols = TAPS * BLOCK_N;
   static constexpr int kNumAcc = (2 * kAccCols <= 512) ? 2 : 1;    // double-buffer the accumulators when they fit
   static constexpr int kTmemCols = (kNumAcc * kAccCols <= 128) ? 128 : (kNumAcc * kAccCols <= 256 ? 256 : 512);
@@ -1251,32 +1256,68 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // weight repacking: fp32 OIHW master weights <-> the bf16 tap-major matrices the GEMMs read
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
-                                    __nv_bfloat16* __restrict__ wpt, int Cout, int Cin, int cin_pad, int cout_pad,
-                                    int taps) {
+// Tiled (32 output channels x 32 input channels x taps through shared memory) so that the OIHW side is read / written
+// in runs of 32*taps contiguous floats and BOTH tap-major sides in runs of 32 contiguous elements -- the first version
+// used one thread per packed element with three 64-bit divisions and stride-`taps` / stride-`cout` scattered accesses
+// (0.76 ms per step for 2 x 27 launches, profiles/r01_bench_launches_v3.md).
+constexpr int kPackTile = 32;
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                           __nv_bfloat16* __restrict__ wpt, int Cout, int Cin,
+                                                           int cin_pad, int cout_pad, int taps) {
   // w: [Cout][Cin][taps] (OIHW);  wp: [taps][cout_pad][cin_pad];  wpt: [taps][cin_pad][cout_pad]  (zero padded)
-  const long long total = (long long)taps * cout_pad * cin_pad;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % cin_pad);
-    const int co = (int)((i / cin_pad) % cout_pad);
-    const int t = (int)(i / ((long long)cin_pad * cout_pad));
-    const float v = (ci < Cin && co < Cout) ? w[((long long)co * Cin + ci) * taps + t] : 0.f;
-    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-    if (wp) wp[i] = b;
-    if (wpt) wpt[((long long)t * cin_pad + ci) * cout_pad + co] = b;
+  extern __shared__ float tile[];  // [32 co][32 * taps + 1]
+  const int row_len = kPackTile * taps + 1;
+  const int ci0 = blockIdx.x * kPackTile, co0 = blockIdx.y * kPackTile;
+  const int per_row = kPackTile * taps;
+  for (int i = threadIdx.x; i < kPackTile * per_row; i += blockDim.x) {
+    const int co_l = i / per_row, rem = i - co_l * per_row;
+    const int co = co0 + co_l, ci = ci0 + rem / taps;
+    tile[co_l * row_len + rem] = (co < Cout && ci < Cin) ? __ldg(w + ((size_t)co * Cin + ci0) * taps + rem) : 0.f;
+  }
+  __syncthreads();
+  const int n = kPackTile * kPackTile * taps;
+  if (wp) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int ci_l = i % kPackTile, co_l = (i / kPackTile) % kPackTile, tp = i / (kPackTile * kPackTile);
+      const int co = co0 + co_l, ci = ci0 + ci_l;
+      if (co < cout_pad && ci < cin_pad)
+        wp[((size_t)tp * cout_pad + co) * cin_pad + ci] = __float2bfloat16_rn(tile[co_l * row_len + ci_l * taps + tp]);
+    }
+  }
+  if (wpt) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int co_l = i % kPackTile, ci_l = (i / kPackTile) % kPackTile, tp = i / (kPackTile * kPackTile);
+      const int co = co0 + co_l, ci = ci0 + ci_l;
+      if (co < cout_pad && ci < cin_pad)
+        wpt[((size_t)tp * cin_pad + ci) * cout_pad + co] = __float2bfloat16_rn(tile[co_l * row_len + ci_l * taps + tp]);
+    }
   }
 }
 
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin,
-                                    int cin_pad, int cout_pad, int taps, int accumulate) {
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout,
+                                                           int Cin, int cin_pad, int cout_pad, int taps, int accumulate) {
   // dwp: [taps][cout_pad][cin_pad] fp32  ->  dw: [Cout][Cin][taps] (OIHW)
-  const long long total = (long long)Cout * Cin * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i % taps);
-    const int ci = (int)((i / taps) % Cin);
-    const int co = (int)(i / ((long long)taps * Cin));
-    const float v = dwp[((long long)t * cout_pad + co) * cin_pad + ci];
-    dw[i] = accumulate ? dw[i] + v : v;
+  extern __shared__ float tile[];  // [32 co][32 * taps + 1]
+  const int row_len = kPackTile * taps + 1;
+  const int ci0 = blockIdx.x * kPackTile, co0 = blockIdx.y * kPackTile;
+  const int n = kPackTile * kPackTile * taps;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int ci_l = i % kPackTile, co_l = (i / kPackTile) % kPackTile, tp = i / (kPackTile * kPackTile);
+    const int co = co0 + co_l, ci = ci0 + ci_l;
+    tile[co_l * row_len + ci_l * taps + tp] =
+        (co < Cout && ci < Cin) ? __ldg(dwp + ((size_t)tp * cout_pad + co) * cin_pad + ci) : 0.f;
+  }
+  __syncthreads();
+  const int per_row = kPackTile * taps;
+  for (int i = threadIdx.x; i < kPackTile * per_row; i += blockDim.x) {
+    const int co_l = i / per_row, rem = i - co_l * per_row;
+    const int co = co0 + co_l, ci = ci0 + rem / taps;
+    if (co < Cout && ci < Cin) {
+      float* dst = dw + ((size_t)co * Cin + ci0) * taps + rem;
+      const float v = tile[co_l * row_len + rem];
+      *dst = accumulate ? *dst + v : v;
+    }
   }
 }
 
@@ -1497,11 +1538,11 @@ int nbdt_conv_pack_weights(const float* w_oihw, void* wpack, void* wpack_t, int 
                            int cin_pad, int ksize, void* stream) {
   NBDT_REQUIRE(w_oihw && (wpack || wpack_t), "NULL tensor");
   NBDT_REQUIRE(cout_pad >= Cout && cin_pad >= Cin, "padded sizes smaller than the real ones");
-  const long long total = (long long)ksize * ksize * cout_pad * cin_pad;
-  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_oihw, reinterpret_cast<__nv_bfloat16*>(wpack),
-                                                               reinterpret_cast<__nv_bfloat16*>(wpack_t), Cout, Cin,
-                                                               cin_pad, cout_pad, ksize * ksize);
+  const int taps = ksize * ksize;
+  const dim3 grid((cin_pad + kPackTile - 1) / kPackTile, (cout_pad + kPackTile - 1) / kPackTile);
+  pack_weights_kernel<<<grid, 256, kPackTile * (kPackTile * taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      w_oihw, reinterpret_cast<__nv_bfloat16*>(wpack), reinterpret_cast<__nv_bfloat16*>(wpack_t), Cout, Cin, cin_pad,
+      cout_pad, taps);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }
@@ -1510,10 +1551,10 @@ int nbdt_conv_pack_weights(const float* w_oihw, void* wpack, void* wpack_t, int 
 int nbdt_conv_unpack_wgrad(const float* dwp, float* dw_oihw, int Cout, int Cin, int cout_pad, int cin_pad, int ksize,
                            int accumulate, void* stream) {
   NBDT_REQUIRE(dwp && dw_oihw, "NULL tensor");
-  const long long total = (long long)Cout * Cin * ksize * ksize;
-  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-  unpack_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dwp, dw_oihw, Cout, Cin, cin_pad, cout_pad, ksize * ksize,
-                                                              accumulate);
+  const int taps = ksize * ksize;
+  const dim3 grid((Cin + kPackTile - 1) / kPackTile, (Cout + kPackTile - 1) / kPackTile);
+  unpack_wgrad_kernel<<<grid, 256, kPackTile * (kPackTile * taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      dwp, dw_oihw, Cout, Cin, cin_pad, cout_pad, taps, accumulate);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }

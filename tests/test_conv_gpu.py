@@ -108,3 +108,25 @@ def test_pack_weights_padding():
     assert torch.equal(wp[:, :160, :16], w.permute(2, 3, 0, 1).reshape(9, 160, 16).bfloat16())
     assert (wp[:, 160:] == 0).all() and (wp[:, :, 16:] == 0).all()
     assert torch.equal(wpt, wp.transpose(1, 2))
+
+
+# The CTA-pair kernels (tcgen05.mma.cta_group::2; H-halo variant for 16/32-wide stride-1 3x3) only engage from one pair
+# tile per SM pair on; NBDT_B200_CONV_PAIR_MIN=1 forces them for the small parity shapes (incl. odd tile counts), and two
+# shapes are large enough to take them by default.
+@pytest.fixture
+def force_pair_kernels(monkeypatch):
+    monkeypatch.setenv("NBDT_B200_CONV_PAIR_MIN", "1")
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(3, 32, 32, 160, 160, 3, 1), (5, 16, 16, 320, 640, 3, 1), (1, 32, 32, 64, 64, 3, 1)])
+def test_conv_fwd_dgrad_pair_kernels(shape, force_pair_kernels):
+    test_conv_fwd(shape)
+    test_conv_dgrad(shape)
+
+
+@pytest.mark.parametrize("shape", [(160, 32, 32, 160, 160, 3, 1), (301, 8, 8, 128, 160, 3, 1), (80, 32, 32, 64, 128, 3, 2)])
+def test_conv_fwd_dgrad_large(shape):
+    """Default dispatch at sizes where the pair kernels are selected (>= 74 pair tiles), odd tile count included."""
+    test_conv_fwd(shape)
+    test_conv_dgrad(shape)
+    test_conv_wgrad(shape)
