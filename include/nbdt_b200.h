@@ -164,6 +164,10 @@ int nbdt_bn_apply(const void* x, const void* residual, void* y, long long M, int
 int nbdt_bn_backward(const void* x, const void* act, const float* scale_shift, const void* dy, const void* extra,
                      void* dx, void* dres, long long M, int C, int c_real, const float* gamma,
                      const float* mean_invstd, float* dsums, void* stream);
+/* Same for y = SiLU(x*scale + shift) (no residual): the activation gradient is recomputed from x and scale_shift. */
+int nbdt_bn_backward_silu(const void* x, const float* scale_shift, const void* dy, const void* extra, void* dx,
+                          long long M, int C, int c_real, const float* gamma, const float* mean_invstd, float* dsums,
+                          void* stream);
 /* feat[N][C] (fp32) = mean over the HW rows of each image;  da = dfeat / HW broadcast. */
 int nbdt_avgpool_fwd(const void* a, float* feat, int N, int HW, int C, void* stream);
 int nbdt_avgpool_bwd(const float* dfeat, void* da, int N, int HW, int C, void* stream);
@@ -175,6 +179,8 @@ int nbdt_stem_fwd_strided(const float* x, const float* w, void* y, int N, int H,
                           void* stream);
 int nbdt_stem_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int cout, int c_phys,
                     void* stream);
+int nbdt_stem_wgrad_strided(const float* x, const void* dy, float* dw, int N, int H, int W, int cout, int c_phys,
+                            int stride, void* stream);
 /* Fused SGD over a flat fp32 buffer: m = momentum*m + (g*grad_scale + wd*p); p -= lr*m (first_step: m = g'). */
 int nbdt_sgd_step(float* params, const float* grads, float* momentum_buf, long long n, float lr, float momentum,
                   float weight_decay, float grad_scale, int first_step, void* stream);
@@ -192,6 +198,14 @@ int nbdt_dwconv_fwd(const void* x, const float* w, const float* scale_shift, voi
                     int ksize, int stride, int act, void* stream);
 /* Squeeze-excitation scaling y[n,p,c] = x[n,p,c]*s[n][c]; x, y bf16 [N][HW][C] (may alias), s fp32 [N][C]. */
 int nbdt_se_scale(const void* x, const float* s, void* y, int N, int HW, int C, void* stream);
+/* Training path of the MBConv blocks (depthwise conv without the fused affine, i.e. nbdt_dwconv_fwd with scale_shift = NULL,
+ * act = 0): data gradient dx [N,H,W,C] from dy [N,ceil(H/s),ceil(W/s),C]; weight gradient dw fp32 [ksize*ksize][C]
+ * (overwritten); gradient of the squeeze-excitation scale ds[n][c] = sum_p x[n,p,c]*dy[n,p,c]. */
+int nbdt_dwconv_dgrad(const void* dy, const float* w, void* dx, int N, int H, int W, int C, int ksize, int stride,
+                      void* stream);
+int nbdt_dwconv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int ksize, int stride,
+                      void* stream);
+int nbdt_se_dscale(const void* x, const void* dy, float* ds, int N, int HW, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -253,7 +253,12 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const uint4* __restr
 // ReLU mask of the forward pass: kMaskNone (no activation), kMaskAct (read the saved forward output: needed when a
 // residual was added before the ReLU), kMaskRecompute (x*scale + shift > 0, bit-identical to the forward's fmaf:
 // saves reading one tensor in each backward kernel).
-enum { kMaskNone = 0, kMaskAct = 1, kMaskRecompute = 2 };
+// kMaskSiLU: the forward activation was SiLU(z), z = x*scale + shift: g = dy * SiLU'(z), SiLU'(z) = s (1 + z (1 - s)), s = sigmoid(z)
+enum { kMaskNone = 0, kMaskAct = 1, kMaskRecompute = 2, kMaskSiLU = 3 };
+__device__ __forceinline__ float silu_grad(float z) {
+  const float sg = __fdividef(1.f, 1.f + __expf(-z));
+  return sg * fmaf(z, 1.f - sg, 1.f);
+}
 
 struct BwdPack {
   uint4 x, g, a;
@@ -269,7 +274,7 @@ struct BwdReduceOp {
   float mean[8], sc[8], sh[8];
   __device__ __forceinline__ void init(int o) {
     load8(mean_invstd + o * 8, mean);
-    if (MASK == kMaskRecompute) {
+    if (MASK == kMaskRecompute || MASK == kMaskSiLU) {
       load8(scale_shift + o * 8, sc);
       load8(scale_shift + C + o * 8, sh);
     }
@@ -291,7 +296,8 @@ struct BwdReduceOp {
       bool on = true;
       if (MASK == kMaskAct) on = fa[e] > 0.f;
       if (MASK == kMaskRecompute) on = fmaf(fx[e], sc[e], sh[e]) > 0.f;
-      const float g = on ? fg[e] : 0.f;
+      float g = on ? fg[e] : 0.f;
+      if (MASK == kMaskSiLU) g = fg[e] * silu_grad(fmaf(fx[e], sc[e], sh[e]));
       acc[0][e] += g;
       acc[1][e] = fmaf(g, fx[e] - mean[e], acc[1][e]);
     }
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(const uint4* 
     load8(coef + o * 8, k1);
     load8(coef + C + o * 8, ka);
     load8(coef + 2 * C + o * 8, kb);
-    if (MASK == kMaskRecompute) {
+    if (MASK == kMaskRecompute || MASK == kMaskSiLU) {
       load8(scale_shift + o * 8, sc);
       load8(scale_shift + C + o * 8, sh);
     }
@@ -363,7 +369,8 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(const uint4* 
         bool on = true;
         if (MASK == kMaskAct) on = fa[e] > 0.f;
         if (MASK == kMaskRecompute) on = fmaf(fx[e], sc[e], sh[e]) > 0.f;
-        const float g = on ? fg[e] : 0.f;
+        float g = on ? fg[e] : 0.f;
+        if (MASK == kMaskSiLU) g = fg[e] * silu_grad(fmaf(fx[e], sc[e], sh[e]));
         float v = fmaf(k1[e], g, fmaf(ka[e], fx[e], kb[e]));
         if (EXTRA) v += fe[e];
         out[e] = v;
@@ -510,19 +517,20 @@ __global__ void __launch_bounds__(128) stem_fwd_kernel(const float* __restrict__
 // shared memory between two __syncthreads with 8 warps per SM: latency-bound, 0.4 ms per step.)
 __global__ void __launch_bounds__(128) stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                          float* __restrict__ dw, int N, int H, int W, int cout,
-                                                         int c_phys) {
+                                                         int c_phys, int stride) {
   const int lane = threadIdx.x;                         // pixel lane
   const int co0 = (blockIdx.y * 4 + threadIdx.y) * 4;   // first of this thread's 4 output channels
   if (co0 >= cout) return;                              // whole warp (one threadIdx.y per warp)
-  const unsigned total = (unsigned)N * H * W;
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;  // dy is [N, Ho, Wo, c_phys]
+  const unsigned total = (unsigned)N * Ho * Wo;
   float acc[4][27];
 #pragma unroll
   for (int c = 0; c < 4; ++c)
 #pragma unroll
     for (int k = 0; k < 27; ++k) acc[c][k] = 0.f;
   for (unsigned pix = blockIdx.x * 32 + lane; pix < total; pix += gridDim.x * 32) {
-    const int wq = (int)(pix % (unsigned)W), hq = (int)((pix / (unsigned)W) % (unsigned)H);
-    const unsigned n = pix / ((unsigned)W * (unsigned)H);
+    const int wq = (int)(pix % (unsigned)Wo) * stride, hq = (int)((pix / (unsigned)Wo) % (unsigned)Ho) * stride;
+    const unsigned n = pix / ((unsigned)Wo * (unsigned)Ho);
     const uint2 gv = __ldg(reinterpret_cast<const uint2*>(dy + (size_t)pix * c_phys + co0));
     const float g[4] = {__uint_as_float(gv.x << 16), __uint_as_float(gv.x & 0xffff0000u),
                         __uint_as_float(gv.y << 16), __uint_as_float(gv.y & 0xffff0000u)};
@@ -642,13 +650,12 @@ int nbdt_bn_apply(const void* x, const void* residual, void* y, long long M, int
 // Backward of y = act(bn(x) (+ residual)).  ReLU mask: `act` (the forward OUTPUT y) when given; else recomputed from
 // x and `scale_shift` when given (only valid when no residual was added before the ReLU); else no activation.
 // dx = d/dx (+ extra); dres (may be NULL) = gradient w.r.t. the residual; dsums[0..2C) = (dbeta, dgamma).
-int nbdt_bn_backward(const void* x, const void* act, const float* scale_shift, const void* dy, const void* extra,
-                     void* dx, void* dres, long long M, int C, int c_real, const float* gamma,
-                     const float* mean_invstd, float* dsums, void* stream) {
+static int bn_backward_impl(int mask, const void* x, const void* act, const float* scale_shift, const void* dy,
+                            const void* extra, void* dx, void* dres, long long M, int C, int c_real, const float* gamma,
+                            const float* mean_invstd, float* dsums, void* stream) {
   NBDT_REQUIRE(x && dy && dx && gamma && mean_invstd && dsums, "NULL tensor");
   NBDT_REQUIRE(C % 8 == 0 && C <= 8192 && M > 0, "bad shape M=%lld C=%d", M, C);
   cudaStream_t st = (cudaStream_t)stream;
-  const int mask = act ? kMaskAct : (scale_shift ? kMaskRecompute : kMaskNone);
   float* coef = dsums + 2 * C;      // [3][C]
   float* partials = dsums + 5 * C;  // [grid][2][C]
   const uint4* xs = reinterpret_cast<const uint4*>(x);
@@ -663,6 +670,8 @@ int nbdt_bn_backward(const void* x, const void* act, const float* scale_shift, c
     bn_bwd_reduce_kernel<kMaskAct><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
   else if (mask == kMaskRecompute)
     bn_bwd_reduce_kernel<kMaskRecompute><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
+  else if (mask == kMaskSiLU)
+    bn_bwd_reduce_kernel<kMaskSiLU><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
   else
     bn_bwd_reduce_kernel<kMaskNone><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
   bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinalizeThreads, 0, st>>>(partials, grid, M, C, c_real, gamma, mean_invstd, dsums, coef);
@@ -678,11 +687,28 @@ int nbdt_bn_backward(const void* x, const void* act, const float* scale_shift, c
   } while (0)
   if (mask == kMaskAct) NBDT_BWD_APPLY_M(kMaskAct);
   else if (mask == kMaskRecompute) NBDT_BWD_APPLY_M(kMaskRecompute);
+  else if (mask == kMaskSiLU) NBDT_BWD_APPLY_M(kMaskSiLU);
   else NBDT_BWD_APPLY_M(kMaskNone);
 #undef NBDT_BWD_APPLY_M
 #undef NBDT_BWD_APPLY
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
+}
+
+int nbdt_bn_backward(const void* x, const void* act, const float* scale_shift, const void* dy, const void* extra,
+                     void* dx, void* dres, long long M, int C, int c_real, const float* gamma,
+                     const float* mean_invstd, float* dsums, void* stream) {
+  const int mask = act ? kMaskAct : (scale_shift ? kMaskRecompute : kMaskNone);
+  return bn_backward_impl(mask, x, act, scale_shift, dy, extra, dx, dres, M, C, c_real, gamma, mean_invstd, dsums, stream);
+}
+
+// Same for y = SiLU(bn(x)) (no residual before the activation): the activation gradient is recomputed from x and scale_shift.
+int nbdt_bn_backward_silu(const void* x, const float* scale_shift, const void* dy, const void* extra, void* dx,
+                          long long M, int C, int c_real, const float* gamma, const float* mean_invstd, float* dsums,
+                          void* stream) {
+  NBDT_REQUIRE(scale_shift != nullptr, "scale_shift is required for the SiLU backward");
+  return bn_backward_impl(kMaskSiLU, x, nullptr, scale_shift, dy, extra, dx, nullptr, M, C, c_real, gamma, mean_invstd, dsums,
+                          stream);
 }
 
 int nbdt_avgpool_fwd(const void* a, float* feat, int N, int HW, int C, void* stream) {
@@ -728,20 +754,24 @@ int nbdt_stem_fwd(const float* x, const float* w, void* y, int N, int H, int W, 
 }
 
 // dw fp32 [cout][3][3][3] (overwritten) from x NCHW fp32 and dy NHWC bf16 [N,H,W,c_phys].
-int nbdt_stem_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int cout, int c_phys, void* stream) {
+int nbdt_stem_wgrad_strided(const float* x, const void* dy, float* dw, int N, int H, int W, int cout, int c_phys,
+                            int stride, void* stream) {
   NBDT_REQUIRE(x && dy && dw, "NULL tensor");
-  NBDT_REQUIRE(cout * 27 <= 8 * kThreads, "stem with %d output channels is not supported", cout);
+  NBDT_REQUIRE(stride == 1 || stride == 2, "stem stride %d is not supported", stride);
   NBDT_REQUIRE((long long)N * H * W < (1LL << 31) - 64 * 4096, "stem: too many pixels (%lld)", (long long)N * H * W);
   cudaStream_t st = (cudaStream_t)stream;
   NBDT_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)cout * 27 * sizeof(float), st));
-  const long long pix = (long long)N * H * W;
+  const long long pix = (long long)N * ((H + stride - 1) / stride) * ((W + stride - 1) / stride);
   if (pix == 0) return NBDT_OK;
   NBDT_REQUIRE(c_phys % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7) == 0, "stem wgrad: dy must be 8-byte aligned");
   const int gx = (int)std::min<long long>((pix + 31) / 32, (long long)sm_count() * 4);
   stem_wgrad_kernel<<<dim3(gx, (cout + 15) / 16), dim3(32, 4), 0, st>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), dw, N,
-                                                                         H, W, cout, c_phys);
+                                                                         H, W, cout, c_phys, stride);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
+}
+int nbdt_stem_wgrad(const float* x, const void* dy, float* dw, int N, int H, int W, int cout, int c_phys, void* stream) {
+  return nbdt_stem_wgrad_strided(x, dy, dw, N, H, W, cout, c_phys, 1, stream);
 }
 
 // One fused SGD update over a flat fp32 parameter buffer (momentum, weight decay; gradient pre-scaled by grad_scale).

@@ -137,6 +137,162 @@ __global__ void __launch_bounds__(256) se_scale_kernel(const uint4* __restrict__
   }
 }
 
+// Data gradient of the depthwise convolution: dx[n,hi,wi,c] = sum over taps (r,s) with (hi + PAD - r) and (wi + PAD - s)
+// divisible by S of w[r][s][c] * dy[n, (hi+PAD-r)/S, (wi+PAD-s)/S, c].  One thread per (input pixel, channel octet).
+// bytes: N*Ho*Wo*C*2 read (the K*K re-use is served by L1/L2) + N*H*W*C*2 written
+template <int K, int S>
+__global__ void __launch_bounds__(256) dwconv_dgrad_kernel(const uint4* __restrict__ dy, const float* __restrict__ w,
+                                                           uint4* __restrict__ dx, int N, int H, int W, int C, int Ho,
+                                                           int Wo) {
+  constexpr int PAD = K / 2;
+  const unsigned octets = C / 8;
+  const unsigned total = (unsigned)N * H * W * octets;
+  for (unsigned item = blockIdx.x * blockDim.x + threadIdx.x; item < total; item += gridDim.x * blockDim.x) {
+    const unsigned o = item % octets;
+    unsigned t = item / octets;
+    const int wi = t % (unsigned)W;
+    t /= (unsigned)W;
+    const int hi = t % (unsigned)H;
+    const unsigned n = t / (unsigned)H;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const int hn = hi + PAD - r;
+      if (hn < 0 || (S == 2 && (hn & 1))) continue;
+      const int ho = hn / S;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        const int wn = wi + PAD - s;
+        if (wn < 0 || (S == 2 && (wn & 1))) continue;
+        const int wo = wn / S;
+        if (wo >= Wo) continue;
+        float f[8];
+        unpack8(__ldg(dy + ((size_t)(n * Ho + ho) * Wo + wo) * octets + o), f);
+        const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(r * K + s) * C + o * 8);
+        const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(f[e], wv[e], acc[e]);
+      }
+    }
+    dx[item] = pack8(acc);
+  }
+}
+
+// Weight gradient of the depthwise convolution: dw[r*K+s][c] = sum over output pixels of dy[n,ho,wo,c] * x[n, ho*S+r-PAD,
+// wo*S+s-PAD, c].  Thread (pixel lane, channel octet) keeps the K x 8 partial sums of ONE kernel row r = blockIdx.y in
+// registers over its share of the output pixels; lanes are combined in shared memory, CTAs with fp32 atomics.
+// bytes: (N*H*W + N*Ho*Wo)*C*2 read per kernel row (K passes; the operands of neighbouring rows overlap in L2)
+template <int K, int S>
+__global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
+                                                           float* __restrict__ dw, int N, int H, int W, int C, int Ho,
+                                                           int Wo) {
+  constexpr int PAD = K / 2;
+  __shared__ float red[256 * 8];
+  const int octets = C / 8;
+  const int r = blockIdx.y;  // kernel row
+  const int R = octets <= 256 ? 256 / octets : 1;
+  const unsigned total = (unsigned)N * Ho * Wo;
+  for (int o = threadIdx.x % octets, lane = threadIdx.x / octets; o < octets; o += 256) {
+    float acc[K][8];
+#pragma unroll
+    for (int s = 0; s < K; ++s)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[s][e] = 0.f;
+    if (lane < R || octets > 256) {
+      const unsigned step = octets <= 256 ? gridDim.x * R : gridDim.x;
+      for (unsigned pix = blockIdx.x * (octets <= 256 ? R : 1) + (octets <= 256 ? lane : 0); pix < total; pix += step) {
+        const int wo = pix % (unsigned)Wo;
+        const unsigned t = pix / (unsigned)Wo;
+        const int ho = t % (unsigned)Ho;
+        const unsigned n = t / (unsigned)Ho;
+        const int hi = ho * S + r - PAD;
+        if (hi < 0 || hi >= H) continue;
+        float g[8];
+        unpack8(__ldg(dy + (size_t)pix * octets + o), g);
+        const uint4* row = x + ((size_t)(n * H + hi) * W) * octets + o;
+#pragma unroll
+        for (int s = 0; s < K; ++s) {
+          const int wi = wo * S + s - PAD;
+          if (wi < 0 || wi >= W) continue;
+          float f[8];
+          unpack8(__ldg(row + (size_t)wi * octets), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[s][e] = fmaf(g[e], f[e], acc[s][e]);
+        }
+      }
+    }
+    // combine the R pixel lanes of this CTA (one tap column at a time through shared memory), then one atomic per value
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      __syncthreads();
+      if (octets <= 256) {
+        if (lane < R)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) red[(lane * octets + o) * 8 + e] = acc[s][e];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += 256) {
+          float v = 0.f;
+          for (int q = 0; q < R; ++q) v += red[q * C + c];
+          atomicAdd(dw + (size_t)(r * K + s) * C + c, v);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(dw + (size_t)(r * K + s) * C + o * 8 + e, acc[s][e]);
+      }
+    }
+    if (octets <= 256) break;
+  }
+}
+
+// ds[n][c] = sum over the HW pixels of image n of x[n,p,c] * dy[n,p,c]  (gradient of the squeeze-excitation scale).
+// Same slicing as avgpool_fwd_kernel (bn_ops.cu): CTA (slice, image); slices combined with fp32 atomics into a zeroed output.
+__global__ void __launch_bounds__(256) se_dscale_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
+                                                        float* __restrict__ ds, int HW, int C, int pix_per_cta) {
+  __shared__ float red[256 * 8];
+  const int octets = C / 8;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const uint4* xi = x + (size_t)n * HW * octets;
+  const uint4* gi = dy + (size_t)n * HW * octets;
+  if (octets <= 256) {
+    const int R = 256 / octets;
+    const int r = threadIdx.x / octets, o = threadIdx.x - r * octets;
+    float sacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (r < R) {
+      for (int p = p0 + r; p < p1; p += R) {
+        float f[8], g[8];
+        unpack8(__ldg(xi + (size_t)p * octets + o), f);
+        unpack8(__ldg(gi + (size_t)p * octets + o), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sacc[e] = fmaf(f[e], g[e], sacc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[(r * octets + o) * 8 + e] = sacc[e];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float t = 0.f;
+      for (int q = 0; q < R; ++q) t += red[q * C + c];
+      atomicAdd(ds + (size_t)n * C + c, t);
+    }
+  } else {
+    for (int o = threadIdx.x; o < octets; o += 256) {
+      float sacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int p = p0; p < p1; ++p) {
+        float f[8], g[8];
+        unpack8(__ldg(xi + (size_t)p * octets + o), f);
+        unpack8(__ldg(gi + (size_t)p * octets + o), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sacc[e] = fmaf(f[e], g[e], sacc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(ds + (size_t)n * C + o * 8 + e, sacc[e]);
+    }
+  }
+}
+
 int sm_count() {
   int dev = 0;
   cudaGetDevice(&dev);
@@ -185,6 +341,73 @@ int nbdt_se_scale(const void* x, const float* s, void* y, int N, int HW, int C, 
   const int gx = std::max(1, std::min((HW + R - 1) / R, std::max(1, sm_count() * 8 / N)));
   se_scale_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(x), s,
                                                                   reinterpret_cast<uint4*>(y), HW, C);
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+// Data gradient of nbdt_dwconv_fwd without the fused affine/activation: dx bf16 [N,H,W,C] from dy bf16 [N,Ho,Wo,C].
+int nbdt_dwconv_dgrad(const void* dy, const float* w, void* dx, int N, int H, int W, int C, int ksize, int stride,
+                      void* stream) {
+  NBDT_REQUIRE(dy && w && dx, "NULL tensor");
+  NBDT_REQUIRE((ksize == 3 || ksize == 5) && (stride == 1 || stride == 2), "unsupported depthwise conv %dx%d stride %d",
+               ksize, ksize, stride);
+  NBDT_REQUIRE(C % 8 == 0 && N > 0 && H > 0 && W > 0, "bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  const long long items = (long long)N * H * W * (C / 8);
+  NBDT_REQUIRE(items < (1LL << 31) - (1 << 24), "depthwise conv too large (%lld work items)", items);
+  const int grid = (int)std::min<long long>((items + 255) / 256, (long long)sm_count() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint4* gs = reinterpret_cast<const uint4*>(dy);
+  uint4* xs = reinterpret_cast<uint4*>(dx);
+#define NBDT_DWD(K, S) dwconv_dgrad_kernel<K, S><<<grid, 256, 0, st>>>(gs, w, xs, N, H, W, C, Ho, Wo)
+  if (ksize == 3 && stride == 1) NBDT_DWD(3, 1);
+  else if (ksize == 3) NBDT_DWD(3, 2);
+  else if (stride == 1) NBDT_DWD(5, 1);
+  else NBDT_DWD(5, 2);
+#undef NBDT_DWD
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+// Weight gradient: dw fp32 [ksize*ksize][C] (tap-major, overwritten) from x bf16 [N,H,W,C] and dy bf16 [N,Ho,Wo,C].
+int nbdt_dwconv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int ksize, int stride,
+                      void* stream) {
+  NBDT_REQUIRE(x && dy && dw, "NULL tensor");
+  NBDT_REQUIRE((ksize == 3 || ksize == 5) && (stride == 1 || stride == 2), "unsupported depthwise conv %dx%d stride %d",
+               ksize, ksize, stride);
+  NBDT_REQUIRE(C % 8 == 0 && C <= 2048 && N > 0 && H > 0 && W > 0, "bad shape N=%d H=%d W=%d C=%d", N, H, W, C);
+  const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+  NBDT_REQUIRE((long long)N * Ho * Wo < (1LL << 31) - (1 << 24), "depthwise conv too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  NBDT_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)ksize * ksize * C * sizeof(float), st));
+  const int octets = C / 8;
+  const int R = octets <= 256 ? 256 / octets : 1;
+  const long long pix = (long long)N * Ho * Wo;
+  const int gx = (int)std::max<long long>(1, std::min<long long>((pix + R - 1) / R, (long long)sm_count() * 4 / ksize + 1));
+  const uint4* xs = reinterpret_cast<const uint4*>(x);
+  const uint4* gs = reinterpret_cast<const uint4*>(dy);
+#define NBDT_DWW(K, S) dwconv_wgrad_kernel<K, S><<<dim3(gx, K), 256, 0, st>>>(xs, gs, dw, N, H, W, C, Ho, Wo)
+  if (ksize == 3 && stride == 1) NBDT_DWW(3, 1);
+  else if (ksize == 3) NBDT_DWW(3, 2);
+  else if (stride == 1) NBDT_DWW(5, 1);
+  else NBDT_DWW(5, 2);
+#undef NBDT_DWW
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+// ds[n][c] = sum_p x[n,p,c] * dy[n,p,c]: gradient of nbdt_se_scale with respect to s.  x, dy bf16 [N][HW][C]; ds fp32 [N][C].
+int nbdt_se_dscale(const void* x, const void* dy, float* ds, int N, int HW, int C, void* stream) {
+  NBDT_REQUIRE(x && dy && ds, "NULL tensor");
+  NBDT_REQUIRE(C % 8 == 0 && C <= 8192 && N > 0 && N <= 65535 && HW > 0, "bad shape N=%d HW=%d C=%d", N, HW, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  NBDT_CUDA_OK(cudaMemsetAsync(ds, 0, (size_t)N * C * sizeof(float), st));
+  const int want = std::max(1, (4 * sm_count() + N - 1) / N);
+  const int slices = std::max(1, std::min(want, (HW + 63) / 64));
+  const int pix_per_cta = (HW + slices - 1) / slices;
+  const int gx = (HW + pix_per_cta - 1) / pix_per_cta;
+  se_dscale_kernel<<<dim3(gx, N), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy), ds, HW, C,
+                                                pix_per_cta);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }

@@ -52,8 +52,8 @@ def stem(x, conv_mod, bn):
     L.require_cuda(x, "backbone stem")
     if x.dim() != 4 or x.shape[1] != 3:
         raise ValueError(f"expected (N, 3, H, W) images, got {tuple(x.shape)}")
-    _check_conv(conv_mod)
-    y = StemFunction.apply(x, conv_mod.weight, pad64(conv_mod.out_channels))
+    stride = _check_conv(conv_mod)
+    y = StemFunction.apply(x, conv_mod.weight, pad64(conv_mod.out_channels), stride)
     return bn_act(y, bn, relu=True) if bn is not None else y
 
 

@@ -58,6 +58,11 @@ SIGNATURES = {
     "nbdt_stem_fwd": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 5 + [c_ptr]),
     "nbdt_stem_fwd_strided": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 6 + [c_ptr]),
     "nbdt_dwconv_fwd": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 7 + [c_ptr]),
+    "nbdt_dwconv_dgrad": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 6 + [c_ptr]),
+    "nbdt_dwconv_wgrad": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 6 + [c_ptr]),
+    "nbdt_se_dscale": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 3 + [c_ptr]),
+    "nbdt_stem_wgrad_strided": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 6 + [c_ptr]),
+    "nbdt_bn_backward_silu": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nbdt_se_scale": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 3 + [c_ptr]),
     "nbdt_stem_wgrad": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 5 + [c_ptr]),
     "nbdt_sgd_step": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, ctypes.c_longlong, c_f32, c_f32, c_f32, c_f32, ctypes.c_int, c_ptr]),

@@ -3,8 +3,10 @@ BatchNorm + SiLU fused, squeeze-excitation scaling, eval-mode BatchNorm + activa
 implicit-GEMM kernel.  NHWC bf16 activations with the channel count padded to a multiple of 64 (padding channels
 are exactly zero everywhere: zero weights, zero BN scale/shift, SiLU(0) = 0).
 
-Everything here is forward-only (csrc/mbconv_ops.cu has no backward kernels yet): calling it with autograd enabled on
-parameters that require grad raises instead of silently detaching."""
+The functions in the first half are the inference path (folded BatchNorm, cached packed weights): calling them with
+autograd enabled on parameters that require grad raises instead of silently detaching.  `DepthwiseConvFunction` and
+`SEScaleFunction` are the autograd functions of the training path (depthwise dgrad / wgrad, squeeze-excitation gradient
+kernels); the 1x1 convolutions and BatchNorm + SiLU of the training path are nn_ops.ConvFunction / BatchNormActFunction."""
 import torch
 
 from . import conv_ops as C
@@ -153,3 +155,75 @@ def se_scale(x, s):
         L.check(L.load().nbdt_se_scale(_p(x), _p(s), _p(y), N, H * W, Cp, _stream(x)))
     _count()
     return y
+
+
+def _pack_dw(weight, c_phys):
+    """[C,1,k,k] -> tap-major [k*k][c_phys] fp32, zero for the padding channels."""
+    ch, _, k, _ = weight.shape
+    w = torch.zeros((k * k, c_phys), dtype=torch.float32, device=weight.device)
+    w[:, :ch] = weight.detach().float().reshape(ch, k * k).t()
+    return w
+
+
+class DepthwiseConvFunction(torch.autograd.Function):
+    """Depthwise k x k convolution (k in {3, 5}, stride 1 or 2, padding k//2) on NHWC bf16 activations."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride):
+        C._check_act(x, "depthwise conv input")
+        N, H, W, Cp = x.shape
+        ch, _, k, _ = weight.shape
+        assert Cp >= ch
+        w = _pack_dw(weight, Cp)
+        y = torch.empty((N, (H + stride - 1) // stride, (W + stride - 1) // stride, Cp), dtype=torch.bfloat16, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.load().nbdt_dwconv_fwd(_p(x), _p(w), None, _p(y), N, H, W, Cp, k, int(stride), ACT_NONE, _stream(x)))
+        _count()
+        ctx.save_for_backward(x, w)
+        ctx.meta = (tuple(weight.shape), int(stride))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        wshape, stride = ctx.meta
+        ch, _, k, _ = wshape
+        N, H, W, Cp = x.shape
+        dy = dy.contiguous()
+        dx = dw = None
+        lib = L.load()
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                L.check(lib.nbdt_dwconv_dgrad(_p(dy), _p(w), _p(dx), N, H, W, Cp, k, stride, _stream(x)))
+                _count()
+            if ctx.needs_input_grad[1]:
+                dwp = torch.empty((k * k, Cp), dtype=torch.float32, device=x.device)
+                L.check(lib.nbdt_dwconv_wgrad(_p(x), _p(dy), _p(dwp), N, H, W, Cp, k, stride, _stream(x)))
+                _count(2)
+                dw = dwp[:, :ch].t().reshape(wshape)
+        return dx, dw, None
+
+
+class SEScaleFunction(torch.autograd.Function):
+    """y[n,h,w,c] = x[n,h,w,c] * s[n,c]  (s fp32 (N, C_phys)); also used for stochastic depth (s = mask / keep_prob)."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.save_for_backward(x, s)
+        return se_scale(x, s)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, s = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ds = None
+        if ctx.needs_input_grad[0]:
+            dx = se_scale(dy, s)
+        if ctx.needs_input_grad[1]:
+            N, H, W, Cp = x.shape
+            ds = torch.empty((N, Cp), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                L.check(L.load().nbdt_se_dscale(_p(x), _p(dy), _p(ds), N, H * W, Cp, _stream(x)))
+            _count(2)
+        return dx, ds

@@ -48,22 +48,23 @@ def _pad_vec(v, n, fill=0.0):
 
 
 class StemFunction(torch.autograd.Function):
-    """3x3 stride-1 conv on the 3-channel NCHW fp32 input -> NHWC bf16 with `c_phys` physical channels."""
+    """3x3 conv (stride 1 or 2, padding 1) on the 3-channel NCHW fp32 input -> NHWC bf16 with `c_phys` physical channels."""
 
     @staticmethod
-    def forward(ctx, x, weight, c_phys):
+    def forward(ctx, x, weight, c_phys, stride=1):
         L.require_cuda(x, "stem conv")
         x = x.float().contiguous()
         w = weight.detach().float().contiguous()
         N, cin, H, W = x.shape
         assert cin == 3 and tuple(w.shape[1:]) == (3, 3, 3), "the stem kernel handles 3x3 convs on 3 input channels"
         cout = w.shape[0]
-        y = torch.empty((N, H, W, c_phys), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((N, (H + stride - 1) // stride, (W + stride - 1) // stride, c_phys), dtype=torch.bfloat16,
+                        device=x.device)
         with torch.cuda.device(x.device):
-            L.check(L.load().nbdt_stem_fwd(_p(x), _p(w), _p(y), N, H, W, cout, c_phys, _stream(x)))
+            L.check(L.load().nbdt_stem_fwd_strided(_p(x), _p(w), _p(y), N, H, W, cout, c_phys, int(stride), _stream(x)))
         _count()
         ctx.save_for_backward(x)
-        ctx.cout, ctx.c_phys = cout, c_phys
+        ctx.cout, ctx.c_phys, ctx.stride = cout, c_phys, int(stride)
         return y
 
     @staticmethod
@@ -73,9 +74,10 @@ class StemFunction(torch.autograd.Function):
         N, _, H, W = x.shape
         dw = torch.empty((ctx.cout, 3, 3, 3), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            L.check(L.load().nbdt_stem_wgrad(_p(x), _p(dy), _p(dw), N, H, W, ctx.cout, ctx.c_phys, _stream(x)))
+            L.check(L.load().nbdt_stem_wgrad_strided(_p(x), _p(dy), _p(dw), N, H, W, ctx.cout, ctx.c_phys, ctx.stride,
+                                                     _stream(x)))
         _count()
-        return None, dw, None
+        return None, dw, None, None
 
 
 class ConvFunction(torch.autograd.Function):
@@ -90,7 +92,9 @@ class ConvFunction(torch.autograd.Function):
         cout, cin, k, _ = weight.shape
         cin_phys = x.shape[3]
         assert cin_phys >= cin
-        wp, wpt = C.pack_weights(weight, cin_pad=cin_phys, cout_pad=cout)
+        # output channels the GEMM tiles can cover (multiples of 64 / 128 / 160); others are zero-padded to 64s
+        cout_phys = cout if (cout % 64 == 0 or cout % 160 == 0) else C.pad64(cout)
+        wp, wpt = C.pack_weights(weight, cin_pad=cin_phys, cout_pad=cout_phys)
         y = C.conv_fwd(x, wp, k, stride, residual)
         ctx.save_for_backward(x, wpt)
         ctx.meta = (tuple(weight.shape), k, stride, residual is not None)
@@ -151,15 +155,18 @@ class BatchNormActFunction(torch.autograd.Function):
                 L.check(lib.nbdt_bn_eval_scale(Cp, c_real, _p(g), _p(b), _p(running_mean), _p(running_var), float(eps),
                                                _p(scale_shift), _stream(x)))
                 _count()
+            act = int(relu)  # activation code: 0 none, 1 ReLU, 2 SiLU
+            if act == 2 and residual is not None:
+                raise NotImplementedError("SiLU after a residual add is not implemented")
             y = torch.empty_like(x)
-            L.check(lib.nbdt_bn_apply(_p(x), _p(residual), _p(y), M, Cp, _p(scale_shift), int(relu), _stream(x)))
+            L.check(lib.nbdt_bn_apply(_p(x), _p(residual), _p(y), M, Cp, _p(scale_shift), act, _stream(x)))
             _count()
         ctx.training = training
-        ctx.meta = (M, Cp, c_real, relu, residual is not None)
+        ctx.meta = (M, Cp, c_real, act, residual is not None)
         # ReLU mask in backward: recomputed from x and scale/shift (bit-identical fmaf) unless a residual was added
-        # before the activation, in which case the saved output is needed
-        mask_from_act = relu and residual is not None
-        ctx.save_for_backward(x, y if mask_from_act else None, scale_shift if (relu and not mask_from_act) else None,
+        # before the activation, in which case the saved output is needed; SiLU's gradient is always recomputed
+        mask_from_act = act == 1 and residual is not None
+        ctx.save_for_backward(x, y if mask_from_act else None, scale_shift if (act and not mask_from_act) else None,
                               g, mean_invstd)
         ctx.set_materialize_grads(False)
         if want_skip:
@@ -180,8 +187,12 @@ class BatchNormActFunction(torch.autograd.Function):
         dres = torch.empty_like(x) if has_res else None
         dsums = torch.empty((L.load().nbdt_bn_scratch_floats(Cp),), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            L.check(L.load().nbdt_bn_backward(_p(x), _p(act), _p(scale_shift), _p(dy), _p(extra), _p(dx), _p(dres), M, Cp,
-                                              c_real, _p(g), _p(mean_invstd), _p(dsums), _stream(x)))
+            if relu == 2:
+                L.check(L.load().nbdt_bn_backward_silu(_p(x), _p(scale_shift), _p(dy), _p(extra), _p(dx), M, Cp, c_real,
+                                                       _p(g), _p(mean_invstd), _p(dsums), _stream(x)))
+            else:
+                L.check(L.load().nbdt_bn_backward(_p(x), _p(act), _p(scale_shift), _p(dy), _p(extra), _p(dx), _p(dres), M,
+                                                  Cp, c_real, _p(g), _p(mean_invstd), _p(dsums), _stream(x)))
         _count(3)
         return dx, dsums[Cp:Cp + c_real], dsums[:c_real], None, None, None, None, None, None, dres, None
 

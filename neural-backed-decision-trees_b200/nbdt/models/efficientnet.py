@@ -13,9 +13,12 @@ checkpoints load with `load_state_dict(strict=True)` -- and runs the forward pas
             -> 1x1 project conv on tcgen05 -> BN (+ residual) in one pass
   head      1x1 conv 320 -> 1280 -> BN + SiLU -> global average pool -> Linear (library GEMM)
 
-Activations are NHWC bf16 with channel counts padded to multiples of 64.  Eval-mode only: BatchNorm uses the running
-statistics, StochasticDepth / Dropout are identities (as in torchvision's eval mode); training kernels (depthwise
-dgrad / wgrad, SiLU and SE backward) are not built yet and a forward in training mode raises.
+Activations are NHWC bf16 with channel counts padded to multiples of 64.  Eval mode: folded BatchNorm (running statistics),
+depthwise conv + BN + SiLU in one kernel, cached packed weights; StochasticDepth / Dropout are identities.  Training mode:
+batch-statistics BatchNorm + SiLU through nn_ops.BatchNormActFunction (SiLU gradient recomputed in the backward kernels),
+1x1 convs through nn_ops.ConvFunction (tcgen05 fwd / dgrad / wgrad), depthwise conv and squeeze-excitation through
+mbconv_ops.DepthwiseConvFunction / SEScaleFunction, row-mode stochastic depth as a per-image scale, dropout on the pooled
+features.
 """
 import math
 
@@ -23,6 +26,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from nbdt._b200 import backbone as B
 from nbdt._b200 import conv_ops as C
 from nbdt._b200 import mbconv_ops as M
 from nbdt._b200.nn_ops import AvgPoolFunction
@@ -55,15 +59,14 @@ class SqueezeExcitation(nn.Module):
         self.scale_activation = nn.Sigmoid()
 
     def forward(self, x):
-        """x: NHWC bf16 (N, H, W, C_phys) -> x * sigmoid(fc2(silu(fc1(mean_hw x))))."""
-        M.require_inference(self.fc1.weight, self.fc2.weight, x)
+        """x: NHWC bf16 (N, H, W, C_phys) -> x * sigmoid(fc2(silu(fc1(mean_hw x)))).  Differentiable: the pooling and the
+        scaling are own kernels with backward kernels, the two tiny FC layers are library GEMMs under autograd."""
         c = self.fc1.in_channels
-        pooled = AvgPoolFunction.apply(x)  # (N, C_phys) fp32, own kernel
+        pooled = AvgPoolFunction.apply(x)  # (N, C_phys) fp32
         s = F.linear(pooled[:, :c], self.fc1.weight.flatten(1), self.fc1.bias)
         s = F.linear(F.silu(s), self.fc2.weight.flatten(1), self.fc2.bias)
-        scale = torch.zeros_like(pooled)
-        scale[:, :c] = torch.sigmoid(s)
-        return M.se_scale(x, scale)
+        scale = F.pad(torch.sigmoid(s), (0, pooled.shape[1] - c))  # padding channels stay zero
+        return M.SEScaleFunction.apply(x, scale)
 
 
 class MBConv(nn.Module):
@@ -84,13 +87,32 @@ class MBConv(nn.Module):
     def forward(self, x):
         y = x
         mods = list(self.block)
-        if len(mods) == 4:
-            y = M.bn_act_eval(M.conv1x1(y, mods[0][0]), mods[0][1], M.ACT_SILU)
         dw, se, proj = mods[-3], mods[-2], mods[-1]
-        y = M.dwconv_bn_act(y, dw[0], dw[1], M.ACT_SILU)
+        if not self.training:
+            if len(mods) == 4:
+                y = M.bn_act_eval(M.conv1x1(y, mods[0][0]), mods[0][1], M.ACT_SILU)
+            y = M.dwconv_bn_act(y, dw[0], dw[1], M.ACT_SILU)
+            y = se(y)
+            y = M.conv1x1(y, proj[0])
+            return M.bn_act_eval(y, proj[1], M.ACT_NONE, residual=x if self.use_res_connect else None)
+        # training: batch-statistics BatchNorm, autograd functions over the fwd / dgrad / wgrad kernels
+        if len(mods) == 4:
+            y = B.bn_act(B.conv(y, mods[0][0]), mods[0][1], relu=M.ACT_SILU)
+        conv = dw[0]
+        y = M.DepthwiseConvFunction.apply(y, conv.weight, conv.stride[0])
+        y = B.bn_act(y, dw[1], relu=M.ACT_SILU)
         y = se(y)
-        y = M.conv1x1(y, proj[0])
-        return M.bn_act_eval(y, proj[1], M.ACT_NONE, residual=x if self.use_res_connect else None)
+        y = B.conv(y, proj[0])
+        if not self.use_res_connect:
+            return B.bn_act(y, proj[1], relu=M.ACT_NONE)
+        if self.sd_prob <= 0.0:
+            return B.bn_act(y, proj[1], relu=M.ACT_NONE, residual=x)  # residual add fused into the BN apply pass
+        # stochastic depth, "row" mode (torchvision.ops.StochasticDepth): drop the whole branch per image, rescale the rest
+        y = B.bn_act(y, proj[1], relu=M.ACT_NONE)
+        keep = 1.0 - self.sd_prob
+        noise = torch.empty(y.shape[0], device=y.device, dtype=torch.float32).bernoulli_(keep) / keep
+        y = M.SEScaleFunction.apply(y, noise[:, None].expand(y.shape[0], y.shape[3]).contiguous())
+        return y + x
 
 
 class EfficientNet(nn.Module):
@@ -126,21 +148,28 @@ class EfficientNet(nn.Module):
                 nn.init.zeros_(m.bias)
 
     def forward(self, x):
-        if self.training:
-            raise NotImplementedError("EfficientNet on nbdt-b200 is inference-only so far: call .eval() "
-                                      "(NBDT wrappers do, nbdt/model.py:343-344)")
         f = self.features
         stem = f[0]
-        y = M.stem(x, stem[0], C.pad64(stem[0].out_channels))
-        y = M.bn_act_eval(y, stem[1], M.ACT_SILU)
+        if self.training:
+            y = B.stem(x, stem[0], None)  # strided 3x3 conv, own kernels forward and backward
+            y = B.bn_act(y, stem[1], relu=M.ACT_SILU)
+        else:
+            y = M.stem(x, stem[0], C.pad64(stem[0].out_channels))
+            y = M.bn_act_eval(y, stem[1], M.ACT_SILU)
         for stage in list(f)[1:-1]:
             for block in stage:
                 y = block(y)
         head = f[-1]
-        y = M.bn_act_eval(M.conv1x1(y, head[0]), head[1], M.ACT_SILU)
+        if self.training:
+            y = B.bn_act(B.conv(y, head[0]), head[1], relu=M.ACT_SILU)
+        else:
+            y = M.bn_act_eval(M.conv1x1(y, head[0]), head[1], M.ACT_SILU)
         feat = AvgPoolFunction.apply(y)  # (N, C_phys) fp32
         lin = self.classifier[1]
-        return F.linear(feat[:, : lin.in_features], lin.weight, lin.bias)
+        feat = feat[:, : lin.in_features]
+        if self.training:
+            feat = F.dropout(feat, p=self.classifier[0].p, training=True)
+        return F.linear(feat, lin.weight, lin.bias)
 
 
 def efficientnet_b0(pretrained=False, progress=True, num_classes=1000, weights=None, **kwargs):
