@@ -207,6 +207,8 @@ def run_b200(args, rank, world, local_rank):
     from nbdt._b200 import conv_ops, nn_ops
     from nbdt._b200.optim import FusedSGD
 
+    if os.environ.get("NBDT_B200_WGRAD_STREAM", "1") != "0":
+        nn_ops.enable_wgrad_overlap(True)  # weight-gradient kernels on a side stream; joined before all-reduce / SGD
     torch.manual_seed(0)
     net = wrn28_10_cifar10().to(dev)
     net.train()

@@ -18,8 +18,16 @@ def _stream(t):
 # step), and they are tensor-bound while the BatchNorm backward kernels that follow the data-gradient are HBM-bound:
 # they run on a side stream and overlap (the wgrad CTAs leave enough shared memory for the BN CTAs to co-reside).
 # Only when the gradient goes straight into a FusedSGD flat buffer -- the optimizer step joins the side stream.
+# OPT-IN (enable_wgrad_overlap(True) or NBDT_B200_WGRAD_STREAM=1): with it on, parameter gradients are complete only after
+# join_wgrad_streams() -- FusedSGD.step() and FlatGradientAllReduce.reduce() call it, code that reads .grad right after
+# backward() (gradient clipping, logging) must call it itself.  bench.py turns it on.
 _SIDE_STREAMS = {}
-_OVERLAP_WGRAD = os.environ.get("NBDT_B200_WGRAD_STREAM", "1") != "0"
+_OVERLAP_WGRAD = os.environ.get("NBDT_B200_WGRAD_STREAM", "0") == "1"
+
+
+def enable_wgrad_overlap(on=True):
+    global _OVERLAP_WGRAD
+    _OVERLAP_WGRAD = bool(on)
 
 
 def wgrad_stream(device):

@@ -150,3 +150,22 @@ def test_efficientnet_b0_keeps_torchvision_layout():
     ours.load_state_dict(b, strict=True)
     assert sum(p.numel() for p in ours.parameters()) == 5288548
     assert efficientnet_b0(num_classes=10).classifier[1].out_features == 10
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference: exactly one JSON line on stdout with the contract's keys (the CPU arm of the brief)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-batch", "2"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    r = json.loads(lines[0])
+    assert r["impl"] == "reference" and r["unit"] == "images/sec" and r["value"] > 0 and r["higher_is_better"] is True
+    assert r["cpu_baseline"]["kind"] == "port" and r["cpu_baseline"]["cores"] >= 1
+    assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["value"] == r["value"]
