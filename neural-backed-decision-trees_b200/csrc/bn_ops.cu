@@ -2,10 +2,11 @@
 // parameters and statistics): training-mode BatchNorm statistics / apply(+ReLU, +residual) / backward,
 // global average pooling, the 3-channel stem convolution, fused SGD.
 //
-// Every kernel streams its tensors once with 16-byte vector accesses (8 bf16 channels per thread),
-// keeps per-channel partial sums in registers, reduces them across the CTA in shared memory and
-// finishes with one fp32 atomic per channel per CTA.  Roofline: HBM; algorithmic bytes are listed
-// per kernel below (M = N*H*W rows, C channels).
+// Every kernel streams its tensors once with 16-byte vector accesses (8 bf16 channels per thread); the
+// reductions keep per-channel partial sums in registers, combine them across the CTA in shared memory and
+// write one partial per CTA that a sliced finalize kernel sums in a fixed order (deterministic).
+// Roofline: HBM; algorithmic bytes are listed per kernel below (M = N*H*W rows, C channels); measured
+// fractions: profiles/r01_bn_kernels.md.
 //
 // Replaces, in the reference's backbones, nn.BatchNorm2d + F.relu (+ residual add)
 // (nbdt/models/resnet.py:50-54,70-73 and the pytorchcv pre-activation blocks), F.avg_pool2d

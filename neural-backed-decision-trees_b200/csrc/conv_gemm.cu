@@ -17,12 +17,23 @@
 // CTA layout (192 threads, persistent, one CTA per SM):
 //   warp 0    TMA producer: per (tap, 64-channel k-block) one A box + one B (weights) box into a
 //             kStages-deep shared-memory ring, completion signalled on `full` mbarriers
-//   warp 1    MMA issuer: one elected thread issues 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per stage,
+//   warp 1    MMA issuer: one elected thread issues the tcgen05.mma's of a stage (K = 16 each),
 //             tcgen05.commit releases the stage (`empty`) and finally publishes the accumulator
 //   warps 2-5 epilogue: tcgen05.ld the fp32 accumulator (TMEM, double buffered so the next tile's MMAs
 //             overlap), optional residual add, convert to bf16, vectorised global stores
 //
-// Roofline: tensor-pipe bound.  FLOPs per launch = 2 * N*Ho*Wo * Cout * Cin * taps.
+// Three forward / data-gradient kernels share that layout (launch_tap_gemm picks one):
+//   tap_gemm_kernel    one CTA per 128-pixel tile, M = 128 (small problems)
+//   tap_gemm2_kernel   a 2-CTA cluster per pair of tiles, tcgen05.mma.cta_group::2 with M = 256: each CTA stages
+//                      half of the weight tile
+//   tap_gemm2h_kernel  the same plus an H-halo activation tile that serves the three taps of a filter column
+//                      (stride-1 3x3 on maps 16 / 32 pixels wide)
+// and wgrad_kernel computes the weight gradient (pixel index = K, MN-major operands, halo tiles for the taps of a
+// filter row / column, team scheduling for operands larger than L2).
+//
+// Roofline: tensor pipe by FLOPs (2 * N*Ho*Wo * Cout * Cin * taps per launch); in practice the L2 -> shared-memory
+// fill rate (~12-14 TB/s chip-wide) bounds the 160-channel layers: every variant above exists to move fewer bytes per MMA
+// (profiles/r01_conv_ncu.md, r01_conv_ncu_v2.md).
 #include <cuda_bf16.h>
 
 #include <algorithm>
