@@ -45,6 +45,22 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------------
+def saturating_tree_point():
+    """The committed bench_tree.py measurement of the same kernel at a saturating size (profiles/r01_tree_sweep_v7.jsonl):
+    reported next to the latency-bound launch of the BASELINE batch, not re-measured here."""
+    path = os.path.join(ROOT, "profiles", "r01_tree_sweep_v7.jsonl")
+    try:
+        with open(path) as f:
+            for line in f:
+                r = json.loads(line)
+                if r.get("dataset") == "CIFAR10" and r.get("dtype") == "float32" and r.get("kind") == "soft":
+                    return {"rows": r["rows"], "classes": r["C"], "gbs": r["gbs"], "frac": r["frac"], "ms": r["ms"],
+                            "source": "profiles/r01_tree_sweep_v7.jsonl (python bench_tree.py --quick on a B200 of this pool)"}
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def usable_cores():
     """Host threads the CPU arm should use: the cores this process may actually run on (affinity mask and cgroup CPU
     quota), then a 1-second calibration -- on a box whose container is throttled below os.cpu_count() an
@@ -417,10 +433,11 @@ def run_b200(args, rank, world, local_rank):
                                       "launches_per_step": v[2] / prof_steps} for k, v in conv_stats.items()},
                      "conv_share_of_step": (conv_ms / prof_steps) / ms_per_step,
                      "timed_with": f"CUDA events around each launch, {prof_steps} eager steps right after the timed region"},
-        "tree_roofline": {"kernel": "tree_kernel<soft loss fwd+bwd>", "bound": "hbm",
+        "tree_roofline": {"kernel": "tree_spec_<hash><float, soft loss fwd+bwd> (memset of the loss scalar + kernel, 50 launches in a CUDA graph)", "bound": "hbm",
                           "achieved": tree_bytes / (tree_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": tree_bytes / (tree_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_us": tree_ms * 1e3,
-                          "note": "45 KB per launch at the BASELINE batch: latency-bound; saturating sweep in profiles/"},
+                          "note": "45 KB per launch at the BASELINE batch: latency-bound; saturating sweep in profiles/",
+                          "saturating_sweep": saturating_tree_point()},
         "step_tflops": FLOPS_PER_IMAGE * B * world / (ms_per_step / 1e3) / 1e12,
         "loss": {"first_step": loss_first, "after_timed_steps": loss_last},  # sanity: the same synthetic batch is being fitted
     }
