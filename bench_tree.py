@@ -55,11 +55,49 @@ def time_point(tree, kind, rows, C, dtype, iters=20, warmup=3, group=None):
             "l2": f"{iters} back-to-back launches rotating over {nsets} buffer sets ({nsets * alg_bytes / 1e6:.0f} MB > L2)"}
 
 
+def cpu_baseline_point(dataset, hierarchy, C, kind="soft", budget_s=3.0):
+    """The plain-C restatement of the reference's per-node algorithm (oracle/tree_oracle.c, OpenMP over rows) on the
+    host cores, on a bounded sample of the same workload: GB/s of the same algorithmic bytes (fp32 logits)."""
+    import time
+
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    from nbdt.utils import dataset_to_default_path_wnids, hierarchy_to_path_graph
+    from oracle import tree_oracle as O
+    from oracle import tree_oracle_c as OC
+
+    ct = OC.CTree(O.OracleTree(hierarchy_to_path_graph(dataset, hierarchy), dataset_to_default_path_wnids(dataset)))
+    rng = np.random.default_rng(0)
+    rows = 4096
+    fn = OC.soft_tree_sup_loss if kind == "soft" else OC.hard_tree_sup_loss
+    while True:
+        x = (3 * rng.standard_normal((rows, C))).astype(np.float32)
+        y = rng.integers(0, C, rows)
+        fn(ct, x[:256], y[:256])
+        t0 = time.time()
+        fn(ct, x, y)
+        dt = time.time() - t0
+        if dt > budget_s / 4 or rows >= (1 << 22):
+            break
+        rows *= 4
+    alg_bytes = 2 * rows * C * 4 + 8 * rows + 4
+    return {"value": alg_bytes / dt / 1e9, "unit": "GB/s", "cores": OC.threads(), "kind": "port",
+            "sample": f"{rows} rows x {C} classes fp32, {kind} loss fwd+bwd, oracle/tree_oracle.c (per-node restatement of the reference, "
+                      f"fp64 arithmetic, OpenMP over rows), {dt * 1e3:.0f} ms"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--group", type=int, default=None)
+    ap.add_argument("--cpu-only", action="store_true", help="only the CPU baselines (no GPU needed)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.cpu_only:
+        for dataset, hierarchy, C in (("CIFAR10", "induced", 10), ("CIFAR100", "induced", 100), ("Imagenet1000", "induced", 1000)):
+            print(json.dumps({"dataset": dataset, "C": C, "cpu_baseline": cpu_baseline_point(dataset, hierarchy, C)}), flush=True)
+        return
     from nbdt.tree import Tree
 
     pk, src = peaks()
@@ -75,6 +113,8 @@ def main():
                 for kind in ("soft",) if args.quick else ("soft", "hard"):
                     r = time_point(tree, kind, rows, C, dtype)
                     r.update(dataset=dataset, frac=r["gbs"] / pk["hbm_gbs"], peak=pk["hbm_gbs"], peak_source=src)
+                    if not args.no_cpu_baseline and dtype == torch.float32 and kind == "soft" and rows == rows_for[C][-1]:
+                        r["cpu_baseline"] = cpu_baseline_point(dataset, hierarchy, C)
                     print(json.dumps(r), flush=True)
 
 

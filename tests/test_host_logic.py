@@ -169,3 +169,18 @@ def test_bench_reference_arm_prints_one_json_line():
     assert r["impl"] == "reference" and r["unit"] == "images/sec" and r["value"] > 0 and r["higher_is_better"] is True
     assert r["cpu_baseline"]["kind"] == "port" and r["cpu_baseline"]["cores"] >= 1
     assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["value"] == r["value"]
+
+
+def test_bench_tree_cpu_baseline_leg():
+    """bench_tree.py's cpu_baseline: the plain-C restatement on the host cores, bounded sample, reported in GB/s."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_tree", os.path.join(root, "bench_tree.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.cpu_baseline_point("CIFAR10", "induced", 10, budget_s=0.05)
+    assert r["unit"] == "GB/s" and r["value"] > 0 and r["cores"] >= 1 and r["kind"] == "port"
+    r = mod.cpu_baseline_point("CIFAR100", "wordnet", 100, kind="hard", budget_s=0.05)
+    assert r["value"] > 0 and "hard" in r["sample"]

@@ -107,6 +107,28 @@ def test_oracle_weight_schedule(case, oracle_trees):
     np.testing.assert_allclose(grad, g["soft_grad_sched_f64"], rtol=2e-5, atol=2e-8)
 
 
+# ---- oracle/tree_oracle.c (plain-C restatement; bench_tree.py's cpu_baseline) pinned to the same golden vectors ----
+@pytest.mark.parametrize("case", TREE_CASES)
+def test_c_oracle_pinned_to_reference(case, oracle_trees):
+    from oracle import tree_oracle_c as OC
+
+    g, t = load_golden(case), oracle_trees[case]
+    ct = OC.CTree(t)
+    x, y = g["logits"], g["targets"]  # float32 logits, as the reference saw them
+    cp = OC.soft_probs(ct, x)
+    np.testing.assert_allclose(cp, g["soft_probs_f64in"], rtol=2e-6, atol=1e-9)
+    np.testing.assert_allclose(cp, O.soft_probs(t, x), rtol=1e-12, atol=1e-15)
+    for tag, xw, tsw in (("default", 1.0, 1.0), ("tsw10", 1.0, 10.0), ("xw05_tsw2", 0.5, 2.0)):
+        ls, gs = OC.soft_tree_sup_loss(ct, x, y, xw, tsw)
+        np.testing.assert_allclose(ls, g[f"soft_loss_{tag}_f64"], rtol=1e-6)
+        np.testing.assert_allclose(gs, g[f"soft_grad_{tag}_f64"], rtol=2e-5, atol=2e-8)
+        lh, gh = OC.hard_tree_sup_loss(ct, x, y, xw, tsw, tsw)
+        np.testing.assert_allclose(lh, g[f"hard_loss_{tag}_f64"], rtol=1e-10)
+        np.testing.assert_allclose(gh, g[f"hard_grad_{tag}_f64"], rtol=1e-9, atol=1e-13)
+    # loss only (no gradient buffer)
+    assert OC.soft_tree_sup_loss(ct, x, y, want_grad=False)[1] is None
+
+
 # ---- oracle/torch_port.py (the CPU baseline bench.py times) pinned to the same golden vectors ----
 @pytest.mark.parametrize("case", ["cifar10_induced", "cifar100_wordnet", "tiny200_induced_resnet18"])
 def test_torch_port_tree_losses(case, oracle_trees):
