@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NBDT_B200_VERSION 100
+#define NBDT_B200_VERSION 101 /* 101: MBConv entry points, nbdt_bn_backward takes scale_shift, strided stem */
 
 enum { NBDT_OK = 0, NBDT_EINVAL = 1, NBDT_ECUDA = 2, NBDT_ETREE = 3, NBDT_ETOOLARGE = 4 };
 enum { NBDT_F32 = 0, NBDT_BF16 = 1, NBDT_F16 = 2 };
