@@ -129,6 +129,26 @@ def test_c_oracle_pinned_to_reference(case, oracle_trees):
     assert OC.soft_tree_sup_loss(ct, x, y, want_grad=False)[1] is None
 
 
+@pytest.mark.parametrize("leaves,kmax,seed,chain", [(7, 2, 0, 0.0), (33, 5, 1, 0.5), (100, 13, 2, 0.0), (257, 3, 3, 0.9)])
+def test_c_oracle_equals_numpy_oracle_on_random_hierarchies(tmp_path, leaves, kmax, seed, chain):
+    """Ragged / deep / wide hierarchies the golden set does not contain: the two restatements must agree to round-off."""
+    from conftest import write_random_hierarchy
+    from oracle import tree_oracle_c as OC
+
+    t = O.OracleTree(*write_random_hierarchy(tmp_path, leaves, kmax, seed, chain_bias=chain))
+    ct = OC.CTree(t)
+    rng = np.random.default_rng(seed)
+    x = (4 * rng.standard_normal((37, leaves))).astype(np.float32)
+    y = rng.integers(0, leaves, 37)
+    np.testing.assert_allclose(OC.soft_probs(ct, x), O.soft_probs(t, x), rtol=1e-11, atol=1e-300)
+    for fc, fn, kw in ((OC.soft_tree_sup_loss, O.soft_tree_sup_loss, {}),
+                       (OC.hard_tree_sup_loss, O.hard_tree_sup_loss, {"tree_supervision_weight": 3.0})):
+        lc, gc = fc(ct, x, y, 0.7, 3.0, *kw.values())
+        ln, gn = fn(t, x, y, xent_weight=0.7, tree_weight=3.0, **kw)
+        np.testing.assert_allclose(lc, ln, rtol=1e-12)
+        np.testing.assert_allclose(gc, gn, rtol=1e-9, atol=1e-15)
+
+
 # ---- oracle/torch_port.py (the CPU baseline bench.py times) pinned to the same golden vectors ----
 @pytest.mark.parametrize("case", ["cifar10_induced", "cifar100_wordnet", "tiny200_induced_resnet18"])
 def test_torch_port_tree_losses(case, oracle_trees):
