@@ -48,7 +48,81 @@ def _generate():
     mod.main()
 
 
-def build(force=False, verbose=False):
+def _shipped_descs():
+    """(name, C, child_ptr, child_node, root) of every shipped hierarchy, numbered like nbdt/_b200/tables.py."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("gen_tree_kernels", os.path.join(CSRC, "gen_tree_kernels.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    nbdt = os.path.join(HERE, "nbdt")
+    out, seen = [], set()
+    for dataset in sorted(os.listdir(os.path.join(nbdt, "hierarchies"))):
+        for fname in sorted(os.listdir(os.path.join(nbdt, "hierarchies", dataset))):
+            if not fname.endswith(".json"):
+                continue
+            pw = os.path.join(nbdt, "wnids", dataset + ".txt")
+            wnids = [l.strip() for l in open(pw)] if os.path.exists(pw) else None
+            C, children, root = mod.flatten(os.path.join(nbdt, "hierarchies", dataset, fname), wnids)
+            h = mod.fnv1a(C, children, root)
+            if h in seen:
+                continue
+            seen.add(h)
+            ptr = [0]
+            for ch in children:
+                ptr.append(ptr[-1] + len(ch))
+            out.append((f"{dataset}/{fname}", C, ptr, [c for ch in children for c in ch], root))
+    return out
+
+
+def _precompile_one(job):
+    import ctypes
+
+    name, C, ptr, nodes, root, mode, dtype = job
+    lib = ctypes.CDLL(LIB)
+
+    class Desc(ctypes.Structure):
+        _fields_ = [("num_classes", ctypes.c_int32), ("num_inodes", ctypes.c_int32), ("root", ctypes.c_int32),
+                    ("child_ptr", ctypes.POINTER(ctypes.c_int32)), ("child_node", ctypes.POINTER(ctypes.c_int32))]
+
+    a = (ctypes.c_int32 * len(ptr))(*ptr)
+    b = (ctypes.c_int32 * len(nodes))(*nodes)
+    d = Desc(C, len(ptr) - 1, root, a, b)
+    lib.nbdt_tree_jit_precompile.argtypes = [ctypes.POINTER(Desc), ctypes.c_int, ctypes.c_int]
+    rc = lib.nbdt_tree_jit_precompile(ctypes.byref(d), mode, dtype)
+    lib.nbdt_last_error.restype = ctypes.c_char_p
+    return name, mode, dtype, rc, (lib.nbdt_last_error() or b"").decode() if rc else ""
+
+
+def precompile_tree_kernels(verbose=False):
+    """Populate lib/tree_cache/ with the run-time-specialised tree kernels (csrc/tree_jit.cu) of every shipped hierarchy with
+    at most 256 leaves: soft loss, hard loss, soft forward x fp32, bf16, fp16.  NVRTC needs no GPU.  Any other hierarchy is
+    compiled on first use at run time; this only moves the few seconds per kernel to build time."""
+    from concurrent.futures import ProcessPoolExecutor
+
+    jobs = [(name, C, ptr, nodes, root, mode, dtype) for name, C, ptr, nodes, root in _shipped_descs() if 2 <= C <= 256
+            for mode in (0, 1, 2) for dtype in (0, 1, 2)]
+    failed = 0
+    with ProcessPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for name, mode, dtype, rc, err in ex.map(_precompile_one, jobs):
+            if rc != 0:
+                failed += 1
+                sys.stderr.write(f"tree JIT precompile failed for {name} mode {mode} dtype {dtype}: {err}\n")
+            elif verbose:
+                sys.stderr.write(f"tree JIT precompiled {name} mode {mode} dtype {dtype}\n")
+    if failed:
+        sys.stderr.write(f"{failed} of {len(jobs)} tree kernels were not precompiled (they compile at first use instead)\n")
+    return len(jobs) - failed
+
+
+def build(force=False, verbose=False, precompile=True):
+    lib = _build_lib(force, verbose)
+    if precompile:
+        precompile_tree_kernels(verbose)
+    return lib
+
+
+def _build_lib(force=False, verbose=False):
     _generate()
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
@@ -81,4 +155,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, precompile="--no-precompile" not in sys.argv))

@@ -32,6 +32,7 @@
 
 #include "common.h"
 #include "tree_spec.h"
+#include "tree_jit.h"
 #include "tree_v2.h"
 
 namespace {
@@ -427,6 +428,7 @@ struct nbdt_tree {
   int force_g;  // env NBDT_B200_TREE_G (0 = heuristic)
   const SpecEntry* spec;  // hierarchy-specialised straight-line kernels, when generated for this tree
   TreeV2* v2;             // second-generation generic kernel (tree_v2.cu) for the loss / soft-forward modes
+  TreeJit* jit;           // run-time compiled straight-line kernels (tree_jit.cu), any hierarchy up to 256 leaves
 };
 
 namespace {
@@ -521,6 +523,13 @@ int launch(const nbdt_tree* t, int dtype, const Params& p, cudaStream_t stream) 
   if (MODE == kSoftLoss) rc = try_launch_spec(t, kSpecSoftLoss, dtype, p, stream);
   if (MODE == kHardLoss) rc = try_launch_spec(t, kSpecHardLoss, dtype, p, stream);
   if (MODE == kSoftFwd) rc = try_launch_spec(t, kSpecSoftFwd, dtype, p, stream);
+  if (rc < 0 && t->jit && !t->force_g && (MODE == kSoftLoss || MODE == kHardLoss || MODE == kSoftFwd)) {
+    SpecParams sp;
+    sp.x = p.x; sp.B = p.B; sp.ld = p.ld; sp.targets = p.targets; sp.class_probs = p.class_probs; sp.loss = p.loss;
+    sp.grad = p.grad; sp.w_xent = p.w_xent; sp.w_tree = p.w_tree; sp.inv_rows = p.inv_rows; sp.grad_scale = p.grad_scale;
+    rc = tree_jit_launch(t->jit, MODE == kSoftLoss ? kSpecSoftLoss : (MODE == kHardLoss ? kSpecHardLoss : kSpecSoftFwd),
+                         dtype, sp, stream);
+  }
   if (rc < 0 && t->v2 && !t->force_g && (MODE == kSoftLoss || MODE == kHardLoss || MODE == kSoftFwd)) {
     SpecParams sp;
     sp.x = p.x; sp.B = p.B; sp.ld = p.ld; sp.targets = p.targets; sp.class_probs = p.class_probs; sp.loss = p.loss;
@@ -696,6 +705,12 @@ int nbdt_tree_create(const nbdt_tree_desc* d, int device, nbdt_tree** out) {
     dv.sched[gi].down_rounds = down_rounds[gi];
   }
   t->v2 = nullptr;
+  t->jit = nullptr;
+  if (!getenv("NBDT_B200_TREE_GENERIC"))
+    if (int rc3 = tree_jit_create(d, device, t->sm_count, t->max_smem, &t->jit)) {
+      nbdt_tree_destroy(t);
+      return rc3;
+    }
   if (int rc2 = tree_v2_create(d, device, t->sm_count, t->max_smem, &t->v2)) {
     nbdt_tree_destroy(t);
     return rc2;
@@ -707,6 +722,7 @@ int nbdt_tree_create(const nbdt_tree_desc* d, int device, nbdt_tree** out) {
 void nbdt_tree_destroy(nbdt_tree* t) {
   if (!t) return;
   tree_v2_destroy(t->v2);
+  tree_jit_destroy(t->jit);
   if (t->arena) {
     int cur = -1;
     cudaGetDevice(&cur);

@@ -1,0 +1,1220 @@
+// Hierarchy-specialised tree-head / tree-loss kernels, generated and compiled at run time.
+//
+// Why: the table-driven kernels (tree.cu, tree_lv.cu) interpret the hierarchy -- every node costs table loads, index
+// arithmetic and shared-memory traffic -- and are instruction-issue bound far below the HBM roofline.  Here the
+// hierarchy IS the program: for one nbdt_tree_desc this file emits a straight-line CUDA kernel (no loops over nodes, no
+// tables, every constant an immediate), compiles it with NVRTC to an sm_100a cubin, caches the cubin on disk
+// (lib/tree_cache/, pre-populated for the shipped hierarchies by build.py) and launches it through cudaLibrary*.
+// Any hierarchy up to kMaxLeaves leaves gets such a kernel -- shipped, user-supplied or re-induced during training
+// (nbdt/loss.py:303-315 in the reference) -- not only a build-time list.
+//
+// Kernel shape (one THREAD per row, rows of a warp are consecutive):
+//   sweep A  the row is read once with the widest vector loads its size allows, max(x) is taken, and x is parked in
+//            shared memory TRANSPOSED (slot c of thread t at word c*TPB + t: conflict-free scalar access, immediate
+//            offsets).  4*C bytes of shared memory per row is the whole per-row footprint (+ spilled node values).
+//   pass 1   post-order: subtree sums S[v] in registers; per inner node the child probabilities from the node logits
+//            S[c]/#leaves(c) (binary node: one ex2 + one rcp; the SMALLER child probability is kept, its sign bit says
+//            which child it belongs to, so both probabilities keep full relative accuracy); sum exp(x - max) for the
+//            plain cross-entropy rides along.  Node values stay in REGISTERS up to a budget, the rest in shared memory.
+//   pass 2   pre-order: path probabilities P[c] = P[parent]*p[c] (reference nbdt/model.py:207-242 multiplies
+//            probabilities); at a leaf exp(P) by a degree-6 polynomial (FMA pipe), Z = sum exp(P), and the running
+//            prefix F of E = exp(P)*P over the leaves in DFS order overwrites the (dead) x slot.
+//   pass 4   pre-order: with leaves in DFS order every subtree sum of E is a difference of two prefix values and the
+//            target's one-hot term is a step at the target's position, so the bottom-up gradient sweep disappears:
+//            H[c] = T[end_c] - T[beg_c], dm = H[c] - p[c]*H[v], A[c] = A[v] + dm/#leaves(c); leaf slots receive A.
+//   sweep B  x is read again (L2/L1 hit), dL/dx = A + w_x/B*(softmax(x) - onehot) is written with vector stores.
+// The hard loss (loss.py:212-257) needs only pass 1 and ONE pre-order pass (its gradient lives on the target's path).
+// HBM traffic = algorithmic bytes: logits + targets read once, gradient (or class probabilities) written once.
+//
+// Same closed form as tree.cu; reference semantics nbdt/model.py:83-123,207-242 and nbdt/loss.py:191-266.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "tree_jit.h"
+
+namespace {
+
+constexpr int kGeneratorVersion = 7;   // part of the cache key: bump when the emitted code changes
+constexpr int kMaxLeaves = 256;        // 4*C bytes of shared memory per row: above this too few rows fit on an SM
+constexpr int kTPB = 32;               // one warp per CTA: rows are thread-private, only __syncwarp around the cooperative I/O sweeps
+// Shared-memory layout of a 32-row block: slot c (class c, later prefix / gradient) of row r lives at word
+//   c*32 + c/U + rho(r),   rho(r) = (r*K) & 31,   U = elements per I/O vector,   K = ((C/U) & 31) | 1 (odd)
+// Thread-per-row access (fixed c, r = lane): rho is a permutation of the banks -> conflict-free, and the offset of slot c
+// from the thread's base (rho(lane) words) is an immediate.  Cooperative sweeps (a lane holds the U consecutive columns of
+// one vector; consecutive lanes hold consecutive vectors, running on into the next row): for the k-th element of the
+// vectors the bank is (vector index within the row + rho(row)) & 31, and rho advances by C/U (or C/U + 1) per row, so the 32
+// lanes of an instruction hit 32 different banks (31 when C/U is even).  Spilled node values are thread-private: any bank
+// permutation works, they follow the row slots.
+constexpr int kRegValueCap = 168;      // node values kept in registers; the rest go to shared memory
+
+// Tuning knobs (environment, read when a tree is created; non-default values become part of the cache key).
+struct Knobs {
+  int regcap = kRegValueCap;  // NBDT_B200_KA_REGCAP: node values kept in registers
+  int minb = 0;               // NBDT_B200_KA_MINB: __launch_bounds__ min blocks (0 = derived from the register estimate)
+  int unroll = 8;             // NBDT_B200_KA_UNROLL: unroll factor of the I/O sweeps (0 = full)
+  int prefetch = 1;           // NBDT_B200_KA_PREFETCH: row blocks ahead whose lines are prefetched into L2 (0 = off)
+  int maxld = 24;             // NBDT_B200_KA_MAXLD: 16-byte loads a lane keeps in flight in sweep A before their stores
+  int fence = 8;              // NBDT_B200_KA_FENCE: nodes between scheduling fences of the straight-line passes (0 = none)
+  bool is_default() const { return regcap == kRegValueCap && minb == 0 && unroll == 8 && prefetch == 1 && maxld == 24 && fence == 8; }
+};
+Knobs read_knobs() {
+  Knobs k;
+  auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e && *e ? atoi(e) : dflt; };
+  k.regcap = std::max(0, geti("NBDT_B200_KA_REGCAP", k.regcap));
+  k.minb = std::max(0, std::min(32, geti("NBDT_B200_KA_MINB", k.minb)));
+  k.unroll = std::max(0, geti("NBDT_B200_KA_UNROLL", k.unroll));
+  k.prefetch = std::max(0, std::min(8, geti("NBDT_B200_KA_PREFETCH", k.prefetch)));
+  k.maxld = std::max(1, std::min(64, geti("NBDT_B200_KA_MAXLD", k.maxld)));
+  k.fence = std::max(0, geti("NBDT_B200_KA_FENCE", k.fence));
+  return k;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// hierarchy analysis
+// ------------------------------------------------------------------------------------------------------------------
+struct KTree {
+  int C = 0, N = 0, NV = 0, root = 0;        // root: node id (C + index)
+  std::vector<std::vector<int>> ch;          // [N] child node ids (leaf c -> c, inner i -> C + i)
+  std::vector<int> cnt, beg, end;            // [NV] #leaves, DFS leaf range [beg, end)
+  std::vector<int> pos, leaf_at;             // [C] DFS position of class c; class at DFS position
+  unsigned long long hash = 0;
+  int max_children = 0;
+};
+
+unsigned long long fnv(const nbdt_tree_desc* d) {
+  unsigned long long h = 0xCBF29CE484222325ull;
+  auto mix = [&](int v) {
+    for (int b = 0; b < 4; ++b) {
+      h ^= (unsigned long long)((v >> (8 * b)) & 0xFF);
+      h *= 0x100000001B3ull;
+    }
+  };
+  mix(d->num_classes); mix(d->num_inodes); mix(d->root);
+  for (int i = 0; i <= d->num_inodes; ++i) mix(d->child_ptr[i]);
+  for (int i = 0; i < d->child_ptr[d->num_inodes]; ++i) mix(d->child_node[i]);
+  return h;
+}
+
+void analyse(const nbdt_tree_desc* d, KTree* t) {  // desc already validated by nbdt_tree_create
+  t->C = d->num_classes; t->N = d->num_inodes; t->NV = t->C + t->N; t->root = t->C + d->root;
+  t->ch.resize(t->N);
+  for (int i = 0; i < t->N; ++i) {
+    t->ch[i].assign(d->child_node + d->child_ptr[i], d->child_node + d->child_ptr[i + 1]);
+    t->max_children = std::max(t->max_children, (int)t->ch[i].size());
+  }
+  t->cnt.assign(t->NV, 0); t->beg.assign(t->NV, 0); t->end.assign(t->NV, 0);
+  t->pos.assign(t->C, 0); t->leaf_at.assign(t->C, 0);
+  // iterative DFS in child order: leaves get consecutive positions
+  struct Frame { int v; size_t k; };
+  std::vector<Frame> st;
+  st.push_back({t->root, 0});
+  t->beg[t->root] = 0;
+  int next = 0;
+  while (!st.empty()) {
+    Frame& f = st.back();
+    const std::vector<int>& c = t->ch[f.v - t->C];
+    if (f.k == c.size()) {
+      t->end[f.v] = next;
+      t->cnt[f.v] = next - t->beg[f.v];
+      st.pop_back();
+      continue;
+    }
+    const int u = c[f.k++];
+    if (u < t->C) {
+      t->pos[u] = next; t->leaf_at[next] = u; t->beg[u] = next; t->end[u] = next + 1; t->cnt[u] = 1;
+      ++next;
+    } else {
+      t->beg[u] = next;
+      st.push_back({u, 0});
+    }
+  }
+  t->hash = fnv(d);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// code generation
+// ------------------------------------------------------------------------------------------------------------------
+struct Variant {
+  int mode;    // kSpecSoftLoss / kSpecHardLoss / kSpecSoftFwd
+  int dtype;   // NBDT_F32 / BF16 / F16
+  int vec;     // bytes per logits/gradient vector access (16, 8, 4, 2)
+  int ovec;    // bytes per class_probs vector store (soft forward)
+  int key() const { return ((mode * 4 + dtype) * 32 + vec) * 32 + ovec; }
+};
+
+struct Plan {
+  int nvalues = 0;                 // persistent node values
+  int nspill = 0;                  // of which in shared memory
+  std::vector<int> value_slot;     // [NV]: first value index of node v's values (binary inner: 1 value at the node; k-ary: per child)
+  int smem_bytes = 0;              // per CTA (upper bound over the variants' skew)
+  int min_blocks = 1;              // __launch_bounds__ second argument
+  Knobs knobs;
+};
+
+struct Out {
+  std::string s;
+  void f(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    va_list ap2;
+    va_copy(ap2, ap);
+    const int n = vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (n < (int)sizeof buf) {
+      s.append(buf, (size_t)std::max(n, 0));
+    } else {
+      std::vector<char> big((size_t)n + 1);
+      vsnprintf(big.data(), big.size(), fmt, ap2);
+      s.append(big.data(), (size_t)n);
+    }
+    va_end(ap2);
+    s.push_back('\n');
+  }
+};
+
+std::string lit(double v) {  // exact fp32 literal
+  char buf[64];
+  snprintf(buf, sizeof buf, "%af", (double)(float)v);
+  return buf;
+}
+
+constexpr double kLog2e = 1.4426950408889634;
+
+const char* kPrelude = R"SRC(
+// GENERATED by csrc/tree_jit.cu -- hierarchy-specialised straight-line tree kernel (see that file for the scheme).
+struct KAParams {
+  const void* x; long long B, ld; const long long* targets; float* class_probs; float* loss; void* grad;
+  float w_xent, w_tree, inv_rows, grad_scale;
+};
+#ifndef KA_HOST
+#define KA_DEV __device__ __forceinline__
+typedef unsigned int u32;
+typedef u32 KA_XSB;  // shared-memory byte address of the thread's slot 0
+typedef unsigned short u16;
+KA_DEV float ex2(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+KA_DEV float lg2(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+KA_DEV float rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+KA_DEV float u2f(u32 v) { return __uint_as_float(v); }
+KA_DEV u32 f2u(float v) { return __float_as_uint(v); }
+KA_DEV float h2f(u32 v) { float r; asm("{ .reg .b16 h; cvt.u16.u32 h, %1; cvt.f32.f16 %0, h; }" : "=f"(r) : "r"(v)); return r; }
+KA_DEV u32 pack_bf16(float lo, float hi) { u32 r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+KA_DEV u32 pack_f16(float lo, float hi) { u32 r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+KA_DEV uint4 ld16(const char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+KA_DEV uint2 ld8(const char* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+KA_DEV u32 ld4(const char* p) { return __ldg(reinterpret_cast<const u32*>(p)); }
+KA_DEV u32 ld2(const char* p) { return __ldg(reinterpret_cast<const u16*>(p)); }
+// second read of the row in sweep B: volatile so that it is not merged with sweep A's loads (which would keep the whole row live)
+KA_DEV uint4 ld16b(const char* p) { uint4 r; asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r; }
+KA_DEV uint2 ld8b(const char* p) { uint2 r; asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p)); return r; }
+KA_DEV u32 ld4b(const char* p) { u32 r; asm volatile("ld.global.u32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }
+KA_DEV u32 ld2b(const char* p) { u32 r; asm volatile("{ .reg .b16 h; ld.global.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(r) : "l"(p)); return r; }
+#define KA_LDX(dst, base, slot, off) float dst; asm volatile("ld.shared.f32 %0, [%1+" #off "];" : "=f"(dst) : "r"(base))
+#define KA_STX(base, slot, off, val) asm volatile("st.shared.f32 [%0+" #off "], %1;" :: "r"(base), "f"(val))
+#define KA_OPAQUE(x) asm volatile("" : "+f"(x))
+#define KA_DYN_OFF(idx) ((u32)(idx) * 128u + ((u32)(idx) / KA_U) * 4u)
+#define KA_ADDX_DYN(idx, val) { float dv_; const u32 da_ = xsb + KA_DYN_OFF(idx); asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dv_) : "r"(da_)); dv_ += (val); asm volatile("st.shared.f32 [%0], %1;" :: "r"(da_), "f"(dv_)); }
+#define KA_LDX_DYN(dst, idx) float dst; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dst) : "r"(xsb + KA_DYN_OFF(idx)))
+#define KA_STX_DYN(idx, val) asm volatile("st.shared.f32 [%0], %1;" :: "r"(xsb + KA_DYN_OFF(idx)), "f"(val))
+// cooperative sweeps: slot `col` (a multiple of the vector size) of row `row` of the block, and accesses relative to it
+#define KA_SLOT_ADDR(base, col, row) ((base) + ((u32)(col) * 32u + (u32)(col) / KA_U + (((u32)(row) * KA_K) & 31u)) * 4u)
+#define KA_STD(a, k, off, val) asm volatile("st.shared.f32 [%0+" #off "], %1;" :: "r"(a), "f"(val))
+#define KA_LDD(dst, a, k, off) float dst; asm volatile("ld.shared.f32 %0, [%1+" #off "];" : "=f"(dst) : "r"(a))
+// per-row (-log2 sum exp(x), weight of the plain cross-entropy term) pair
+#define KA_STS2(rsb, v0, v1) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(rsb), "f"(v0), "f"(v1))
+#define KA_LDS2(rsw, row, d0, d1) float d0, d1; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(d0), "=f"(d1) : "r"((rsw) + (u32)(row) * 8u))
+KA_DEV void st16(char* p, u32 a, u32 b, u32 c, u32 d) { *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d); }
+KA_DEV void st8(char* p, u32 a, u32 b) { *reinterpret_cast<uint2*>(p) = make_uint2(a, b); }
+KA_DEV void st4(char* p, u32 a) { *reinterpret_cast<u32*>(p) = a; }
+KA_DEV void st2(char* p, u32 a) { *reinterpret_cast<u16*>(p) = (u16)a; }
+#endif
+// exp(t), t in [0, 1] (a class probability): degree-6 interpolant on the FMA pipe, max rel. error 1.5e-7
+KA_DEV float exp01(float t) {
+  float r = 0.002307842718437314f;
+  r = fmaf(r, t, 0.0069595566019415855f);
+  r = fmaf(r, t, 0.04264117032289505f);
+  r = fmaf(r, t, 0.16631804406642914f);
+  r = fmaf(r, t, 0.5000588297843933f);
+  r = fmaf(r, t, 0.9999963045120239f);
+  return fmaf(r, t, 1.0f);
+}
+// smaller child probability of a binary node with the sign bit set when it belongs to the SECOND child
+// (t = node logit of the first child minus that of the second, in log2 units)
+KA_DEV float signed_lo(float t) {
+  const float q = ex2(-fabsf(t));
+  const float lo = q * rcp(1.f + q);
+  return u2f(f2u(lo) | (~f2u(t) & 0x80000000u));
+}
+KA_DEV bool first_is_hi(float s) { return (int)f2u(s) < 0; }
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+)SRC";
+
+struct Gen {
+  const KTree& t;
+  const Variant v;
+  const Plan& plan;
+  Out o;
+  int acc = 0;  // round-robin partial accumulators
+  Gen(const KTree& t_, const Variant& v_, const Plan& p_) : t(t_), v(v_), plan(p_) {}
+
+  bool leaf(int n) const { return n < t.C; }
+  const std::vector<int>& kids(int n) const { return t.ch[n - t.C]; }
+  bool binary(int n) const { return kids(n).size() == 2; }
+  bool loss_mode() const { return v.mode != kSpecSoftFwd; }
+  int esz() const { return v.dtype == NBDT_F32 ? 4 : 2; }
+
+  // ---- persistent node values: register variable or shared-memory slot ----
+  // value id of a binary node = plan.value_slot[node]; of child k of a k-ary node = plan.value_slot[node] + k
+  bool spilled(int vid) const { return vid >= plan.nvalues - plan.nspill; }
+  int tmp = 0;
+  // Scheduling fences.  The passes are one basic block of thousands of instructions with hundreds of independent chains;
+  // left alone ptxas front-loads as many of them as it can and spills hundreds of registers.  Every `fence` nodes the next
+  // node's input is OR-ed with (last value produced & zr), zr a run-time zero: a real data dependency that changes no value
+  // and costs one LOP3, so the scheduler's window is a group of nodes rather than the whole pass.
+  int since = 0, nfence = 0;
+  std::string last;
+  std::string base = "xsb";
+  void note(const std::string& name) { last = name; ++since; }
+  bool fence_due() const { return plan.knobs.fence > 0 && since >= plan.knobs.fence && !last.empty(); }
+  std::string fenced(const std::string& val) {
+    if (!fence_due()) return val;
+    since = 0;
+    char b[32];
+    snprintf(b, sizeof b, "fz%d", nfence++);
+    o.f("    const float %s = u2f(f2u(%s) | (f2u(%s) & zr));", b, val.c_str(), last.c_str());
+    return b;
+  }
+  void fence_base() {  // same for the shared-memory base of the following loads / stores
+    if (!fence_due()) return;
+    since = 0;
+    char b[32];
+    snprintf(b, sizeof b, "xb%d", nfence++);
+    o.f("    const KA_XSB %s = xsb + (f2u(%s) & zr);", b, last.c_str());
+    base = b;
+  }
+  int U = 1, K = 1;  // skew unit and row multiplier of the shared-memory layout (see the layout comment at the top)
+  int row_words() const { return (t.C * 32 + t.C / U + 32 + 3) & ~3; }
+  int soff(int slot) const {  // byte offset of a slot from the thread's base
+    if (slot < t.C) return (slot * 32 + slot / U) * 4;
+    return (row_words() + (slot - t.C) * 32) * 4;
+  }
+  int eoff(int k) const { return (k * 32 + k / U) * 4; }  // element k of a vector, relative to the vector's first slot
+  // shared-memory slot access: slots 0..C-1 are the row (x -> prefix F -> gradient), C.. the spilled node values.
+  // Emitted as volatile inline PTX with immediate offsets (KA_LDX / KA_STX): plain C++ accesses get forwarded by the
+  // compiler into registers and from there into local-memory spills.
+  std::string ldx(int slot) {
+    char b[32];
+    snprintf(b, sizeof b, "t%d", tmp++);
+    o.f("    KA_LDX(%s, %s, %d, %d);", b, base.c_str(), slot, soff(slot));
+    return b;
+  }
+  void stx(int slot, const std::string& val) { o.f("    KA_STX(%s, %d, %d, %s);", base.c_str(), slot, soff(slot), val.c_str()); }
+  int spill_slot(int vid) const { return t.C + vid - (plan.nvalues - plan.nspill); }
+  std::string vget(int vid) {
+    if (spilled(vid)) return ldx(spill_slot(vid));
+    return "nv" + std::to_string(vid);
+  }
+  void vset(int vid, const std::string& expr) {
+    if (spilled(vid)) stx(spill_slot(vid), expr);
+    else o.f("    const float nv%d = %s;", vid, expr.c_str());
+  }
+
+  // ---- row vectors ----
+  int nvec() const { return t.C * esz() / v.vec; }
+  int per_vec() const { return v.vec / esz(); }
+  void load_vec(const char* name, int i, bool again = false) {  // again: the second read of the row (must not be merged with the first)
+    const int off = i * v.vec;
+    const char* sfx = again ? "b" : "";
+    switch (v.vec) {
+      case 16: o.f("    const uint4 %s%d = ld16%s(xr + %d);", name, i, sfx, off); break;
+      case 8: o.f("    const uint2 %s%d = ld8%s(xr + %d);", name, i, sfx, off); break;
+      case 4: o.f("    const u32 %s%d = ld4%s(xr + %d);", name, i, sfx, off); break;
+      default: o.f("    const u32 %s%d = ld2%s(xr + %d);", name, i, sfx, off); break;
+    }
+  }
+  std::string word(const char* name, int i, int w) const {  // w-th 32-bit word of vector i
+    char b[48];
+    static const char* comp[4] = {"x", "y", "z", "w"};
+    if (v.vec >= 8) snprintf(b, sizeof b, "%s%d.%s", name, i, comp[w]);
+    else snprintf(b, sizeof b, "%s%d", name, i);
+    return b;
+  }
+  std::string elem(const char* name, int c) const {  // fp32 value of class c out of the loaded vectors
+    const int pv = per_vec(), i = c / pv, j = c % pv;
+    char b[96];
+    if (v.dtype == NBDT_F32) {
+      snprintf(b, sizeof b, "u2f(%s)", word(name, i, j).c_str());
+    } else {
+      const std::string w = word(name, i, j / 2);
+      if (v.dtype == NBDT_BF16) {
+        if (v.vec == 2) snprintf(b, sizeof b, "u2f(%s << 16)", w.c_str());
+        else if (j % 2 == 0) snprintf(b, sizeof b, "u2f(%s << 16)", w.c_str());
+        else snprintf(b, sizeof b, "u2f(%s & 0xffff0000u)", w.c_str());
+      } else {
+        if (v.vec == 2 || j % 2 == 0) snprintf(b, sizeof b, "h2f(%s)", w.c_str());
+        else snprintf(b, sizeof b, "h2f(%s >> 16)", w.c_str());
+      }
+    }
+    return b;
+  }
+
+  // ---- pass 1: post-order ----
+  void up(int n) {
+    if (leaf(n)) {
+      fence_base();
+      o.f("    KA_LDX(s%d, %s, %d, %d);", n, base.c_str(), n, soff(n));
+      note("s" + std::to_string(n));
+      if (loss_mode()) { o.f("    zx%d += ex2(fmaf(s%d, kLog2e, nm));", acc & 3, n); ++acc; }
+      return;
+    }
+    const std::vector<int>& c = kids(n);
+    for (int k : c) up(k);
+    if (n != t.root) {
+      std::string sum;
+      for (size_t k = 0; k < c.size(); ++k) { char b[24]; snprintf(b, sizeof b, "%ss%d", k ? " + " : "", c[k]); sum += b; }
+      o.f("    const float s%d = %s;", n, sum.c_str());
+    }
+    const int vid = plan.value_slot[n];
+    if (c.size() == 1) return;  // a single child has probability 1: nothing to keep
+    if (binary(n)) {
+      char e[160];
+      // t = m_a - m_b in log2 units
+      snprintf(e, sizeof e, "fmaf(s%d, %s, s%d * %s)", c[0], lit(kLog2e / t.cnt[c[0]]).c_str(), c[1], lit(-kLog2e / t.cnt[c[1]]).c_str());
+      if (v.mode == kSpecHardLoss) vset(vid, e);
+      else vset(vid, std::string("signed_lo(") + e + ")");
+      if (!spilled(vid)) note("nv" + std::to_string(vid));
+      return;
+    }
+    // k-ary: softmax over the children (log2 domain)
+    o.f("    {");
+    for (int k : c) o.f("      const float a%d = s%d * %s;", k, k, lit(kLog2e / t.cnt[k]).c_str());
+    std::string mx = "a" + std::to_string(c[0]);
+    for (size_t k = 1; k < c.size(); ++k) mx = "fmaxf(" + mx + ", a" + std::to_string(c[k]) + ")";
+    o.f("      const float mx = %s;", mx.c_str());
+    if (v.mode == kSpecHardLoss) {
+      for (size_t k = 0; k < c.size(); ++k) o.f("      km%d = a%d - mx;", vid + (int)k, c[k]);
+    } else {
+      std::string sum;
+      for (size_t k = 0; k < c.size(); ++k) {
+        o.f("      const float q%d = ex2(a%d - mx);", c[k], c[k]);
+        sum += (k ? " + q" : "q") + std::to_string(c[k]);
+      }
+      o.f("      const float r = rcp(%s);", sum.c_str());
+      for (size_t k = 0; k < c.size(); ++k) o.f("      km%d = q%d * r;", vid + (int)k, c[k]);
+    }
+    o.f("    }");
+    for (size_t k = 0; k < c.size(); ++k)
+      if (spilled(vid + (int)k)) stx(spill_slot(vid + (int)k), "km" + std::to_string(vid + (int)k));
+  }
+  // k-ary values are declared before the block that sets them
+  void declare_kary() {
+    for (int n = t.C; n < t.NV; ++n) {
+      const std::vector<int>& c = kids(n);
+      if (c.size() <= 2) continue;
+      for (size_t k = 0; k < c.size(); ++k) o.f("    float km%d;", plan.value_slot[n] + (int)k);
+    }
+  }
+  std::string kget(int vid) {  // k-ary child value
+    if (spilled(vid)) return ldx(spill_slot(vid));
+    return "km" + std::to_string(vid);
+  }
+
+  // ---- pass 2 (soft): pre-order path probabilities ----
+  // `pre` prefixes every variable name of the traversal (the loss makes two: "P" sums exp(P) and picks P[target]; "Q" is the
+  // down half of the merged down/up gradient traversal).  what: 0 = soft forward (store P), 1 = sums only.
+  void leaf_prob(int c, const char* pre, int what) {
+    if (what == 0) {
+      stx(c, std::string(pre) + std::to_string(c));
+      note(std::string(pre) + std::to_string(c));
+    } else {
+      o.f("    { const float e = exp01(%s%d); z2%d += e; pry = (posy == %d) ? %s%d : pry; }", pre, c, acc & 3, t.pos[c], pre, c);
+      note("z2" + std::to_string(acc & 3));
+      ++acc;
+    }
+  }
+  // children's path probabilities of node n from the node's own (P: expression, "" = 1)
+  void child_probs(int n, const std::string& P, const char* pre) {
+    const std::vector<int>& c = kids(n);
+    const int vid = plan.value_slot[n];
+    if (c.size() == 1) {
+      o.f("    const float %s%d = %s;", pre, c[0], P.empty() ? "1.f" : P.c_str());
+    } else if (binary(n)) {
+      const std::string s = fenced(vget(vid));
+      // the second traversal recomputes what the first one computed: without the opaque copy the compiler merges the two and
+      // keeps every path probability of the first traversal alive (hundreds of spilled registers)
+      if (pre[0] == 'Q') o.f("    float %ss%d = %s; KA_OPAQUE(%ss%d);", pre, n, s.c_str(), pre, n);
+      else o.f("    const float %ss%d = %s;", pre, n, s.c_str());
+      if (P.empty()) o.f("    const float %sl%d = fabsf(%ss%d); const float %sh%d = 1.f - %sl%d;", pre, n, pre, n, pre, n, pre, n);
+      else o.f("    const float %sl%d = %s * fabsf(%ss%d); const float %sh%d = %s - %sl%d;", pre, n, P.c_str(), pre, n, pre, n, P.c_str(), pre, n);
+      o.f("    const float %s%d = first_is_hi(%ss%d) ? %sh%d : %sl%d; const float %s%d = first_is_hi(%ss%d) ? %sl%d : %sh%d;",
+          pre, c[0], pre, n, pre, n, pre, n, pre, c[1], pre, n, pre, n, pre, n);
+    } else {
+      for (size_t k = 0; k < c.size(); ++k) {
+        const std::string pk = kget(vid + (int)k);
+        if (pre[0] == 'Q') {
+          o.f("    float %sk%d = %s; KA_OPAQUE(%sk%d);", pre, c[k], pk.c_str(), pre, c[k]);
+          if (P.empty()) o.f("    const float %s%d = %sk%d;", pre, c[k], pre, c[k]);
+          else o.f("    const float %s%d = %s * %sk%d;", pre, c[k], P.c_str(), pre, c[k]);
+        } else if (P.empty()) o.f("    const float %s%d = %s;", pre, c[k], pk.c_str());
+        else o.f("    const float %s%d = %s * %s;", pre, c[k], P.c_str(), pk.c_str());
+      }
+    }
+  }
+  void down(int n, const std::string& P, const char* pre, int what) {
+    child_probs(n, P, pre);
+    for (int k : kids(n)) {
+      if (leaf(k)) leaf_prob(k, pre, what);
+      else down(k, pre + std::to_string(k), pre, what);
+    }
+  }
+
+  // ---- pass 3 (soft loss): one traversal, path probabilities on the way down, on the way up the subtree sums
+  // H[v] = sum over the leaves under v of dL/dP[leaf] * P[leaf] (up to the factor cA) and per node the gradient of its child
+  // logits dm[c] = H[c] - p[c]*H[v], which REPLACES the node's probability value (register or slot).  Returns the name of
+  // H[n].  Nothing is stored per leaf: the row's x stays in its slots for the final pass.
+  std::string updown(int n, const std::string& P) {
+    const std::vector<int>& c = kids(n);
+    const int vid = plan.value_slot[n];
+    child_probs(n, P, "Q");
+    std::vector<std::string> h;
+    for (int k : c) {
+      if (leaf(k)) {
+        o.f("    const float G%d = Q%d * (exp01(Q%d) - ((posy == %d) ? Z : 0.f));", k, k, k, t.pos[k]);
+        h.push_back("G" + std::to_string(k));
+      } else {
+        h.push_back(updown(k, "Q" + std::to_string(k)));
+      }
+    }
+    const std::string H = "G" + std::to_string(n);
+    if (c.size() == 1) {
+      o.f("    const float %s = %s;", H.c_str(), h[0].c_str());
+      return H;
+    }
+    std::string sum;
+    for (size_t k = 0; k < h.size(); ++k) sum += (k ? " + " : "") + h[k];
+    o.f("    const float %s = %s;", H.c_str(), sum.c_str());
+    note(H);
+    if (binary(n)) {
+      o.f("    const float pa%d = first_is_hi(Qs%d) ? 1.f - fabsf(Qs%d) : fabsf(Qs%d);", n, n, n, n);
+      char e[96];
+      snprintf(e, sizeof e, "cA * fmaf(-pa%d, %s, %s)", n, H.c_str(), h[0].c_str());
+      dset(vid, e);
+    } else {
+      for (size_t k = 0; k < c.size(); ++k) {
+        char e[128];
+        snprintf(e, sizeof e, "cA * fmaf(-Qk%d, %s, %s)", c[k], H.c_str(), h[k].c_str());
+        dset(vid + (int)k, e);
+      }
+    }
+    return H;
+  }
+  // gradient values: same placement as the probability values they replace
+  void dset(int vid, const std::string& expr) {
+    if (spilled(vid)) stx(spill_slot(vid), expr);
+    else o.f("    const float dv%d = %s;", vid, expr.c_str());
+  }
+  std::string dget(int vid) {
+    if (spilled(vid)) return ldx(spill_slot(vid));
+    return "dv" + std::to_string(vid);
+  }
+  // leaf c: dL/dx[c] = A[c] + cx * softmax(x)[c]  (the one-hot of the target is subtracted afterwards), written over x
+  void leaf_out(int c, const std::string& A) {
+    const std::string xv = ldx(c);
+    char e[128];
+    snprintf(e, sizeof e, "fmaf(cx, ex2(fmaf(%s, kLog2e, nl)), %s)", xv.c_str(), A.c_str());
+    stx(c, e);
+  }
+
+  // ---- pass 4 (soft loss): pre-order, A[c] = A[v] + dm[c]/#leaves(c) ----
+  void back(int n, const std::string& A) {
+    const std::vector<int>& c = kids(n);
+    const int vid = plan.value_slot[n];
+    auto fma_a = [&](int child, const std::string& d) {
+      const std::string inv = lit(1.0 / t.cnt[child]);
+      if (A.empty()) o.f("    const float A%d = %s * %s;", child, d.c_str(), inv.c_str());
+      else o.f("    const float A%d = fmaf(%s, %s, %s);", child, d.c_str(), inv.c_str(), A.c_str());
+    };
+    if (c.size() == 1) {
+      o.f("    const float A%d = %s;", c[0], A.empty() ? "0.f" : A.c_str());
+    } else if (binary(n)) {
+      const std::string d = fenced(dget(vid));
+      fma_a(c[0], d);
+      fma_a(c[1], "-" + d);
+    } else {
+      for (size_t k = 0; k < c.size(); ++k) fma_a(c[k], dget(vid + (int)k));
+    }
+    note("A" + std::to_string(c.back()));
+    for (int ck : c) {
+      if (leaf(ck)) leaf_out(ck, "A" + std::to_string(ck));
+      else back(ck, "A" + std::to_string(ck));
+    }
+  }
+
+  // ---- hard loss: one pre-order pass (loss along the target's path + its gradient) ----
+  // on: expression of the node's on-path indicator ("" = 1); A as above
+  void hard(int n, const std::string& on, const std::string& A) {
+    const std::vector<int>& c = kids(n);
+    const int vid = plan.value_slot[n];
+    const std::string onv = on.empty() ? "1.f" : on;
+    auto fma_a = [&](int child, const std::string& d) {
+      const std::string inv = lit(1.0 / t.cnt[child]);
+      if (A.empty()) o.f("    const float A%d = %s * %s;", child, d.c_str(), inv.c_str());
+      else o.f("    const float A%d = fmaf(%s, %s, %s);", child, d.c_str(), inv.c_str(), A.c_str());
+    };
+    if (c.size() == 1) {
+      o.f("    const float on%d = %s; const float A%d = %s;", c[0], onv.c_str(), c[0], A.empty() ? "0.f" : A.c_str());
+    } else if (binary(n)) {
+      const int a = c[0], b = c[1];
+      o.f("    const float on%d = (posy < %d) ? %s : 0.f; const float on%d = %s - on%d;", a, t.end[a], onv.c_str(), b, onv.c_str(), a);
+      o.f("    const float ht%d = %s; const float hq%d = ex2(-fabsf(ht%d)); const float hd%d = 1.f + hq%d; const float hr%d = rcp(hd%d);",
+          n, fenced(vget(vid)).c_str(), n, n, n, n, n, n);
+      o.f("    const float pa%d = ht%d >= 0.f ? hr%d : hq%d * hr%d;", n, n, n, n, n);
+      // -log2 p(child) = log2(1 + 2^-|t|) + max(-t, 0) for the first child, + max(t, 0) for the second
+      o.f("    lp = fmaf(%s, lg2(hd%d), lp); lp = fmaf(on%d, fmaxf(-ht%d, 0.f), lp); lp = fmaf(on%d, fmaxf(ht%d, 0.f), lp);",
+          onv.c_str(), n, a, n, b, n);
+      o.f("    const float d%d = nkg * fmaf(-pa%d, %s, on%d);", n, n, onv.c_str(), a);
+      fma_a(a, "d" + std::to_string(n));
+      fma_a(b, "-d" + std::to_string(n));
+    } else {
+      std::string sum;
+      for (size_t k = 0; k < c.size(); ++k) {
+        const int ck = c[k];
+        o.f("    const float on%d = ((unsigned)(posy - %d) < %du) ? %s : 0.f;", ck, t.beg[ck], t.cnt[ck], onv.c_str());
+        o.f("    const float km_%d = %s; const float kq_%d = ex2(km_%d);", ck, kget(vid + (int)k).c_str(), ck, ck);
+        sum += (k ? " + kq_" : "kq_") + std::to_string(ck);
+      }
+      o.f("    const float hs%d = %s; const float hr%d = rcp(hs%d);", n, sum.c_str(), n, n);
+      o.f("    lp = fmaf(%s, lg2(hs%d), lp);", onv.c_str(), n);
+      for (int ck : c) {
+        o.f("    lp = fmaf(-on%d, km_%d, lp);", ck, ck);
+        o.f("    const float dk%d = nkg * fmaf(-kq_%d * hr%d, %s, on%d);", ck, ck, n, onv.c_str(), ck);
+        fma_a(ck, "dk" + std::to_string(ck));
+      }
+    }
+    for (int ck : c) {
+      note("A" + std::to_string(ck));
+      if (leaf(ck)) leaf_out(ck, "A" + std::to_string(ck));
+      else hard(ck, "on" + std::to_string(ck), "A" + std::to_string(ck));
+    }
+  }
+
+  void store_out(const char* ptr, int i, int vec, bool f32, const std::vector<std::string>& vals) {
+    // vals: fp32 expressions of the elements of vector i
+    std::vector<std::string> words;
+    if (f32) {
+      for (const std::string& e : vals) words.push_back("f2u(" + e + ")");
+    } else if (vec == 2) {
+      words.push_back(std::string(v.dtype == NBDT_BF16 ? "pack_bf16(" : "pack_f16(") + vals[0] + ", 0.f)");
+    } else {
+      for (size_t k = 0; k + 1 < vals.size(); k += 2)
+        words.push_back(std::string(v.dtype == NBDT_BF16 ? "pack_bf16(" : "pack_f16(") + vals[k] + ", " + vals[k + 1] + ")");
+    }
+    std::string args;
+    for (size_t k = 0; k < words.size(); ++k) args += ", " + words[k];
+    o.f("    st%d(%s + %d%s);", vec, ptr, i * vec, args.c_str());
+  }
+
+  // one vector of the row block: load + unpack to floats f0..f{pv-1} (sweeps A and B of the cooperative I/O)
+  void coop_load(const char* name, bool again) {
+    const char* sfx = again ? "b" : "";
+    switch (v.vec) {
+      case 16: o.f("        const uint4 %s0 = ld16%s(gp);", name, sfx); break;
+      case 8: o.f("        const uint2 %s0 = ld8%s(gp);", name, sfx); break;
+      case 4: o.f("        const u32 %s0 = ld4%s(gp);", name, sfx); break;
+      default: o.f("        const u32 %s0 = ld2%s(gp);", name, sfx); break;
+    }
+  }
+  // advance (row, col) of this lane's vector by one sweep iteration (KA_TPB vectors of pv elements)
+  void coop_step(int pv) {
+    o.f("      col += (KA_TPB * %d) %% KA_C; row += (KA_TPB * %d) / KA_C;", pv, pv);
+    o.f("      if (col >= KA_C) { col -= KA_C; ++row; }");
+  }
+
+  std::string run() {
+    const int C = t.C;
+    const int pv = per_vec();
+    o.s.reserve((size_t)C * 2200);
+    o.f("#define KA_C %d", C);
+    U = v.mode == kSpecSoftFwd ? std::min(pv, v.ovec / 4) : pv;
+    K = ((C / U) & 31) | 1;
+    o.f("#ifdef KA_HOST\n#define KA_TPB 1\n#else\n#define KA_TPB %d\n#endif\n#define KA_U %du\n#define KA_K %du", kTPB, U, K);
+    o.s += kPrelude;
+    if (loss_mode()) {
+      std::string tab;
+      for (int c = 0; c < C; ++c) tab += std::to_string(t.pos[c]) + (c + 1 < C ? "," : "");
+      o.f("#ifdef KA_HOST\nstatic const unsigned short ka_pos[KA_C] = {%s};\n#else\n__device__ const unsigned short ka_pos[KA_C] = {%s};\n#endif", tab.c_str(), tab.c_str());
+    }
+    o.f("// hierarchy %016llx: %d leaves, %d inner nodes; mode %d dtype %d vec %d; %d node values (%d in shared memory)",
+        t.hash, C, t.N, v.mode, v.dtype, v.vec, plan.nvalues, plan.nspill);
+
+    // ---- sweep A: the block's rows, coalesced, into the transposed slots ----
+    o.f("KA_DEV void ka_sweep_a(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int lane) {");
+    o.f("    const char* xb = reinterpret_cast<const char*>(p.x) + row0 * p.ld * %d;", esz());
+    o.f("    int row = (lane * %d) / KA_C, col = (lane * %d) %% KA_C;", pv, pv);
+    const int nit = C / pv;  // vectors per lane and block
+    // full block of contiguous rows (the common case): every load has an immediate offset from one pointer and a whole group
+    // of loads is in flight before the first store needs its data
+    o.f("#ifndef KA_HOST");
+    o.f("    if (nrows == KA_TPB && p.ld == KA_C) {");
+    o.f("      const char* gp = xb + lane * %d;", v.vec);
+    const int maxld = std::max(1, plan.knobs.maxld * 16 / v.vec);
+    for (int g0 = 0; g0 < nit; g0 += maxld) {
+      const int g1 = std::min(nit, g0 + maxld);
+      for (int it = g0; it < g1; ++it) {
+        switch (v.vec) {
+          case 16: o.f("      const uint4 lv%d = ld16(gp + %d);", it, it * kTPB * v.vec); break;
+          case 8: o.f("      const uint2 lv%d = ld8(gp + %d);", it, it * kTPB * v.vec); break;
+          case 4: o.f("      const u32 lv%d = ld4(gp + %d);", it, it * kTPB * v.vec); break;
+          default: o.f("      const u32 lv%d = ld2(gp + %d);", it, it * kTPB * v.vec); break;
+        }
+      }
+      for (int it = g0; it < g1; ++it) {
+        o.f("      { const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);");
+        for (int j = 0; j < pv; ++j) o.f("        KA_STD(a, %d, %d, %s);", j, eoff(j), elem("lv", it * pv + j).c_str());
+        o.f("      }");
+        coop_step(pv);
+      }
+    }
+    o.f("      return;");
+    o.f("    }");
+    o.f("#endif");
+    if (plan.knobs.unroll > 0) o.f("#pragma unroll %d", plan.knobs.unroll); else o.f("#pragma unroll");
+    o.f("    for (int it = 0; it < %d; ++it) {", nit);
+    o.f("      if (row < nrows) {");
+    o.f("        const char* gp = xb + ((long long)row * p.ld + col) * %d;", esz());
+    coop_load("lv", false);
+    o.f("        const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);");
+    for (int j = 0; j < pv; ++j) o.f("        KA_STD(a, %d, %d, %s);", j, eoff(j), elem("lv", j).c_str());
+    o.f("      }");
+    coop_step(pv);
+    o.f("    }");
+    o.f("}");
+
+    // ---- the row function: one thread, one row, straight-line ----
+    o.f("KA_DEV void ka_row(const KAParams& p, long long row, long long yy, KA_XSB xsb, u32 zr, float& loss_acc) {");
+    if (loss_mode()) {
+      // rows with an out-of-range target are ignored: zero loss, zero gradient (nn.CrossEntropyLoss's ignore_index
+      // rows; the reference's class_index_to_child_index has no entry for them either)
+      o.f("    if ((unsigned long long)yy >= %dull) {", C);
+      o.f("      for (int c = 0; c < KA_C; ++c) KA_STX_DYN(c, 0.f);");
+      o.f("      return;");
+      o.f("    }");
+      o.f("    const int y = (int)(unsigned)yy;");
+      o.f("    const int posy = ka_pos[y];");
+      o.f("    const float kx = p.w_xent * p.inv_rows, kt = p.w_tree * p.inv_rows;");
+      // max of the row (thread-private sweep over the slots)
+      o.f("    float m0 = -3.0e38f, m1 = m0, m2 = m0, m3 = m0;");
+      for (int c = 0; c < C; ++c) {
+        const std::string xv = ldx(c);
+        o.f("    m%d = fmaxf(m%d, %s);", c & 3, c & 3, xv.c_str());
+      }
+      o.f("    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));");
+      o.f("    const float nm = -mx * kLog2e;");
+      o.f("    float zx0 = 0.f, zx1 = 0.f, zx2 = 0.f, zx3 = 0.f;");
+      o.f("    KA_LDX_DYN(xy, y);");
+    }
+    // ---- pass 1 ----
+    declare_kary();
+    acc = 0;
+    up(t.root);
+    if (loss_mode()) {
+      o.f("    const float l2zx = lg2((zx0 + zx1) + (zx2 + zx3));");
+      o.f("    const float lse1 = fmaf(l2zx, kLn2, mx);");
+    }
+    if (v.mode == kSpecSoftFwd) {
+      acc = 0;
+      down(t.root, "", "P", 0);
+      o.f("}");
+    } else {
+      o.f("    const float cx = kx * p.grad_scale;");
+      o.f("    const float nl = -fmaf(mx, kLog2e, l2zx);");
+      if (v.mode == kSpecSoftLoss) {
+        o.f("    float z20 = 0.f, z21 = 0.f, z22 = 0.f, z23 = 0.f, pry = 0.f;");
+        acc = 0;
+        down(t.root, "", "P", 1);
+        o.f("    const float Z = (z20 + z21) + (z22 + z23);");
+        o.f("    loss_acc += kx * (lse1 - xy) + kt * (kLn2 * lg2(Z) - pry);");
+        o.f("    if (!p.grad) return;");
+        o.f("    const float cA = kt * p.grad_scale * rcp(Z);");
+        updown(t.root, "");
+        back(t.root, "");
+      } else {
+        o.f("    float lp = 0.f;");
+        o.f("    const float nkg = -kt * p.grad_scale;");
+        hard(t.root, "", "");
+        o.f("    loss_acc += kx * (lse1 - xy) + kt * kLn2 * lp;");
+        o.f("    if (!p.grad) return;");
+      }
+      // the slots now hold dL/dx except for the one-hot of the plain cross-entropy term
+      o.f("    KA_ADDX_DYN(y, -cx);");
+      o.f("}");
+    }
+
+    // ---- sweep B: coalesced write of the block's gradient rows / class probabilities (the slots hold the final values) ----
+    o.f("KA_DEV void ka_sweep_b(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int lane) {");
+    {
+      const bool fwd = v.mode == kSpecSoftFwd;
+      const int ov = fwd ? v.ovec : v.vec;          // bytes per output vector
+      const int po = fwd ? v.ovec / 4 : pv;         // elements per output vector
+      const int oesz = fwd ? 4 : esz();
+      const int nito = C / po;
+      if (fwd) o.f("    char* ob = reinterpret_cast<char*>(p.class_probs + row0 * KA_C); const long long old = KA_C;");
+      else o.f("    char* ob = reinterpret_cast<char*>(p.grad) + row0 * p.ld * %d; const long long old = p.ld;", oesz);
+      o.f("    int row = (lane * %d) / KA_C, col = (lane * %d) %% KA_C;", po, po);
+      o.f("#ifndef KA_HOST");
+      o.f("    if (nrows == KA_TPB && old == KA_C) {");
+      o.f("      char* op = ob + lane * %d;", ov);
+      for (int it = 0; it < nito; ++it) {
+        o.f("      { const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);");
+        std::vector<std::string> vals;
+        for (int j = 0; j < po; ++j) {
+          o.f("        KA_LDD(q%d, a, %d, %d);", j, j, eoff(j));
+          vals.push_back("q" + std::to_string(j));
+        }
+        store_out("    op", it * kTPB, ov, fwd || v.dtype == NBDT_F32, vals);
+        o.f("      }");
+        coop_step(po);
+      }
+      o.f("      return;");
+      o.f("    }");
+      o.f("#endif");
+      if (plan.knobs.unroll > 0) o.f("#pragma unroll %d", plan.knobs.unroll); else o.f("#pragma unroll");
+      o.f("    for (int it = 0; it < %d; ++it) {", nito);
+      o.f("      if (row < nrows) {");
+      o.f("        const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);");
+      std::vector<std::string> vals;
+      for (int j = 0; j < po; ++j) {
+        o.f("        KA_LDD(q%d, a, %d, %d);", j, j, eoff(j));
+        vals.push_back("q" + std::to_string(j));
+      }
+      o.f("        char* op = ob + ((long long)row * old + col) * %d;", oesz);
+      store_out("    op", 0, ov, fwd || v.dtype == NBDT_F32, vals);
+      o.f("      }");
+      coop_step(po);
+      o.f("    }");
+    }
+    o.f("}");
+
+    // ---- kernel: one warp per CTA, 32 rows per iteration ----
+    o.f("#ifndef KA_HOST");
+    o.f("extern \"C\" __global__ void __launch_bounds__(KA_TPB, %d) nbdt_tree_ka(const KAParams p) {", plan.min_blocks);
+    o.f("  extern __shared__ float ka_smem[];");
+    o.f("  const int lane = threadIdx.x;");
+    o.f("  const u32 xsw = (u32)__cvta_generic_to_shared(ka_smem);");
+    o.f("  const u32 xsb = xsw + ((lane * KA_K) & 31u) * 4u;");
+    o.f("  float loss_acc = 0.f;");
+    o.f("  const u32 zr = (u32)((unsigned long long)p.B >> 48);  // zero at run time, unknown at compile time (scheduling fences)");
+    o.f("  for (long long row0 = (long long)blockIdx.x * KA_TPB; row0 < p.B; row0 += (long long)gridDim.x * KA_TPB) {");
+    o.f("    const int nrows = (int)(p.B - row0 < KA_TPB ? p.B - row0 : KA_TPB);");
+    o.f("    long long yy = 0;");
+    if (loss_mode()) o.f("    if (lane < nrows) yy = p.targets[row0 + lane];");
+    if (plan.knobs.prefetch > 0) {
+      // the lines of a block further ahead go to L2 now, so that its sweep A pays an L2 hit instead of an HBM access
+      o.f("    {");
+      o.f("      const long long pr0 = row0 + %dll * gridDim.x * KA_TPB;", plan.knobs.prefetch);
+      o.f("      if (pr0 < p.B && p.ld <= 2 * KA_C) {");
+      o.f("        const long long pn = p.B - pr0 < KA_TPB ? p.B - pr0 : KA_TPB;");
+      o.f("        const char* pb = reinterpret_cast<const char*>(p.x) + pr0 * p.ld * %d;", esz());
+      o.f("        const long long plen = ((pn - 1) * p.ld + KA_C) * %d;", esz());
+      o.f("        for (long long po = lane * 128; po < plen; po += KA_TPB * 128) asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(pb + po));");
+      o.f("      }");
+      o.f("    }");
+    }
+    o.f("    ka_sweep_a(p, row0, nrows, xsw, lane);");
+    o.f("    __syncwarp();");
+    o.f("    if (lane < nrows) ka_row(p, row0 + lane, yy, xsb, zr, loss_acc);");
+    o.f("    __syncwarp();");
+    if (loss_mode()) o.f("    if (p.grad) ka_sweep_b(p, row0, nrows, xsw, lane);");
+    else o.f("    ka_sweep_b(p, row0, nrows, xsw, lane);");
+    o.f("    __syncwarp();");
+    o.f("  }");
+    if (loss_mode()) {
+      o.f("  for (int s = 16; s > 0; s >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, s);");
+      o.f("  if (lane == 0) atomicAdd(p.loss, loss_acc);");
+    }
+    o.f("}");
+    o.f("#endif");
+    return o.s;
+  }
+};
+
+Plan make_plan(const KTree& t, int max_smem, const Knobs& knobs) {
+  Plan p;
+  p.knobs = knobs;
+  p.value_slot.assign(t.NV, -1);
+  // values in post-order (the order pass 1 produces them): the first kRegValueCap stay in registers
+  std::vector<int> order;  // inner nodes, post-order
+  {
+    struct Frame { int v; size_t k; };
+    std::vector<Frame> st;
+    st.push_back({t.root, 0});
+    while (!st.empty()) {
+      Frame& f = st.back();
+      const std::vector<int>& c = t.ch[f.v - t.C];
+      if (f.k == c.size()) { order.push_back(f.v); st.pop_back(); continue; }
+      const int u = c[f.k++];
+      if (u >= t.C) st.push_back({u, 0});
+    }
+  }
+  for (int n : order) {
+    const size_t k = t.ch[n - t.C].size();
+    if (k <= 1) continue;
+    p.value_slot[n] = p.nvalues;
+    p.nvalues += k == 2 ? 1 : (int)k;
+  }
+  p.nspill = std::max(0, p.nvalues - knobs.regcap);
+  p.smem_bytes = (t.C * 32 + t.C + 36 + p.nspill * 32) * 4;
+  const int regs = std::min(255, ((p.nvalues - p.nspill) + 64 + 7) / 8 * 8);
+  int by_regs = 65536 / (kTPB * regs);
+  int by_smem = (max_smem > 0 ? max_smem : 227 * 1024) / std::max(1, p.smem_bytes + 1024);
+  p.min_blocks = std::max(1, std::min(32, std::min(by_regs, by_smem)));
+  if (knobs.minb > 0) p.min_blocks = knobs.minb;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// NVRTC (loaded lazily with dlopen: the library must load on machines without it)
+// ------------------------------------------------------------------------------------------------------------------
+struct Nvrtc {
+  typedef struct _nvrtcProgram* prog;
+  int (*CreateProgram)(prog*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*CompileProgram)(prog, int, const char* const*) = nullptr;
+  int (*GetCUBINSize)(prog, size_t*) = nullptr;
+  int (*GetCUBIN)(prog, char*) = nullptr;
+  int (*GetProgramLogSize)(prog, size_t*) = nullptr;
+  int (*GetProgramLog)(prog, char*) = nullptr;
+  int (*DestroyProgram)(prog*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+
+Nvrtc* nvrtc() {
+  static Nvrtc n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    std::vector<std::string> names;
+    if (const char* e = getenv("NBDT_B200_NVRTC")) names.push_back(e);
+    for (const char* s : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so",
+                          "libnvrtc.so.13"})
+      names.push_back(s);
+    void* h = nullptr;
+    for (const std::string& s : names) {
+      h = dlopen(s.c_str(), RTLD_NOW | RTLD_LOCAL);
+      if (h) break;
+    }
+    if (!h) { n.why = "libnvrtc not found (set NBDT_B200_NVRTC to its path)"; return; }
+#define NBDT_SYM(name)                                                                      \
+  *(void**)(&n.name) = dlsym(h, "nvrtc" #name);                                              \
+  if (!n.name) { n.why = "libnvrtc lacks nvrtc" #name; return; }
+    NBDT_SYM(CreateProgram) NBDT_SYM(CompileProgram) NBDT_SYM(GetCUBINSize) NBDT_SYM(GetCUBIN)
+    NBDT_SYM(GetProgramLogSize) NBDT_SYM(GetProgramLog) NBDT_SYM(DestroyProgram) NBDT_SYM(GetErrorString)
+#undef NBDT_SYM
+    n.ok = true;
+  });
+  return &n;
+}
+
+int compile_cubin(const std::string& src, std::vector<char>* cubin, std::string* log) {
+  Nvrtc* n = nvrtc();
+  if (!n->ok) { *log = n->why; return -1; }
+  Nvrtc::prog prog = nullptr;
+  int rc = n->CreateProgram(&prog, src.c_str(), "nbdt_tree_ka.cu", 0, nullptr, nullptr);
+  if (rc) { *log = std::string("nvrtcCreateProgram: ") + n->GetErrorString(rc); return -1; }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v", "-default-device"};
+  rc = n->CompileProgram(prog, 5, opts);
+  size_t ls = 0;
+  if (n->GetProgramLogSize(prog, &ls) == 0 && ls > 1) {
+    log->resize(ls);
+    n->GetProgramLog(prog, &(*log)[0]);
+  }
+  if (rc) {
+    *log = std::string("nvrtcCompileProgram: ") + n->GetErrorString(rc) + "\n" + *log;
+    n->DestroyProgram(&prog);
+    return -1;
+  }
+  size_t cs = 0;
+  rc = n->GetCUBINSize(prog, &cs);
+  if (rc == 0 && cs > 0) {
+    cubin->resize(cs);
+    rc = n->GetCUBIN(prog, cubin->data());
+  }
+  n->DestroyProgram(&prog);
+  if (rc || cs == 0) { *log = "nvrtcGetCUBIN failed"; return -1; }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// on-disk cache
+// ------------------------------------------------------------------------------------------------------------------
+std::string cache_dir() {
+  static std::string dir;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    std::vector<std::string> cand;
+    if (const char* e = getenv("NBDT_B200_CACHE")) cand.push_back(e);
+    Dl_info info;
+    if (dladdr((void*)&cache_dir, &info) && info.dli_fname) {
+      std::string p = info.dli_fname;
+      const size_t s = p.rfind('/');
+      if (s != std::string::npos) cand.push_back(p.substr(0, s) + "/tree_cache");
+    }
+    if (const char* h = getenv("HOME")) cand.push_back(std::string(h) + "/.cache/nbdt_b200");
+    cand.push_back("/tmp/nbdt_b200_cache");
+    for (const std::string& c : cand) {
+      // mkdir -p (two levels are enough for the candidates above)
+      const size_t s = c.rfind('/');
+      if (s != std::string::npos && s > 0) mkdir(c.substr(0, s).c_str(), 0777);
+      mkdir(c.c_str(), 0777);
+      if (access(c.c_str(), W_OK | X_OK) == 0) { dir = c; return; }
+    }
+  });
+  return dir;
+}
+
+// read-only lookups also consult the in-tree directory when the writable one is elsewhere
+std::vector<std::string> cache_read_dirs() {
+  std::vector<std::string> v;
+  const std::string w = cache_dir();
+  if (!w.empty()) v.push_back(w);
+  Dl_info info;
+  if (dladdr((void*)&cache_dir, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    const size_t s = p.rfind('/');
+    if (s != std::string::npos) {
+      const std::string d = p.substr(0, s) + "/tree_cache";
+      if (d != w) v.push_back(d);
+    }
+  }
+  return v;
+}
+
+std::string variant_name(const KTree& t, const Variant& v, const Knobs& k) {
+  char b[192];
+  int n = snprintf(b, sizeof b, "ka%d_%016llx_m%d_t%d_v%d_o%d", kGeneratorVersion, t.hash, v.mode, v.dtype, v.vec, v.ovec);
+  if (!k.is_default()) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence);
+  return b;
+}
+
+bool read_file(const std::string& path, std::vector<char>* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out->resize(n > 0 ? (size_t)n : 0);
+  const bool ok = n > 0 && fread(out->data(), 1, (size_t)n, f) == (size_t)n;
+  fclose(f);
+  return ok;
+}
+
+void write_file_atomic(const std::string& path, const char* data, size_t n) {
+  char tmp[32];
+  snprintf(tmp, sizeof tmp, ".tmp%d", (int)getpid());
+  const std::string t = path + tmp;
+  FILE* f = fopen(t.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(data, 1, n, f) == n;
+  fclose(f);
+  if (ok) rename(t.c_str(), path.c_str());
+  else unlink(t.c_str());
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// per-tree state
+// ------------------------------------------------------------------------------------------------------------------
+struct TreeJit {
+  int device, sm_count, max_smem;
+  KTree tree;
+  Plan plan;
+  int policy;  // 0 off, 1 cache only, 2 compile on demand
+  std::mutex mu;
+  struct Loaded {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kern = nullptr;
+    int blocks_per_sm = 1;
+    bool failed = false;
+  };
+  std::map<int, Loaded> loaded;
+  std::string last_variant;
+};
+
+namespace {
+
+int jit_policy() {
+  const char* e = getenv("NBDT_B200_TREE_JIT");
+  if (!e || !*e) return 2;
+  if (!strcmp(e, "0") || !strcmp(e, "off")) return 0;
+  if (!strcmp(e, "cache")) return 1;
+  return 2;
+}
+
+// cubin for one variant: cache hit, or generate + compile + store.  Returns 0 on success.
+int obtain_cubin(const KTree& t, const Plan& plan, const Variant& v, int policy, std::vector<char>* cubin, std::string* log) {
+  const std::string name = variant_name(t, v, plan.knobs);
+  for (const std::string& d : cache_read_dirs())
+    if (read_file(d + "/" + name + ".cubin", cubin)) return 0;
+  if (policy < 2) { *log = "not in the kernel cache and NBDT_B200_TREE_JIT=cache"; return -1; }
+  Gen g(t, v, plan);
+  const std::string src = g.run();
+  if (compile_cubin(src, cubin, log)) return -1;
+  const std::string dir = cache_dir();
+  if (!dir.empty()) {
+    write_file_atomic(dir + "/" + name + ".cubin", cubin->data(), cubin->size());
+    write_file_atomic(dir + "/" + name + ".log", log->data(), log->size());
+  }
+  return 0;
+}
+
+int max_pow2_dividing(unsigned long long v, int cap) {
+  int a = 1;
+  while (a < cap && (v % (unsigned long long)(a * 2)) == 0) a *= 2;
+  return a;
+}
+
+}  // namespace
+
+int tree_jit_create(const nbdt_tree_desc* d, int device, int sm_count, int max_smem, TreeJit** out) {
+  *out = nullptr;
+  const int policy = jit_policy();
+  if (policy == 0 || d->num_classes > kMaxLeaves || d->num_classes < 2) return NBDT_OK;
+  TreeJit* t = new (std::nothrow) TreeJit();
+  NBDT_REQUIRE(t != nullptr, "out of host memory");
+  t->device = device; t->sm_count = sm_count; t->max_smem = max_smem; t->policy = policy;
+  analyse(d, &t->tree);
+  t->plan = make_plan(t->tree, max_smem, read_knobs());
+  if (t->plan.smem_bytes > max_smem - 1024) { delete t; return NBDT_OK; }
+  *out = t;
+  return NBDT_OK;
+}
+
+void tree_jit_destroy(TreeJit* t) {
+  if (!t) return;
+  for (auto& kv : t->loaded)
+    if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+  delete t;
+}
+
+const char* tree_jit_last_variant(const TreeJit* t) { return t ? t->last_variant.c_str() : ""; }
+
+int tree_jit_launch(TreeJit* t, int mode, int dtype, const SpecParams& p, void* stream) {
+  if (!t || dtype < 0 || dtype > 2 || mode < 0 || mode > 2) return -1;
+  const int esz = dtype == NBDT_F32 ? 4 : 2;
+  const int C = t->tree.C;
+  Variant v;
+  v.mode = mode; v.dtype = dtype;
+  // widest vector every row start of x (and of the gradient) is aligned to
+  unsigned long long align = (unsigned long long)C * esz;
+  align |= (unsigned long long)reinterpret_cast<uintptr_t>(p.x);
+  align |= (unsigned long long)(p.ld * esz);
+  if (mode != kSpecSoftFwd && p.grad) align |= (unsigned long long)reinterpret_cast<uintptr_t>(p.grad);
+  v.vec = max_pow2_dividing(align | 16ull, 16);
+  if (v.vec < esz) return -1;
+  v.ovec = 4;
+  if (mode == kSpecSoftFwd)
+    v.ovec = max_pow2_dividing(((unsigned long long)C * 4) | (unsigned long long)reinterpret_cast<uintptr_t>(p.class_probs) | 16ull, 16);
+  if (v.ovec < 4) return -1;
+
+  TreeJit::Loaded* L;
+  {
+    std::lock_guard<std::mutex> lock(t->mu);
+    L = &t->loaded[v.key()];
+    if (L->failed) return -1;
+    if (!L->kern) {
+      std::vector<char> cubin;
+      std::string log;
+      if (obtain_cubin(t->tree, t->plan, v, t->policy, &cubin, &log)) {
+        L->failed = true;
+        if (getenv("NBDT_B200_TREE_JIT_VERBOSE")) fprintf(stderr, "[nbdt_b200] tree JIT unavailable for %s: %s\n", variant_name(t->tree, v, t->plan.knobs).c_str(), log.c_str());
+        return -1;
+      }
+      cudaError_t e = cudaLibraryLoadData(&L->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+      if (e == cudaSuccess) e = cudaLibraryGetKernel(&L->kern, L->lib, "nbdt_tree_ka");
+      if (e == cudaSuccess && t->plan.smem_bytes > 48 * 1024)
+        e = cudaFuncSetAttribute((const void*)L->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, t->plan.smem_bytes);
+      if (e == cudaSuccess) {
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)L->kern, kTPB, t->plan.smem_bytes);
+        L->blocks_per_sm = std::max(1, nb);
+      }
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        L->failed = true;
+        L->kern = nullptr;
+        if (getenv("NBDT_B200_TREE_JIT_VERBOSE")) fprintf(stderr, "[nbdt_b200] loading the JIT tree kernel failed: %s\n", cudaGetErrorString(e));
+        return -1;
+      }
+    }
+    t->last_variant = variant_name(t->tree, v, t->plan.knobs);
+  }
+  long long grid = (p.B + kTPB - 1) / kTPB;
+  grid = std::min<long long>(grid, (long long)t->sm_count * L->blocks_per_sm);
+  if (grid < 1) grid = 1;
+  SpecParams sp = p;
+  void* args[1] = {&sp};
+  NBDT_CUDA_OK(cudaLaunchKernel((const void*)L->kern, dim3((unsigned)grid), dim3(kTPB), args, (size_t)t->plan.smem_bytes, (cudaStream_t)stream));
+  return NBDT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// C ABI: source / cubin of one variant without a device (build-time cache population, tests, inspection)
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+// Writes the generated CUDA source of (mode, dtype, vec) for `desc` into buf (NUL-terminated, truncated to cap);
+// returns the full length, or -1 when the hierarchy is outside the generator's limits.
+long long nbdt_tree_jit_source(const nbdt_tree_desc* desc, int mode, int dtype, int vec, char* buf, long long cap) {
+  if (!desc || desc->num_classes > kMaxLeaves || desc->num_classes < 2 || mode < 0 || mode > 2 || dtype < 0 || dtype > 2) return -1;
+  KTree t;
+  analyse(desc, &t);
+  const Plan plan = make_plan(t, 227 * 1024, read_knobs());
+  Variant v;
+  v.mode = mode; v.dtype = dtype; v.vec = vec;
+  v.ovec = mode == kSpecSoftFwd ? max_pow2_dividing(((unsigned long long)t.C * 4) | 16ull, 16) : 4;
+  Gen g(t, v, plan);
+  const std::string s = g.run();
+  if (buf && cap > 0) {
+    const size_t n = std::min<size_t>((size_t)cap - 1, s.size());
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (long long)s.size();
+}
+
+// Compiles (or finds in the cache) the cubin of the variant a launch with fully aligned rows would use, without touching a
+// device.  Returns NBDT_OK, or NBDT_EINVAL with nbdt_last_error() set (no NVRTC, compile error, outside the limits).
+int nbdt_tree_jit_precompile(const nbdt_tree_desc* desc, int mode, int dtype) {
+  NBDT_REQUIRE(desc != nullptr, "NULL desc");
+  NBDT_REQUIRE(desc->num_classes <= kMaxLeaves && desc->num_classes >= 2, "hierarchy outside the JIT generator's limits (%d leaves)", desc->num_classes);
+  NBDT_REQUIRE(mode >= 0 && mode <= 2 && dtype >= 0 && dtype <= 2, "bad mode/dtype");
+  KTree t;
+  analyse(desc, &t);
+  const Plan plan = make_plan(t, 227 * 1024, read_knobs());
+  const int esz = dtype == NBDT_F32 ? 4 : 2;
+  Variant v;
+  v.mode = mode; v.dtype = dtype;
+  v.vec = max_pow2_dividing(((unsigned long long)t.C * esz) | 16ull, 16);
+  v.ovec = mode == kSpecSoftFwd ? max_pow2_dividing(((unsigned long long)t.C * 4) | 16ull, 16) : 4;
+  std::vector<char> cubin;
+  std::string log;
+  if (obtain_cubin(t, plan, v, 2, &cubin, &log)) return nbdt::set_error(NBDT_EINVAL, "tree JIT: %s", log.c_str());
+  return NBDT_OK;
+}
+
+}  // extern "C"

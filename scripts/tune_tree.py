@@ -1,0 +1,35 @@
+"""Sweep the code-generation knobs of the run-time-specialised tree kernels (csrc/tree_jit.cu) on the GPU.
+usage: python scripts/tune_tree.py            (prints one JSON line per (hierarchy, knob setting))"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "neural-backed-decision-trees_b200"))
+import torch  # noqa: E402
+
+from bench_tree import peaks, time_point  # noqa: E402
+from nbdt.tree import Tree  # noqa: E402
+
+KNOBS = ["NBDT_B200_KA_REGCAP", "NBDT_B200_KA_MINB", "NBDT_B200_KA_UNROLL", "NBDT_B200_KA_PREFETCH", "NBDT_B200_KA_MAXLD", "NBDT_B200_KA_FENCE"]
+GRID = [(168, 0, 8, 1, 24, 8), (168, 0, 8, 1, 24, 4), (168, 0, 8, 1, 24, 16), (168, 0, 8, 0, 24, 8), (168, 0, 8, 1, 8, 8),
+        (168, 8, 8, 1, 24, 16), (168, 8, 8, 1, 24, 32), (96, 0, 8, 1, 24, 8), (96, 12, 8, 1, 24, 16), (64, 12, 8, 1, 24, 16),
+        (128, 10, 8, 1, 24, 16)]
+if len(sys.argv) > 1:
+    GRID = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+pk, src = peaks()
+cases = [("CIFAR100", "induced", 100, 1 << 20), ("TinyImagenet200", "induced", 200, 1 << 19)]
+for dataset, hierarchy, C, rows in cases:
+    for g in GRID:
+        for k, v in zip(KNOBS, g):
+            os.environ[k] = str(v)
+        tree = Tree(dataset, hierarchy=hierarchy)
+        for dtype in (torch.float32, torch.bfloat16):
+            try:
+                r = time_point(tree, "soft", rows, C, dtype, iters=10, warmup=2)
+            except Exception as e:  # noqa: BLE001
+                print(json.dumps({"dataset": dataset, "knobs": g, "error": str(e)[:200]}), flush=True)
+                continue
+            print(json.dumps({"dataset": dataset, "C": C, "knobs": g, "dtype": r["dtype"], "ms": round(r["ms"], 4),
+                              "gbs": round(r["gbs"], 1), "frac": round(r["gbs"] / pk["hbm_gbs"], 4)}), flush=True)

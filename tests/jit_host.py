@@ -1,0 +1,192 @@
+"""TEST INFRASTRUCTURE: run the code that csrc/tree_jit.cu GENERATES for a hierarchy on the CPU.
+
+The generator emits one straight-line function per hierarchy (`ka_row`: one logits row in, loss + gradient row out).  With
+-DKA_HOST the same text compiles as plain C++ against the few primitives below (exp2f for ex2.approx, 1/x for rcp.approx,
+memcpy loads/stores), so the generated algebra -- DFS prefix sums, the target step, signed child probabilities, the
+hard-loss path walk, k-ary nodes, register/shared-memory value placement -- is checked against the oracle without a GPU.
+The GPU tests then only have to cover what differs on the device (approximate MUFU ops, launch geometry, the cubin cache).
+"""
+import ctypes
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HARNESS = r'''
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define KA_HOST 1
+#define KA_DEV static inline
+typedef unsigned int u32;
+typedef unsigned short u16;
+struct uint4 { u32 x, y, z, w; };
+struct uint2 { u32 x, y; };
+KA_DEV float ex2(float v) { return exp2f(v); }
+KA_DEV float lg2(float v) { return log2f(v); }
+KA_DEV float rcp(float v) { return 1.0f / v; }
+KA_DEV float u2f(u32 v) { float f; memcpy(&f, &v, 4); return f; }
+KA_DEV u32 f2u(float v) { u32 u; memcpy(&u, &v, 4); return u; }
+KA_DEV float h2f(u32 v) {
+  const u32 h = v & 0xffffu, s = (h >> 15) & 1u, e = (h >> 10) & 31u, m = h & 1023u;
+  float r;
+  if (e == 0) r = ldexpf((float)m, -24);
+  else if (e == 31) r = m ? NAN : INFINITY;
+  else r = ldexpf((float)(m | 1024u), (int)e - 25);
+  return s ? -r : r;
+}
+KA_DEV u32 bf16_rn(float f) { u32 u = f2u(f); u += 0x7fffu + ((u >> 16) & 1u); return u >> 16; }
+KA_DEV u32 f16_rn(float f) {  // round to nearest even, normal range + flush of tiny values (enough for gradients in tests)
+  const u32 u = f2u(f), s = (u >> 16) & 0x8000u;
+  const float a = fabsf(f);
+  if (a >= 65520.f) return s | 0x7c00u;
+  if (a < 6.103515625e-05f) { const float q = a * 16777216.f; return s | (u32)lrintf(q); }
+  int e; const float m = frexpf(a, &e);  // a = m * 2^e, m in [0.5, 1)
+  const u32 mant = (u32)lrintf(m * 2048.f);  // 11 bits incl. leading one, may round up to 2048
+  u32 hh = ((u32)(e + 14) << 10) + (mant - 1024u);
+  return s | hh;
+}
+KA_DEV u32 pack_bf16(float lo, float hi) { return bf16_rn(lo) | (bf16_rn(hi) << 16); }
+KA_DEV u32 pack_f16(float lo, float hi) { return f16_rn(lo) | (f16_rn(hi) << 16); }
+KA_DEV uint4 ld16(const char* p) { uint4 r; memcpy(&r, p, 16); return r; }
+KA_DEV uint2 ld8(const char* p) { uint2 r; memcpy(&r, p, 8); return r; }
+KA_DEV u32 ld4(const char* p) { u32 r; memcpy(&r, p, 4); return r; }
+KA_DEV u32 ld2(const char* p) { u16 r; memcpy(&r, p, 2); return r; }
+KA_DEV void st16(char* p, u32 a, u32 b, u32 c, u32 d) { u32 v[4] = {a, b, c, d}; memcpy(p, v, 16); }
+KA_DEV void st8(char* p, u32 a, u32 b) { u32 v[2] = {a, b}; memcpy(p, v, 8); }
+KA_DEV void st4(char* p, u32 a) { memcpy(p, &a, 4); }
+KA_DEV void st2(char* p, u32 a) { u16 v = (u16)a; memcpy(p, &v, 2); }
+typedef float* KA_XSB;
+#define KA_LDX(dst, base, slot, off) const float dst = (base)[slot]
+#define KA_STX(base, slot, off, val) (base)[slot] = (val)
+#define KA_ADDX_DYN(idx, val) xsb[idx] += (val)
+#define KA_OPAQUE(x)
+#define KA_LDX_DYN(dst, idx) const float dst = xsb[idx]
+#define KA_STX_DYN(idx, val) xsb[idx] = (val)
+#define KA_SLOT_ADDR(base, col, row) ((base) + (col))
+#define KA_STD(a, k, off, val) (a)[k] = (val)
+#define KA_LDD(dst, a, k, off) const float dst = (a)[k]
+#define KA_STS2(rsb, v0, v1) { (rsb)[0] = (v0); (rsb)[1] = (v1); }
+#define KA_LDS2(rsw, row, d0, d1) const float d0 = (rsw)[0], d1 = (rsw)[1]
+#define ld16b ld16
+#define ld8b ld8
+#define ld4b ld4
+#define ld2b ld2
+#include "gen.cu"
+extern "C" void ka_run(const KAParams* p, float* loss) {
+  static float Xs[KA_C + 8192];
+  float rs[2] = {0.f, 0.f};
+  float acc = 0.f;
+  for (long long row = 0; row < p->B; ++row) {  // KA_TPB == 1 on the host: a "block" is one row
+    ka_sweep_a(*p, row, 1, Xs, 0);
+    ka_row(*p, row, p->targets ? p->targets[row] : 0, Xs, 0u, acc);
+    if (p->grad || p->class_probs) ka_sweep_b(*p, row, 1, Xs, 0);
+  }
+  if (loss) *loss = acc;
+}
+'''
+
+
+class KAParams(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_void_p), ("B", ctypes.c_longlong), ("ld", ctypes.c_longlong), ("targets", ctypes.c_void_p),
+                ("class_probs", ctypes.c_void_p), ("loss", ctypes.c_void_p), ("grad", ctypes.c_void_p),
+                ("w_xent", ctypes.c_float), ("w_tree", ctypes.c_float), ("inv_rows", ctypes.c_float),
+                ("grad_scale", ctypes.c_float)]
+
+
+def tree_desc(tree):
+    from nbdt._b200 import lib as L
+    from nbdt._b200.tables import flatten
+
+    child_ptr, child_node, root = flatten(tree)
+    desc = L.TreeDesc(len(tree.wnids_leaves), len(tree.inodes), root,
+                      child_ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                      child_node.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+    return desc, (child_ptr, child_node)
+
+
+def generated_source(tree, mode, dtype, vec):
+    from nbdt._b200 import lib as L
+
+    lib = L.load()
+    fn = lib.nbdt_tree_jit_source
+    fn.restype = ctypes.c_longlong
+    fn.argtypes = [ctypes.POINTER(L.TreeDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_longlong]
+    desc, keep = tree_desc(tree)
+    n = fn(ctypes.byref(desc), mode, dtype, vec, None, 0)
+    if n < 0:
+        return None
+    buf = ctypes.create_string_buffer(n + 1)
+    fn(ctypes.byref(desc), mode, dtype, vec, buf, n + 1)
+    return buf.value.decode()
+
+
+_cache = {}
+
+
+def host_kernel(tree, mode, dtype, vec):
+    """ctypes handle of the generated row function compiled for the host."""
+    src = generated_source(tree, mode, dtype, vec)
+    assert src is not None
+    key = hashlib.sha1(src.encode()).hexdigest()
+    if key in _cache:
+        return _cache[key]
+    d = tempfile.mkdtemp(prefix="ka_host_")
+    with open(os.path.join(d, "gen.cu"), "w") as f:
+        f.write(src)
+    with open(os.path.join(d, "harness.cpp"), "w") as f:
+        f.write(HARNESS)
+    so = os.path.join(d, "ka.so")
+    # -O1 -ffp-contract=off: fmaf() stays a real fused multiply-add, a*b+c is not contracted behind our back
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                    os.path.join(d, "harness.cpp")], check=True, cwd=d)
+    lib = ctypes.CDLL(so)
+    lib.ka_run.argtypes = [ctypes.POINTER(KAParams), ctypes.POINTER(ctypes.c_float)]
+    _cache[key] = lib
+    return lib
+
+
+def to_dtype_bytes(x, dtype):
+    """fp32 array -> (raw array in dtype code 0/1/2, the fp32 values it represents)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if dtype == 0:
+        return x, x
+    if dtype == 2:
+        h = x.astype(np.float16)
+        return h.view(np.uint16), h.astype(np.float32)
+    u = x.view(np.uint32)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+    return r, (r.astype(np.uint32) << 16).view(np.float32)
+
+
+def from_dtype_bytes(raw, dtype):
+    if dtype == 0:
+        return raw.astype(np.float64)
+    if dtype == 2:
+        return raw.view(np.float16).astype(np.float64)
+    return (raw.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+
+
+def run_loss(tree, mode, dtype, vec, x, y, w_xent, w_tree, want_grad=True, batch_rows=None, grad_scale=1.0):
+    lib = host_kernel(tree, mode, dtype, vec)
+    raw, _ = to_dtype_bytes(x, dtype)
+    B, C = x.shape
+    y = np.ascontiguousarray(y, dtype=np.int64)
+    grad = np.zeros_like(raw)
+    p = KAParams(raw.ctypes.data, B, C, y.ctypes.data, None, None, grad.ctypes.data if want_grad else None,
+                 w_xent, w_tree, 1.0 / (batch_rows or B), grad_scale)
+    loss = ctypes.c_float()
+    lib.ka_run(ctypes.byref(p), ctypes.byref(loss))
+    return loss.value, (from_dtype_bytes(grad, dtype) if want_grad else None)
+
+
+def run_soft_forward(tree, dtype, vec, x):
+    lib = host_kernel(tree, 2, dtype, vec)
+    raw, _ = to_dtype_bytes(x, dtype)
+    B, C = x.shape
+    out = np.zeros((B, C), dtype=np.float32)
+    p = KAParams(raw.ctypes.data, B, C, None, out.ctypes.data, None, None, 0, 0, 1, 1)
+    lib.ka_run(ctypes.byref(p), None)
+    return out
