@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NBDT_B200_VERSION 101 /* 101: MBConv entry points, nbdt_bn_backward takes scale_shift, strided stem */
+#define NBDT_B200_VERSION 102 /* 102: run-time specialised tree kernels (nbdt_tree_jit_*, nbdt_tree_kernel_variant); out-of-range targets are ignored rows */
 
 enum { NBDT_OK = 0, NBDT_EINVAL = 1, NBDT_ECUDA = 2, NBDT_ETREE = 3, NBDT_ETOOLARGE = 4 };
 enum { NBDT_F32 = 0, NBDT_BF16 = 1, NBDT_F16 = 2 };
@@ -62,6 +62,9 @@ int nbdt_device_count(void);
 int nbdt_tree_create(const nbdt_tree_desc* desc, int device, nbdt_tree** out);
 void nbdt_tree_destroy(nbdt_tree* tree);
 int nbdt_tree_max_depth(const nbdt_tree* tree);    /* max #decisions root->leaf                 */
+/* Name of the hierarchy-specialised kernel variant the last soft-forward / loss launch on this tree used ("" when the
+ * table-driven kernel ran): "ka<generator>_<hierarchy hash>_m<mode>_t<dtype>_v<vector bytes>_o<...>".  For bench lines. */
+const char* nbdt_tree_kernel_variant(const nbdt_tree* tree);
 int nbdt_tree_num_slots(const nbdt_tree* tree);    /* S = sum of children over inner nodes      */
 
 /* class_probs[b,c] = prod over inner nodes n on the path to c of softmax_k(node_logits_n[b,:])[k(n,c)],
@@ -104,6 +107,18 @@ int nbdt_soft_loss(const nbdt_tree* tree, const void* logits, int dtype, const i
 int nbdt_hard_loss(const nbdt_tree* tree, const void* logits, int dtype, const int64_t* targets,
                    int64_t B, int64_t ld, int64_t batch_rows, float w_xent, float w_tree, float tsw,
                    float grad_scale, float* loss, void* grad_logits, void* stream);
+/* Both losses: a row whose target is outside [0, C) is ignored -- it adds nothing to the loss and its gradient row is zero
+ * (nn.CrossEntropyLoss's ignore_index rows, reference loss.py:266 / model.py:127-143); the mean is still taken over
+ * batch_rows, so pass the number of non-ignored rows there to reproduce CrossEntropyLoss's normalisation. */
+
+/* Hierarchy-specialised kernels (csrc/tree_jit.cu).  nbdt_soft_forward / nbdt_soft_loss / nbdt_hard_loss run, for any
+ * hierarchy of up to 1536 leaves, a straight-line kernel generated from the nbdt_tree_desc and compiled with NVRTC on
+ * first use (cached on disk next to the library; NBDT_B200_TREE_JIT=0 disables, =cache uses only cached kernels).  The
+ * two calls below need no device: the generated CUDA source (tests compile it for the host and check it against the
+ * oracle; mode 0 soft loss, 1 hard loss, 2 soft forward; vec = bytes per logits vector access), and ahead-of-time
+ * compilation into the cache (the build does this for the shipped hierarchies). */
+long long nbdt_tree_jit_source(const nbdt_tree_desc* desc, int mode, int dtype, int vec, char* buf, long long cap);
+int nbdt_tree_jit_precompile(const nbdt_tree_desc* desc, int mode, int dtype);
 
 
 /* ---------------------------------------------------------------------------------------------

@@ -96,11 +96,11 @@ def _precompile_one(job):
 
 def precompile_tree_kernels(verbose=False):
     """Populate lib/tree_cache/ with the run-time-specialised tree kernels (csrc/tree_jit.cu) of every shipped hierarchy with
-    at most 256 leaves: soft loss, hard loss, soft forward x fp32, bf16, fp16.  NVRTC needs no GPU.  Any other hierarchy is
+    at most 1536 leaves: soft loss, hard loss, soft forward x fp32, bf16, fp16.  NVRTC needs no GPU.  Any other hierarchy is
     compiled on first use at run time; this only moves the few seconds per kernel to build time."""
     from concurrent.futures import ProcessPoolExecutor
 
-    jobs = [(name, C, ptr, nodes, root, mode, dtype) for name, C, ptr, nodes, root in _shipped_descs() if 2 <= C <= 256
+    jobs = [(name, C, ptr, nodes, root, mode, dtype) for name, C, ptr, nodes, root in _shipped_descs() if 2 <= C <= 1536
             for mode in (0, 1, 2) for dtype in (0, 1, 2)]
     failed = 0
     with ProcessPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:

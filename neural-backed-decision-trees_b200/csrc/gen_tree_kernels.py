@@ -126,11 +126,11 @@ def emit_kernel(name, C, children, root):
     for c in range(C):
         w(f"    const float x{c} = v[{c}];")
     # plain cross-entropy statistics of the raw logits
-    w("    float lse1 = 0.f, inv_s1 = 0.f, xy = 0.f; int y = 0;")
+    w("    float lse1 = 0.f, inv_s1 = 0.f, xy = 0.f; int y = 0; bool ign = false;  // ign: target out of range -> zero loss, zero gradient")
     for c in range(C):
         w(f"    float e{c} = 0.f;")
     w("    if (MODE != kSpecSoftFwd) {")
-    w("      y = (int)p.targets[row];")
+    w("      { const long long yt = p.targets[row]; ign = (unsigned long long)yt >= %dull; y = ign ? 0 : (int)yt; }" % C)
     w("      float m1 = x0;")
     for c in range(1, C):
         w(f"      m1 = fmaxf(m1, x{c});")
@@ -191,7 +191,7 @@ def emit_kernel(name, C, children, root):
     w("      float py = oh0 * P0;")
     for c in range(1, C):
         w(f"      py = fmaf(oh{c}, P{c}, py);")
-    w("      loss_acc += kx * (lse1 - xy) + kt * (kLn2 * lg2(s2) - py);")
+    w("      if (!ign) loss_acc += kx * (lse1 - xy) + kt * (kLn2 * lg2(s2) - py);")
     for c in range(C):
         w(f"      g{c} = kg * (q{c} * inv_s2 - {onehot(c)}) * P{c};")
     w("    } else {")
@@ -230,7 +230,7 @@ def emit_kernel(name, C, children, root):
     w("      float LPy = oh0 * LP0;")
     for c in range(1, C):
         w(f"      LPy = fmaf(oh{c}, LP{c}, LPy);")
-    w("      loss_acc += kx * (lse1 - xy) - kt * kLn2 * LPy;")
+    w("      if (!ign) loss_acc += kx * (lse1 - xy) - kt * kLn2 * LPy;")
     for c in range(C):
         w(f"      g{c} = -kg * oh{c};")
     w("    }")
@@ -249,7 +249,7 @@ def emit_kernel(name, C, children, root):
                 w(f"    const float A{c} = fmaf({term}, {1.0 / cnt[c]!r}f, A{vv});")
     w(f"    float o[{C}];")
     for c in range(C):
-        w(f"    o[{c}] = fmaf(kgx, fmaf(e{c}, inv_s1, -{onehot(c)}), A{c});")
+        w(f"    o[{c}] = ign ? 0.f : fmaf(kgx, fmaf(e{c}, inv_s1, -{onehot(c)}), A{c});")
     w(f"    store_row<T, {C}>(gout + row * p.ld, o);")
     w("  }")
     w("  block_loss_reduce(loss_acc, p.loss, MODE != kSpecSoftFwd);")

@@ -171,8 +171,12 @@ __global__ void __launch_bounds__(512) tree_kernel(const Params p) {
       for (int c = j; c < C; c += G) s1 += __expf(v1[c] - m1);
       s1 = group_sum<G>(s1);
       lse1 = m1 + __logf(s1);
-      if (valid) y = (int)p.targets[myrow];
-      xy = v1[y];
+      // target outside [0, C): the row is ignored (zero loss, zero gradient), like nn.CrossEntropyLoss's ignore_index; y = -1 marks it
+      if (valid) {
+        const long long yt = p.targets[myrow];
+        y = (unsigned long long)yt < (unsigned long long)C ? (int)yt : -1;
+      }
+      xy = v1[y < 0 ? 0 : y];
       __syncwarp();
     }
 
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(512) tree_kernel(const Params p) {
       for (int c = j; c < C; c += G) s2 += __expf(__expf(v2[c]));  // probs in [0,1]: no max shift needed
       s2 = group_sum<G>(s2);
       const float lse2 = __logf(s2);
-      const float py = __expf(v2[y]);
+      const float py = __expf(v2[y < 0 ? 0 : y]);
       row_loss = kx * (lse1 - xy) + kt * (lse2 - py);
       if (p.grad) {
         round_sync<G>();
@@ -337,18 +341,18 @@ __global__ void __launch_bounds__(512) tree_kernel(const Params p) {
         for (int c = j; c < C; c += G) {
           const float pc = __expf(v2[c]);
           const float sm = __expf(pc - lse2);
-          v2[c] = kg * (sm - (c == y ? 1.f : 0.f)) * pc;
+          v2[c] = y < 0 ? 0.f : kg * (sm - (c == y ? 1.f : 0.f)) * pc;
         }
       }
     } else {  // kHardLoss:  tree term = -LP[y] (sum of -lp along the target's path)
-      row_loss = kx * (lse1 - xy) - kt * v2[y];
+      row_loss = kx * (lse1 - xy) - kt * v2[y < 0 ? 0 : y];
       if (p.grad) {
         round_sync<G>();
         const float kg = kt * p.grad_scale;
         for (int c = j; c < C; c += G) v2[c] = (c == y) ? -kg : 0.f;
       }
     }
-    if (j == 0 && valid) loss_acc += row_loss;
+    if (j == 0 && valid && y >= 0) loss_acc += row_loss;
     if (!p.grad) {
       __syncwarp();
       continue;
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(512) tree_kernel(const Params p) {
         if (e < RPW * C && rr < nrows) {
           const long long o = (row0 + rr) * p.ld + c;
           float gx = V1[rr * NVp + c];
-          if (MODE != kSoftBwd) gx += kgx * (__expf(to_f<T>(x[o]) - l1) - (c == yy ? 1.f : 0.f));
+          if (MODE != kSoftBwd) gx = yy < 0 ? 0.f : gx + kgx * (__expf(to_f<T>(x[o]) - l1) - (c == yy ? 1.f : 0.f));
           g[o] = from_f<T>(gx);
         }
       }
@@ -735,6 +739,7 @@ void nbdt_tree_destroy(nbdt_tree* t) {
 
 int nbdt_tree_max_depth(const nbdt_tree* t) { return t ? t->dev.Dmax : -1; }
 int nbdt_tree_num_slots(const nbdt_tree* t) { return t ? t->dev.S : -1; }
+const char* nbdt_tree_kernel_variant(const nbdt_tree* t) { return t ? tree_jit_last_variant(t->jit) : ""; }
 
 int nbdt_soft_forward(const nbdt_tree* tree, const void* logits, int dtype, int64_t B, int64_t ld,
                       float* class_probs, void* stream) {

@@ -32,6 +32,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -47,8 +48,8 @@
 
 namespace {
 
-constexpr int kGeneratorVersion = 7;   // part of the cache key: bump when the emitted code changes
-constexpr int kMaxLeaves = 256;        // 4*C bytes of shared memory per row: above this too few rows fit on an SM
+constexpr int kGeneratorVersion = 9;   // part of the cache key: bump when the emitted code changes
+constexpr int kMaxLeaves = 1536;       // 32 rows x 132 B per leaf of shared memory per block: 1000 leaves (ImageNet) use 16 warps on 150 KB
 constexpr int kTPB = 32;               // one warp per CTA: rows are thread-private, only __syncwarp around the cooperative I/O sweeps
 // Shared-memory layout of a 32-row block: slot c (class c, later prefix / gradient) of row r lives at word
 //   c*32 + c/U + rho(r),   rho(r) = (r*K) & 31,   U = elements per I/O vector,   K = ((C/U) & 31) | 1 (odd)
@@ -65,10 +66,11 @@ struct Knobs {
   int regcap = kRegValueCap;  // NBDT_B200_KA_REGCAP: node values kept in registers
   int minb = 0;               // NBDT_B200_KA_MINB: __launch_bounds__ min blocks (0 = derived from the register estimate)
   int unroll = 8;             // NBDT_B200_KA_UNROLL: unroll factor of the I/O sweeps (0 = full)
-  int prefetch = 1;           // NBDT_B200_KA_PREFETCH: row blocks ahead whose lines are prefetched into L2 (0 = off)
+  int prefetch = 0;           // NBDT_B200_KA_PREFETCH: row blocks ahead whose lines are prefetched into L2 (0 = off; measured: no gain)
   int maxld = 24;             // NBDT_B200_KA_MAXLD: 16-byte loads a lane keeps in flight in sweep A before their stores
   int fence = 8;              // NBDT_B200_KA_FENCE: nodes between scheduling fences of the straight-line passes (0 = none)
-  bool is_default() const { return regcap == kRegValueCap && minb == 0 && unroll == 8 && prefetch == 1 && maxld == 24 && fence == 8; }
+  int warps = 0;              // NBDT_B200_KA_WARPS: warps per row block (0 = by leaf count)
+  bool is_default() const { return regcap == kRegValueCap && minb == 0 && unroll == 8 && prefetch == 0 && maxld == 24 && fence == 8 && warps == 0; }
 };
 Knobs read_knobs() {
   Knobs k;
@@ -79,6 +81,7 @@ Knobs read_knobs() {
   k.prefetch = std::max(0, std::min(8, geti("NBDT_B200_KA_PREFETCH", k.prefetch)));
   k.maxld = std::max(1, std::min(64, geti("NBDT_B200_KA_MAXLD", k.maxld)));
   k.fence = std::max(0, geti("NBDT_B200_KA_FENCE", k.fence));
+  k.warps = std::max(0, std::min(16, geti("NBDT_B200_KA_WARPS", k.warps)));
   return k;
 }
 
@@ -155,12 +158,33 @@ struct Variant {
   int key() const { return ((mode * 4 + dtype) * 32 + vec) * 32 + ovec; }
 };
 
+// A team of W warps shares one block of 32 rows: the hierarchy is cut into disjoint subtrees ("cut subtrees", at most about
+// C/(2W) leaves each) that are bin-packed onto the warps, and the few nodes above the cut ("top tree") go to warp 0.  Every
+// warp runs the straight-line code of ITS subtrees for the same 32 rows (lane = row), so the node values a thread keeps in
+// registers, the code a warp streams through the instruction cache and the shared memory per resident warp all shrink by W.
+// The parts meet at bar.sync between the passes and exchange one value per cut root through shared memory.
+struct Team {
+  int W = 1;
+  std::vector<int> cut_id;                     // [NV] index of the cut subtree rooted here, or -1
+  std::vector<int> cut_nodes;                  // [ncut] root node of each cut subtree, in DFS order
+  std::vector<int> part_of_cut;                // [ncut] warp that owns it
+  std::vector<std::vector<int>> cuts_of_part;  // [W] cut indices, DFS order
+  std::vector<int> part_of_node;               // [NV] owner warp (top-tree nodes: 0)
+  std::vector<char> is_top;                    // [NV]
+  int ntop = 0;
+  int ncut() const { return (int)cut_nodes.size(); }
+};
+
 struct Plan {
-  int nvalues = 0;                 // persistent node values
-  int nspill = 0;                  // of which in shared memory
-  std::vector<int> value_slot;     // [NV]: first value index of node v's values (binary inner: 1 value at the node; k-ary: per child)
+  int nvalues = 0;                 // persistent node values (whole hierarchy)
+  std::vector<int> value_slot;     // [NV]: first value id of node v's values (binary inner: 1 value; k-ary: one per child)
+  std::vector<int> value_part;     // [nvalues] owner warp
+  std::vector<int> value_spill;    // [nvalues] spill index within the owner's spill region, or -1 (register)
+  int maxspill = 0;                // spill slots per warp
   int smem_bytes = 0;              // per CTA (upper bound over the variants' skew)
   int min_blocks = 1;              // __launch_bounds__ second argument
+  int threads = kTPB;              // 32 * W
+  Team team;
   Knobs knobs;
 };
 
@@ -217,11 +241,6 @@ KA_DEV uint4 ld16(const char* p) { return __ldg(reinterpret_cast<const uint4*>(p
 KA_DEV uint2 ld8(const char* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 KA_DEV u32 ld4(const char* p) { return __ldg(reinterpret_cast<const u32*>(p)); }
 KA_DEV u32 ld2(const char* p) { return __ldg(reinterpret_cast<const u16*>(p)); }
-// second read of the row in sweep B: volatile so that it is not merged with sweep A's loads (which would keep the whole row live)
-KA_DEV uint4 ld16b(const char* p) { uint4 r; asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r; }
-KA_DEV uint2 ld8b(const char* p) { uint2 r; asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p)); return r; }
-KA_DEV u32 ld4b(const char* p) { u32 r; asm volatile("ld.global.u32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }
-KA_DEV u32 ld2b(const char* p) { u32 r; asm volatile("{ .reg .b16 h; ld.global.u16 h, [%1]; cvt.u32.u16 %0, h; }" : "=r"(r) : "l"(p)); return r; }
 #define KA_LDX(dst, base, slot, off) float dst; asm volatile("ld.shared.f32 %0, [%1+" #off "];" : "=f"(dst) : "r"(base))
 #define KA_STX(base, slot, off, val) asm volatile("st.shared.f32 [%0+" #off "], %1;" :: "r"(base), "f"(val))
 #define KA_OPAQUE(x) asm volatile("" : "+f"(x))
@@ -233,9 +252,12 @@ KA_DEV u32 ld2b(const char* p) { u32 r; asm volatile("{ .reg .b16 h; ld.global.u
 #define KA_SLOT_ADDR(base, col, row) ((base) + ((u32)(col) * 32u + (u32)(col) / KA_U + (((u32)(row) * KA_K) & 31u)) * 4u)
 #define KA_STD(a, k, off, val) asm volatile("st.shared.f32 [%0+" #off "], %1;" :: "r"(a), "f"(val))
 #define KA_LDD(dst, a, k, off) float dst; asm volatile("ld.shared.f32 %0, [%1+" #off "];" : "=f"(dst) : "r"(a))
-// per-row (-log2 sum exp(x), weight of the plain cross-entropy term) pair
-#define KA_STS2(rsb, v0, v1) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"(rsb), "f"(v0), "f"(v1))
-#define KA_LDS2(rsw, row, d0, d1) float d0, d1; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(d0), "=f"(d1) : "r"((rsw) + (u32)(row) * 8u))
+// the parts of a team meet here (all threads of the CTA); a single-warp kernel needs no barrier inside the row function
+#if KA_W > 1
+#define KA_BAR() asm volatile("bar.sync 0;" ::: "memory")
+#else
+#define KA_BAR()
+#endif
 KA_DEV void st16(char* p, u32 a, u32 b, u32 c, u32 d) { *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d); }
 KA_DEV void st8(char* p, u32 a, u32 b) { *reinterpret_cast<uint2*>(p) = make_uint2(a, b); }
 KA_DEV void st4(char* p, u32 a) { *reinterpret_cast<u32*>(p) = a; }
@@ -267,25 +289,27 @@ struct Gen {
   const KTree& t;
   const Variant v;
   const Plan& plan;
+  const Team& team;
   Out o;
-  int acc = 0;  // round-robin partial accumulators
-  Gen(const KTree& t_, const Variant& v_, const Plan& p_) : t(t_), v(v_), plan(p_) {}
+  int acc = 0;       // round-robin partial accumulators
+  int part = 0;      // warp whose code is being emitted
+  bool top = false;  // emitting the top tree (stops at the cut roots)
+  Gen(const KTree& t_, const Variant& v_, const Plan& p_) : t(t_), v(v_), plan(p_), team(p_.team) {}
 
   bool leaf(int n) const { return n < t.C; }
   const std::vector<int>& kids(int n) const { return t.ch[n - t.C]; }
   bool binary(int n) const { return kids(n).size() == 2; }
   bool loss_mode() const { return v.mode != kSpecSoftFwd; }
   int esz() const { return v.dtype == NBDT_F32 ? 4 : 2; }
+  bool teamed() const { return team.W > 1; }
+  bool is_cut(int n) const { return teamed() && team.cut_id[n] >= 0; }
 
-  // ---- persistent node values: register variable or shared-memory slot ----
-  // value id of a binary node = plan.value_slot[node]; of child k of a k-ary node = plan.value_slot[node] + k
-  bool spilled(int vid) const { return vid >= plan.nvalues - plan.nspill; }
-  int tmp = 0;
-  // Scheduling fences.  The passes are one basic block of thousands of instructions with hundreds of independent chains;
-  // left alone ptxas front-loads as many of them as it can and spills hundreds of registers.  Every `fence` nodes the next
-  // node's input is OR-ed with (last value produced & zr), zr a run-time zero: a real data dependency that changes no value
-  // and costs one LOP3, so the scheduler's window is a group of nodes rather than the whole pass.
-  int since = 0, nfence = 0;
+  // ---- scheduling fences ----
+  // The passes are one basic block of thousands of instructions with hundreds of independent chains; left alone ptxas
+  // front-loads as many of them as it can and spills hundreds of registers.  Every `fence` nodes the next node's input is
+  // OR-ed with (last value produced & zr), zr a run-time zero: a real data dependency that changes no value and costs one
+  // LOP3, so the scheduler's window is a group of nodes rather than the whole pass.
+  int tmp = 0, since = 0, nfence = 0;
   std::string last;
   std::string base = "xsb";
   void note(const std::string& name) { last = name; ++since; }
@@ -306,16 +330,25 @@ struct Gen {
     o.f("    const KA_XSB %s = xsb + (f2u(%s) & zr);", b, last.c_str());
     base = b;
   }
-  int U = 1, K = 1;  // skew unit and row multiplier of the shared-memory layout (see the layout comment at the top)
+
+  // ---- shared-memory slots ----
+  // slots 0..C-1: the row (x, later dL/dx or the class probabilities); then W spill regions of plan.maxspill slots; then the
+  // exchange slots of the team.  Byte offsets are relative to the thread's base (rho(lane) words into the block).
+  int U = 1, K = 1;  // skew unit and row multiplier of the layout (see the layout comment at the top of this file)
   int row_words() const { return (t.C * 32 + t.C / U + 32 + 3) & ~3; }
-  int soff(int slot) const {  // byte offset of a slot from the thread's base
+  int soff(int slot) const {
     if (slot < t.C) return (slot * 32 + slot / U) * 4;
     return (row_words() + (slot - t.C) * 32) * 4;
   }
   int eoff(int k) const { return (k * 32 + k / U) * 4; }  // element k of a vector, relative to the vector's first slot
-  // shared-memory slot access: slots 0..C-1 are the row (x -> prefix F -> gradient), C.. the spilled node values.
-  // Emitted as volatile inline PTX with immediate offsets (KA_LDX / KA_STX): plain C++ accesses get forwarded by the
-  // compiler into registers and from there into local-memory spills.
+  int spill_slot(int vid) const { return t.C + plan.value_part[vid] * plan.maxspill + plan.value_spill[vid]; }
+  int ex_base() const { return t.C + team.W * plan.maxspill; }
+  int ex_p(int k) const { return ex_base() + k; }                      // subtree sum S, then path probability P (hard: on-path flag)
+  int ex_h(int k) const { return ex_base() + team.ncut() + k; }        // gradient sum H, then accumulated gradient A
+  int ex_w(int j, int w) const { return ex_base() + 2 * team.ncut() + j * team.W + w; }  // per-warp partials: 0 max, 1 sum exp, 2 Z, 3 P[target] / path loss
+  int total_slots() const { return ex_base() + 2 * team.ncut() + 4 * team.W; }
+  // Emitted as volatile inline PTX with immediate offsets: plain C++ accesses get forwarded by the compiler into registers and
+  // from there into local-memory spills.
   std::string ldx(int slot) {
     char b[32];
     snprintf(b, sizeof b, "t%d", tmp++);
@@ -323,7 +356,10 @@ struct Gen {
     return b;
   }
   void stx(int slot, const std::string& val) { o.f("    KA_STX(%s, %d, %d, %s);", base.c_str(), slot, soff(slot), val.c_str()); }
-  int spill_slot(int vid) const { return t.C + vid - (plan.nvalues - plan.nspill); }
+
+  // ---- persistent node values: register variable or spill slot of the owning warp ----
+  // value id of a binary node = plan.value_slot[node]; of child k of a k-ary node = plan.value_slot[node] + k
+  bool spilled(int vid) const { return plan.value_spill[vid] >= 0; }
   std::string vget(int vid) {
     if (spilled(vid)) return ldx(spill_slot(vid));
     return "nv" + std::to_string(vid);
@@ -332,20 +368,22 @@ struct Gen {
     if (spilled(vid)) stx(spill_slot(vid), expr);
     else o.f("    const float nv%d = %s;", vid, expr.c_str());
   }
+  std::string kget(int vid) {  // k-ary child value
+    if (spilled(vid)) return ldx(spill_slot(vid));
+    return "km" + std::to_string(vid);
+  }
+  // gradient values: same placement as the probability values they replace
+  void dset(int vid, const std::string& expr) {
+    if (spilled(vid)) stx(spill_slot(vid), expr);
+    else o.f("    const float dv%d = %s;", vid, expr.c_str());
+  }
+  std::string dget(int vid) {
+    if (spilled(vid)) return ldx(spill_slot(vid));
+    return "dv" + std::to_string(vid);
+  }
 
   // ---- row vectors ----
-  int nvec() const { return t.C * esz() / v.vec; }
   int per_vec() const { return v.vec / esz(); }
-  void load_vec(const char* name, int i, bool again = false) {  // again: the second read of the row (must not be merged with the first)
-    const int off = i * v.vec;
-    const char* sfx = again ? "b" : "";
-    switch (v.vec) {
-      case 16: o.f("    const uint4 %s%d = ld16%s(xr + %d);", name, i, sfx, off); break;
-      case 8: o.f("    const uint2 %s%d = ld8%s(xr + %d);", name, i, sfx, off); break;
-      case 4: o.f("    const u32 %s%d = ld4%s(xr + %d);", name, i, sfx, off); break;
-      default: o.f("    const u32 %s%d = ld2%s(xr + %d);", name, i, sfx, off); break;
-    }
-  }
   std::string word(const char* name, int i, int w) const {  // w-th 32-bit word of vector i
     char b[48];
     static const char* comp[4] = {"x", "y", "z", "w"};
@@ -353,7 +391,7 @@ struct Gen {
     else snprintf(b, sizeof b, "%s%d", name, i);
     return b;
   }
-  std::string elem(const char* name, int c) const {  // fp32 value of class c out of the loaded vectors
+  std::string elem(const char* name, int c) const {  // fp32 value of element c out of the loaded vectors name0, name1, ...
     const int pv = per_vec(), i = c / pv, j = c % pv;
     char b[96];
     if (v.dtype == NBDT_F32) {
@@ -361,8 +399,7 @@ struct Gen {
     } else {
       const std::string w = word(name, i, j / 2);
       if (v.dtype == NBDT_BF16) {
-        if (v.vec == 2) snprintf(b, sizeof b, "u2f(%s << 16)", w.c_str());
-        else if (j % 2 == 0) snprintf(b, sizeof b, "u2f(%s << 16)", w.c_str());
+        if (v.vec == 2 || j % 2 == 0) snprintf(b, sizeof b, "u2f(%s << 16)", w.c_str());
         else snprintf(b, sizeof b, "u2f(%s & 0xffff0000u)", w.c_str());
       } else {
         if (v.vec == 2 || j % 2 == 0) snprintf(b, sizeof b, "h2f(%s)", w.c_str());
@@ -372,8 +409,14 @@ struct Gen {
     return b;
   }
 
-  // ---- pass 1: post-order ----
+  // ---- pass 1: post-order.  Subtree sums in registers; per inner node the persistent value ----
   void up(int n) {
+    if (top && is_cut(n)) {  // top tree: the sum of a cut subtree comes from its owner
+      fence_base();
+      o.f("    KA_LDX(ts%d, %s, %d, %d);", n, base.c_str(), ex_p(team.cut_id[n]), soff(ex_p(team.cut_id[n])));
+      note("ts" + std::to_string(n));
+      return;
+    }
     if (leaf(n)) {
       fence_base();
       o.f("    KA_LDX(s%d, %s, %d, %d);", n, base.c_str(), n, soff(n));
@@ -383,9 +426,10 @@ struct Gen {
     }
     const std::vector<int>& c = kids(n);
     for (int k : c) up(k);
+    auto sn = [&](int k) { return std::string(top && is_cut(k) ? "ts" : "s") + std::to_string(k); };
     if (n != t.root) {
       std::string sum;
-      for (size_t k = 0; k < c.size(); ++k) { char b[24]; snprintf(b, sizeof b, "%ss%d", k ? " + " : "", c[k]); sum += b; }
+      for (size_t k = 0; k < c.size(); ++k) sum += (k ? " + " : "") + sn(c[k]);
       o.f("    const float s%d = %s;", n, sum.c_str());
     }
     const int vid = plan.value_slot[n];
@@ -393,7 +437,7 @@ struct Gen {
     if (binary(n)) {
       char e[160];
       // t = m_a - m_b in log2 units
-      snprintf(e, sizeof e, "fmaf(s%d, %s, s%d * %s)", c[0], lit(kLog2e / t.cnt[c[0]]).c_str(), c[1], lit(-kLog2e / t.cnt[c[1]]).c_str());
+      snprintf(e, sizeof e, "fmaf(%s, %s, %s * %s)", sn(c[0]).c_str(), lit(kLog2e / t.cnt[c[0]]).c_str(), sn(c[1]).c_str(), lit(-kLog2e / t.cnt[c[1]]).c_str());
       if (v.mode == kSpecHardLoss) vset(vid, e);
       else vset(vid, std::string("signed_lo(") + e + ")");
       if (!spilled(vid)) note("nv" + std::to_string(vid));
@@ -401,7 +445,7 @@ struct Gen {
     }
     // k-ary: softmax over the children (log2 domain)
     o.f("    {");
-    for (int k : c) o.f("      const float a%d = s%d * %s;", k, k, lit(kLog2e / t.cnt[k]).c_str());
+    for (int k : c) o.f("      const float a%d = %s * %s;", k, sn(k).c_str(), lit(kLog2e / t.cnt[k]).c_str());
     std::string mx = "a" + std::to_string(c[0]);
     for (size_t k = 1; k < c.size(); ++k) mx = "fmaxf(" + mx + ", a" + std::to_string(c[k]) + ")";
     o.f("      const float mx = %s;", mx.c_str());
@@ -420,17 +464,13 @@ struct Gen {
     for (size_t k = 0; k < c.size(); ++k)
       if (spilled(vid + (int)k)) stx(spill_slot(vid + (int)k), "km" + std::to_string(vid + (int)k));
   }
-  // k-ary values are declared before the block that sets them
+  // k-ary values of the current part are declared before the blocks that set them
   void declare_kary() {
     for (int n = t.C; n < t.NV; ++n) {
       const std::vector<int>& c = kids(n);
-      if (c.size() <= 2) continue;
+      if (c.size() <= 2 || team.part_of_node[n] != part) continue;
       for (size_t k = 0; k < c.size(); ++k) o.f("    float km%d;", plan.value_slot[n] + (int)k);
     }
-  }
-  std::string kget(int vid) {  // k-ary child value
-    if (spilled(vid)) return ldx(spill_slot(vid));
-    return "km" + std::to_string(vid);
   }
 
   // ---- pass 2 (soft): pre-order path probabilities ----
@@ -477,7 +517,8 @@ struct Gen {
   void down(int n, const std::string& P, const char* pre, int what) {
     child_probs(n, P, pre);
     for (int k : kids(n)) {
-      if (leaf(k)) leaf_prob(k, pre, what);
+      if (top && is_cut(k)) { stx(ex_p(team.cut_id[k]), pre + std::to_string(k)); note(pre + std::to_string(k)); }
+      else if (leaf(k)) leaf_prob(k, pre, what);
       else down(k, pre + std::to_string(k), pre, what);
     }
   }
@@ -486,18 +527,35 @@ struct Gen {
   // H[v] = sum over the leaves under v of dL/dP[leaf] * P[leaf] (up to the factor cA) and per node the gradient of its child
   // logits dm[c] = H[c] - p[c]*H[v], which REPLACES the node's probability value (register or slot).  Returns the name of
   // H[n].  Nothing is stored per leaf: the row's x stays in its slots for the final pass.
-  std::string updown(int n, const std::string& P) {
+  std::string leaf_g(int k, const std::string& Q) {
+    o.f("    const float G%d = %s * (exp01(%s) - ((posy == %d) ? Z : 0.f));", k, Q.c_str(), Q.c_str(), t.pos[k]);
+    return "G" + std::to_string(k);
+  }
+  void node_grad(int n, const std::string& H, const std::vector<std::string>& h, bool opaque) {
     const std::vector<int>& c = kids(n);
     const int vid = plan.value_slot[n];
+    if (binary(n)) {
+      std::string sp = opaque ? "Qs" + std::to_string(n) : vget(vid);
+      o.f("    const float pa%d = first_is_hi(%s) ? 1.f - fabsf(%s) : fabsf(%s);", n, sp.c_str(), sp.c_str(), sp.c_str());
+      char e[96];
+      snprintf(e, sizeof e, "cA * fmaf(-pa%d, %s, %s)", n, H.c_str(), h[0].c_str());
+      dset(vid, e);
+    } else {
+      for (size_t k = 0; k < c.size(); ++k) {
+        const std::string pk = opaque ? "Qk" + std::to_string(c[k]) : kget(vid + (int)k);
+        char e[128];
+        snprintf(e, sizeof e, "cA * fmaf(-%s, %s, %s)", pk.c_str(), H.c_str(), h[k].c_str());
+        dset(vid + (int)k, e);
+      }
+    }
+  }
+  std::string updown(int n, const std::string& P) {
+    const std::vector<int>& c = kids(n);
     child_probs(n, P, "Q");
     std::vector<std::string> h;
     for (int k : c) {
-      if (leaf(k)) {
-        o.f("    const float G%d = Q%d * (exp01(Q%d) - ((posy == %d) ? Z : 0.f));", k, k, k, t.pos[k]);
-        h.push_back("G" + std::to_string(k));
-      } else {
-        h.push_back(updown(k, "Q" + std::to_string(k)));
-      }
+      if (leaf(k)) h.push_back(leaf_g(k, "Q" + std::to_string(k)));
+      else h.push_back(updown(k, "Q" + std::to_string(k)));
     }
     const std::string H = "G" + std::to_string(n);
     if (c.size() == 1) {
@@ -508,28 +566,24 @@ struct Gen {
     for (size_t k = 0; k < h.size(); ++k) sum += (k ? " + " : "") + h[k];
     o.f("    const float %s = %s;", H.c_str(), sum.c_str());
     note(H);
-    if (binary(n)) {
-      o.f("    const float pa%d = first_is_hi(Qs%d) ? 1.f - fabsf(Qs%d) : fabsf(Qs%d);", n, n, n, n);
-      char e[96];
-      snprintf(e, sizeof e, "cA * fmaf(-pa%d, %s, %s)", n, H.c_str(), h[0].c_str());
-      dset(vid, e);
-    } else {
-      for (size_t k = 0; k < c.size(); ++k) {
-        char e[128];
-        snprintf(e, sizeof e, "cA * fmaf(-Qk%d, %s, %s)", c[k], H.c_str(), h[k].c_str());
-        dset(vid + (int)k, e);
-      }
-    }
+    node_grad(n, H, h, true);
     return H;
   }
-  // gradient values: same placement as the probability values they replace
-  void dset(int vid, const std::string& expr) {
-    if (spilled(vid)) stx(spill_slot(vid), expr);
-    else o.f("    const float dv%d = %s;", vid, expr.c_str());
-  }
-  std::string dget(int vid) {
-    if (spilled(vid)) return ldx(spill_slot(vid));
-    return "dv" + std::to_string(vid);
+  // top tree, up half only: the sums of the cut subtrees come from their owners
+  std::string top_h(int n) {
+    const std::vector<int>& c = kids(n);
+    std::vector<std::string> h;
+    for (int k : c) {
+      if (is_cut(k)) { fence_base(); h.push_back(ldx(ex_h(team.cut_id[k]))); }
+      else h.push_back(top_h(k));
+    }
+    const std::string H = "G" + std::to_string(n);
+    std::string sum;
+    for (size_t k = 0; k < h.size(); ++k) sum += (k ? " + " : "") + h[k];
+    o.f("    const float %s = %s;", H.c_str(), sum.c_str());
+    note(H);
+    if (c.size() > 1) node_grad(n, H, h, false);
+    return H;
   }
   // leaf c: dL/dx[c] = A[c] + cx * softmax(x)[c]  (the one-hot of the target is subtracted afterwards), written over x
   void leaf_out(int c, const std::string& A) {
@@ -543,13 +597,15 @@ struct Gen {
   void back(int n, const std::string& A) {
     const std::vector<int>& c = kids(n);
     const int vid = plan.value_slot[n];
+    const char* ap = top ? "B" : "A";  // the top tree's names must not collide with warp 0's own subtrees
+    auto an = [&](int k) { return std::string(ap) + std::to_string(k); };
     auto fma_a = [&](int child, const std::string& d) {
       const std::string inv = lit(1.0 / t.cnt[child]);
-      if (A.empty()) o.f("    const float A%d = %s * %s;", child, d.c_str(), inv.c_str());
-      else o.f("    const float A%d = fmaf(%s, %s, %s);", child, d.c_str(), inv.c_str(), A.c_str());
+      if (A.empty()) o.f("    const float %s%d = %s * %s;", ap, child, d.c_str(), inv.c_str());
+      else o.f("    const float %s%d = fmaf(%s, %s, %s);", ap, child, d.c_str(), inv.c_str(), A.c_str());
     };
     if (c.size() == 1) {
-      o.f("    const float A%d = %s;", c[0], A.empty() ? "0.f" : A.c_str());
+      o.f("    const float %s%d = %s;", ap, c[0], A.empty() ? "0.f" : A.c_str());
     } else if (binary(n)) {
       const std::string d = fenced(dget(vid));
       fma_a(c[0], d);
@@ -557,10 +613,11 @@ struct Gen {
     } else {
       for (size_t k = 0; k < c.size(); ++k) fma_a(c[k], dget(vid + (int)k));
     }
-    note("A" + std::to_string(c.back()));
+    note(an(c.back()));
     for (int ck : c) {
-      if (leaf(ck)) leaf_out(ck, "A" + std::to_string(ck));
-      else back(ck, "A" + std::to_string(ck));
+      if (top && is_cut(ck)) stx(ex_h(team.cut_id[ck]), an(ck));
+      else if (leaf(ck)) leaf_out(ck, an(ck));
+      else back(ck, an(ck));
     }
   }
 
@@ -570,45 +627,55 @@ struct Gen {
     const std::vector<int>& c = kids(n);
     const int vid = plan.value_slot[n];
     const std::string onv = on.empty() ? "1.f" : on;
+    const char* ap = top ? "B" : "A";    // the top tree's names must not collide with warp 0's own subtrees
+    const char* op = top ? "ton" : "on";
+    auto an = [&](int k) { return std::string(ap) + std::to_string(k); };
+    auto onn = [&](int k) { return std::string(op) + std::to_string(k); };
     auto fma_a = [&](int child, const std::string& d) {
       const std::string inv = lit(1.0 / t.cnt[child]);
-      if (A.empty()) o.f("    const float A%d = %s * %s;", child, d.c_str(), inv.c_str());
-      else o.f("    const float A%d = fmaf(%s, %s, %s);", child, d.c_str(), inv.c_str(), A.c_str());
+      if (A.empty()) o.f("    const float %s%d = %s * %s;", ap, child, d.c_str(), inv.c_str());
+      else o.f("    const float %s%d = fmaf(%s, %s, %s);", ap, child, d.c_str(), inv.c_str(), A.c_str());
     };
     if (c.size() == 1) {
-      o.f("    const float on%d = %s; const float A%d = %s;", c[0], onv.c_str(), c[0], A.empty() ? "0.f" : A.c_str());
+      o.f("    const float %s%d = %s; const float %s%d = %s;", op, c[0], onv.c_str(), ap, c[0], A.empty() ? "0.f" : A.c_str());
     } else if (binary(n)) {
       const int a = c[0], b = c[1];
-      o.f("    const float on%d = (posy < %d) ? %s : 0.f; const float on%d = %s - on%d;", a, t.end[a], onv.c_str(), b, onv.c_str(), a);
+      o.f("    const float %s%d = (posy < %d) ? %s : 0.f; const float %s%d = %s - %s%d;", op, a, t.end[a], onv.c_str(), op, b, onv.c_str(), op, a);
       o.f("    const float ht%d = %s; const float hq%d = ex2(-fabsf(ht%d)); const float hd%d = 1.f + hq%d; const float hr%d = rcp(hd%d);",
           n, fenced(vget(vid)).c_str(), n, n, n, n, n, n);
       o.f("    const float pa%d = ht%d >= 0.f ? hr%d : hq%d * hr%d;", n, n, n, n, n);
       // -log2 p(child) = log2(1 + 2^-|t|) + max(-t, 0) for the first child, + max(t, 0) for the second
-      o.f("    lp = fmaf(%s, lg2(hd%d), lp); lp = fmaf(on%d, fmaxf(-ht%d, 0.f), lp); lp = fmaf(on%d, fmaxf(ht%d, 0.f), lp);",
-          onv.c_str(), n, a, n, b, n);
-      o.f("    const float d%d = nkg * fmaf(-pa%d, %s, on%d);", n, n, onv.c_str(), a);
+      o.f("    lp = fmaf(%s, lg2(hd%d), lp); lp = fmaf(%s%d, fmaxf(-ht%d, 0.f), lp); lp = fmaf(%s%d, fmaxf(ht%d, 0.f), lp);",
+          onv.c_str(), n, op, a, n, op, b, n);
+      o.f("    const float d%d = nkg * fmaf(-pa%d, %s, %s%d);", n, n, onv.c_str(), op, a);
       fma_a(a, "d" + std::to_string(n));
       fma_a(b, "-d" + std::to_string(n));
     } else {
       std::string sum;
       for (size_t k = 0; k < c.size(); ++k) {
         const int ck = c[k];
-        o.f("    const float on%d = ((unsigned)(posy - %d) < %du) ? %s : 0.f;", ck, t.beg[ck], t.cnt[ck], onv.c_str());
+        o.f("    const float %s%d = ((unsigned)(posy - %d) < %du) ? %s : 0.f;", op, ck, t.beg[ck], t.cnt[ck], onv.c_str());
         o.f("    const float km_%d = %s; const float kq_%d = ex2(km_%d);", ck, kget(vid + (int)k).c_str(), ck, ck);
         sum += (k ? " + kq_" : "kq_") + std::to_string(ck);
       }
       o.f("    const float hs%d = %s; const float hr%d = rcp(hs%d);", n, sum.c_str(), n, n);
       o.f("    lp = fmaf(%s, lg2(hs%d), lp);", onv.c_str(), n);
       for (int ck : c) {
-        o.f("    lp = fmaf(-on%d, km_%d, lp);", ck, ck);
-        o.f("    const float dk%d = nkg * fmaf(-kq_%d * hr%d, %s, on%d);", ck, ck, n, onv.c_str(), ck);
+        o.f("    lp = fmaf(-%s%d, km_%d, lp);", op, ck, ck);
+        o.f("    const float dk%d = nkg * fmaf(-kq_%d * hr%d, %s, %s%d);", ck, ck, n, onv.c_str(), op, ck);
         fma_a(ck, "dk" + std::to_string(ck));
       }
     }
     for (int ck : c) {
-      note("A" + std::to_string(ck));
-      if (leaf(ck)) leaf_out(ck, "A" + std::to_string(ck));
-      else hard(ck, "on" + std::to_string(ck), "A" + std::to_string(ck));
+      note(an(ck));
+      if (top && is_cut(ck)) {
+        stx(ex_p(team.cut_id[ck]), onn(ck));
+        stx(ex_h(team.cut_id[ck]), an(ck));
+      } else if (leaf(ck)) {
+        leaf_out(ck, an(ck));
+      } else {
+        hard(ck, onn(ck), an(ck));
+      }
     }
   }
 
@@ -628,62 +695,242 @@ struct Gen {
     o.f("    st%d(%s + %d%s);", vec, ptr, i * vec, args.c_str());
   }
 
-  // one vector of the row block: load + unpack to floats f0..f{pv-1} (sweeps A and B of the cooperative I/O)
-  void coop_load(const char* name, bool again) {
-    const char* sfx = again ? "b" : "";
+  // one vector of the row block in the generic (strided / partial block) sweep
+  void coop_load(const char* name) {
     switch (v.vec) {
-      case 16: o.f("        const uint4 %s0 = ld16%s(gp);", name, sfx); break;
-      case 8: o.f("        const uint2 %s0 = ld8%s(gp);", name, sfx); break;
-      case 4: o.f("        const u32 %s0 = ld4%s(gp);", name, sfx); break;
-      default: o.f("        const u32 %s0 = ld2%s(gp);", name, sfx); break;
+      case 16: o.f("        const uint4 %s0 = ld16(gp);", name); break;
+      case 8: o.f("        const uint2 %s0 = ld8(gp);", name); break;
+      case 4: o.f("        const u32 %s0 = ld4(gp);", name); break;
+      default: o.f("        const u32 %s0 = ld2(gp);", name); break;
     }
   }
-  // advance (row, col) of this lane's vector by one sweep iteration (KA_TPB vectors of pv elements)
+  // advance (row, col) of this thread's vector by one sweep iteration (KA_TPB vectors of pv elements)
   void coop_step(int pv) {
     o.f("      col += (KA_TPB * %d) %% KA_C; row += (KA_TPB * %d) / KA_C;", pv, pv);
     o.f("      if (col >= KA_C) { col -= KA_C; ++row; }");
   }
 
+  // ---- the straight-line code of one warp of the team for one row ----
+  void emit_part(int w) {
+    const int C = t.C, W = team.W;
+    part = w; top = false; acc = 0; since = 0; last.clear(); base = "xsb";
+    const std::vector<int>& cuts = team.cuts_of_part[w];
+    std::vector<int> own;  // own leaves, DFS order
+    for (int k : cuts)
+      for (int pos = t.beg[team.cut_nodes[k]]; pos < t.end[team.cut_nodes[k]]; ++pos) own.push_back(t.leaf_at[pos]);
+    const bool first = w == 0;
+    o.f("// warp %d of %d: %d cut subtrees, %d leaves%s", w, W, (int)cuts.size(), (int)own.size(), first && teamed() ? " + the top tree" : "");
+    o.f("KA_DEV void ka_part%d(const KAParams& p, long long yy, bool live, KA_XSB xsb, u32 zr, float& loss_acc) {", w);
+    if (loss_mode()) {
+      // rows with an out-of-range target are ignored: zero loss, zero gradient (nn.CrossEntropyLoss's ignore_index rows; the
+      // reference's class_index_to_child_index has no entry for them either).  They run the arithmetic on target 0 and are
+      // masked at the two places where a row has an effect.
+      o.f("    const bool valid = (unsigned long long)yy < %dull;", C);
+      o.f("    const int y = valid ? (int)(unsigned)yy : 0;");
+      o.f("    const int posy = ka_pos[y];");
+      o.f("    const float kx = p.w_xent * p.inv_rows, kt = p.w_tree * p.inv_rows;");
+      if (first) o.f("    KA_LDX_DYN(xy, y);");
+      // max over the own leaves
+      o.f("    float m0 = -3.0e38f, m1 = m0, m2 = m0, m3 = m0;");
+      for (size_t i = 0; i < own.size(); ++i) {
+        const std::string xv = ldx(own[i]);
+        o.f("    m%d = fmaxf(m%d, %s);", (int)(i & 3), (int)(i & 3), xv.c_str());
+      }
+      o.f("    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));");
+      o.f("    const float nm = -mx * kLog2e;");
+      o.f("    float zx0 = 0.f, zx1 = 0.f, zx2 = 0.f, zx3 = 0.f;");
+    }
+    // ---- pass 1 over the own subtrees ----
+    declare_kary();
+    for (int k : cuts) {
+      const int r = team.cut_nodes[k];
+      up(r);
+      if (teamed()) stx(ex_p(k), "s" + std::to_string(r));
+    }
+    if (loss_mode()) {
+      o.f("    const float zxw = (zx0 + zx1) + (zx2 + zx3);");
+      if (teamed()) { stx(ex_w(0, w), "mx"); stx(ex_w(1, w), "zxw"); }
+    }
+    o.f("    KA_BAR();");
+    // ---- the whole row's log-sum-exp from the warps' (max, sum) pairs ----
+    if (loss_mode()) {
+      if (teamed()) {
+        std::vector<std::string> ms, zs;
+        for (int u = 0; u < W; ++u) { ms.push_back(ldx(ex_w(0, u))); zs.push_back(ldx(ex_w(1, u))); }
+        std::string mg = ms[0];
+        for (int u = 1; u < W; ++u) mg = "fmaxf(" + mg + ", " + ms[u] + ")";
+        o.f("    const float mxg = %s;", mg.c_str());
+        o.f("    float zxg = 0.f;");
+        for (int u = 0; u < W; ++u) o.f("    zxg = fmaf(%s, ex2((%s - mxg) * kLog2e), zxg);", zs[u].c_str(), ms[u].c_str());
+      } else {
+        o.f("    const float mxg = mx, zxg = zxw;");
+      }
+      o.f("    const float l2zx = lg2(zxg);");
+      o.f("    const float lse1 = fmaf(l2zx, kLn2, mxg);");
+      o.f("    const float cx = kx * p.grad_scale;");
+      o.f("    const float nl = -fmaf(mxg, kLog2e, l2zx);");
+    }
+    // ---- top tree, pass 1 and the way down (warp 0) ----
+    if (teamed()) {
+      if (first) {
+        top = true;
+        up(t.root);
+        if (v.mode == kSpecHardLoss) {
+          o.f("    float lp = 0.f;");
+          o.f("    const float nkg = -kt * p.grad_scale;");
+          hard(t.root, "", "");
+        } else {
+          down(t.root, "", "T", 0);
+        }
+        top = false;
+      }
+      o.f("    KA_BAR();");
+    }
+    // ---- own subtrees ----
+    if (v.mode == kSpecSoftFwd) {
+      for (int k : cuts) {
+        const int r = team.cut_nodes[k];
+        std::string P = teamed() ? ldx(ex_p(k)) : "";
+        if (teamed()) { o.f("    const float P%d = %s;", r, P.c_str()); P = "P" + std::to_string(r); }
+        if (leaf(r)) { if (!teamed()) o.f("    const float P%d = 1.f;", r); leaf_prob(r, "P", 0); }
+        else down(r, P, "P", 0);
+      }
+      o.f("}");
+      return;
+    }
+    if (v.mode == kSpecHardLoss) {
+      if (!teamed()) {
+        o.f("    float lp = 0.f;");
+        o.f("    const float nkg = -kt * p.grad_scale;");
+        hard(t.root, "", "");
+      } else {
+        if (!first) { o.f("    float lp = 0.f;"); o.f("    const float nkg = -kt * p.grad_scale;"); }
+        for (int k : cuts) {
+          const int r = team.cut_nodes[k];
+          const std::string on = ldx(ex_p(k)), A = ldx(ex_h(k));
+          o.f("    const float on%d = %s; const float A%d = %s;", r, on.c_str(), r, A.c_str());
+          if (leaf(r)) leaf_out(r, "A" + std::to_string(r));
+          else hard(r, "on" + std::to_string(r), "A" + std::to_string(r));
+        }
+        stx(ex_w(3, w), "lp");
+        o.f("    KA_BAR();");
+        if (first) {
+          std::string s = "0.f";
+          for (int u = 0; u < W; ++u) s += " + " + ldx(ex_w(3, u));
+          o.f("    const float lpg = %s;", s.c_str());
+        }
+      }
+      if (first) o.f("    if (live && valid) loss_acc += kx * (lse1 - xy) + kt * kLn2 * %s;", teamed() ? "lpg" : "lp");
+    } else {
+      // soft loss: sum exp(P) and P[target] over the own leaves
+      o.f("    float z20 = 0.f, z21 = 0.f, z22 = 0.f, z23 = 0.f, pry = 0.f;");
+      acc = 0;
+      std::vector<std::string> Pr(cuts.size());
+      for (size_t i = 0; i < cuts.size(); ++i) {
+        const int k = cuts[i], r = team.cut_nodes[k];
+        if (teamed()) { Pr[i] = ldx(ex_p(k)); o.f("    const float P%d = %s;", r, Pr[i].c_str()); Pr[i] = "P" + std::to_string(r); }
+        if (leaf(r)) { if (!teamed()) o.f("    const float P%d = 1.f;", r); leaf_prob(r, "P", 1); }
+        else down(r, Pr[i], "P", 1);
+      }
+      o.f("    const float Zw = (z20 + z21) + (z22 + z23);");
+      if (teamed()) {
+        stx(ex_w(2, w), "Zw"); stx(ex_w(3, w), "pry");
+        o.f("    KA_BAR();");
+        std::string sz = "0.f", sp = "0.f";
+        for (int u = 0; u < W; ++u) { sz += " + " + ldx(ex_w(2, u)); sp += " + " + ldx(ex_w(3, u)); }
+        o.f("    const float Z = %s; const float pryg = %s;", sz.c_str(), sp.c_str());
+      } else {
+        o.f("    const float Z = Zw, pryg = pry;");
+      }
+      if (first) o.f("    if (live && valid) loss_acc += kx * (lse1 - xy) + kt * (kLn2 * lg2(Z) - pryg);");
+      o.f("    const float cA = kt * p.grad_scale * rcp(Z);");
+      // the merged down/up traversal of the own subtrees
+      for (size_t i = 0; i < cuts.size(); ++i) {
+        const int k = cuts[i], r = team.cut_nodes[k];
+        std::string Q = teamed() ? "Q" + std::to_string(r) : "";
+        if (teamed()) o.f("    float Q%d = %s; KA_OPAQUE(Q%d);", r, Pr[i].c_str(), r);
+        std::string H;
+        if (leaf(r)) { if (!teamed()) o.f("    const float Q%d = 1.f;", r); H = leaf_g(r, "Q" + std::to_string(r)); }
+        else H = updown(r, Q);
+        if (teamed()) stx(ex_h(k), H);
+      }
+      if (teamed()) {
+        o.f("    KA_BAR();");
+        if (first) {  // top tree: sums up, gradient down to the cut roots
+          top = true;
+          top_h(t.root);
+          back(t.root, "");
+          top = false;
+        }
+        o.f("    KA_BAR();");
+      }
+      for (int k : cuts) {
+        const int r = team.cut_nodes[k];
+        std::string A = "";
+        if (teamed()) { A = ldx(ex_h(k)); o.f("    const float A%d = %s;", r, A.c_str()); A = "A" + std::to_string(r); }
+        if (leaf(r)) leaf_out(r, A.empty() ? "0.f" : A);
+        else back(r, A);
+      }
+    }
+    // the slots of the own leaves now hold dL/dx except for the one-hot of the plain cross-entropy term
+    if (teamed()) o.f("    if (ka_owner[y] == %d) KA_ADDX_DYN(y, -cx);", w);
+    else o.f("    KA_ADDX_DYN(y, -cx);");
+    o.f("    if (!valid) {");
+    for (int c : own) o.f("      KA_STX(xsb, %d, %d, 0.f);", c, soff(c));
+    o.f("    }");
+    o.f("}");
+  }
+
   std::string run() {
-    const int C = t.C;
+    const int C = t.C, W = team.W;
     const int pv = per_vec();
-    o.s.reserve((size_t)C * 2200);
-    o.f("#define KA_C %d", C);
+    o.s.reserve((size_t)C * 2600);
     U = v.mode == kSpecSoftFwd ? std::min(pv, v.ovec / 4) : pv;
     K = ((C / U) & 31) | 1;
-    o.f("#ifdef KA_HOST\n#define KA_TPB 1\n#else\n#define KA_TPB %d\n#endif\n#define KA_U %du\n#define KA_K %du", kTPB, U, K);
+    o.f("#define KA_C %d\n#define KA_W %d", C, W);
+    o.f("#ifdef KA_HOST\n#define KA_TPB 1\n#else\n#define KA_TPB %d\n#endif\n#define KA_U %du\n#define KA_K %du", kTPB * W, U, K);
     o.s += kPrelude;
-    if (loss_mode()) {
+    auto table = [&](const char* type, const char* name, const std::vector<int>& vals) {
       std::string tab;
-      for (int c = 0; c < C; ++c) tab += std::to_string(t.pos[c]) + (c + 1 < C ? "," : "");
-      o.f("#ifdef KA_HOST\nstatic const unsigned short ka_pos[KA_C] = {%s};\n#else\n__device__ const unsigned short ka_pos[KA_C] = {%s};\n#endif", tab.c_str(), tab.c_str());
+      for (size_t c = 0; c < vals.size(); ++c) tab += std::to_string(vals[c]) + (c + 1 < vals.size() ? "," : "");
+      o.f("#ifdef KA_HOST\nstatic const %s %s[%d] = {%s};\n#else\n__device__ const %s %s[%d] = {%s};\n#endif", type, name, (int)vals.size(),
+          tab.c_str(), type, name, (int)vals.size(), tab.c_str());
+    };
+    if (loss_mode()) {
+      table("unsigned short", "ka_pos", t.pos);
+      if (teamed()) {
+        std::vector<int> owner(C);
+        for (int c = 0; c < C; ++c) owner[c] = team.part_of_node[c];
+        table("unsigned char", "ka_owner", owner);
+      }
     }
-    o.f("// hierarchy %016llx: %d leaves, %d inner nodes; mode %d dtype %d vec %d; %d node values (%d in shared memory)",
-        t.hash, C, t.N, v.mode, v.dtype, v.vec, plan.nvalues, plan.nspill);
+    o.f("// hierarchy %016llx: %d leaves, %d inner nodes; mode %d dtype %d vec %d; %d node values; %d warps per row block, %d cut subtrees, %d top nodes",
+        t.hash, C, t.N, v.mode, v.dtype, v.vec, plan.nvalues, W, team.ncut(), team.ntop);
 
     // ---- sweep A: the block's rows, coalesced, into the transposed slots ----
-    o.f("KA_DEV void ka_sweep_a(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int lane) {");
+    o.f("KA_DEV void ka_sweep_a(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int tid) {");
     o.f("    const char* xb = reinterpret_cast<const char*>(p.x) + row0 * p.ld * %d;", esz());
-    o.f("    int row = (lane * %d) / KA_C, col = (lane * %d) %% KA_C;", pv, pv);
-    const int nit = C / pv;  // vectors per lane and block
+    o.f("    int row = (tid * %d) / KA_C, col = (tid * %d) %% KA_C;", pv, pv);
+    const int nvecs = 32 * C / pv;                          // vectors per block
+    const int nit = (nvecs + kTPB * W - 1) / (kTPB * W);    // per thread
     // full block of contiguous rows (the common case): every load has an immediate offset from one pointer and a whole group
     // of loads is in flight before the first store needs its data
     o.f("#ifndef KA_HOST");
-    o.f("    if (nrows == KA_TPB && p.ld == KA_C) {");
-    o.f("      const char* gp = xb + lane * %d;", v.vec);
+    o.f("    if (nrows == 32 && p.ld == KA_C) {");
+    o.f("      const char* gp = xb + tid * %d;", v.vec);
     const int maxld = std::max(1, plan.knobs.maxld * 16 / v.vec);
     for (int g0 = 0; g0 < nit; g0 += maxld) {
       const int g1 = std::min(nit, g0 + maxld);
       for (int it = g0; it < g1; ++it) {
-        switch (v.vec) {
-          case 16: o.f("      const uint4 lv%d = ld16(gp + %d);", it, it * kTPB * v.vec); break;
-          case 8: o.f("      const uint2 lv%d = ld8(gp + %d);", it, it * kTPB * v.vec); break;
-          case 4: o.f("      const u32 lv%d = ld4(gp + %d);", it, it * kTPB * v.vec); break;
-          default: o.f("      const u32 lv%d = ld2(gp + %d);", it, it * kTPB * v.vec); break;
-        }
+        const bool guard = (it + 1) * kTPB * W > nvecs;  // the last iteration may run past the block
+        const char* ty = v.vec == 16 ? "uint4" : (v.vec == 8 ? "uint2" : "u32");
+        const char* zero = v.vec == 16 ? "make_uint4(0u, 0u, 0u, 0u)" : (v.vec == 8 ? "make_uint2(0u, 0u)" : "0u");
+        if (guard) o.f("      const %s lv%d = (tid + %d < %d) ? ld%d(gp + %d) : %s;", ty, it, it * kTPB * W, nvecs, v.vec, it * kTPB * W * v.vec, zero);
+        else o.f("      const %s lv%d = ld%d(gp + %d);", ty, it, v.vec, it * kTPB * W * v.vec);
       }
       for (int it = g0; it < g1; ++it) {
-        o.f("      { const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);");
+        const bool guard = (it + 1) * kTPB * W > nvecs;
+        o.f("      %s{ const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);", guard ? "if (row < 32) " : "");
         for (int j = 0; j < pv; ++j) o.f("        KA_STD(a, %d, %d, %s);", j, eoff(j), elem("lv", it * pv + j).c_str());
         o.f("      }");
         coop_step(pv);
@@ -693,10 +940,11 @@ struct Gen {
     o.f("    }");
     o.f("#endif");
     if (plan.knobs.unroll > 0) o.f("#pragma unroll %d", plan.knobs.unroll); else o.f("#pragma unroll");
-    o.f("    for (int it = 0; it < %d; ++it) {", nit);
+    o.f("#ifdef KA_HOST\n    const int nit = %d;\n#else\n    const int nit = %d;\n#endif", C / pv, nit);
+    o.f("    for (int it = 0; it < nit; ++it) {");
     o.f("      if (row < nrows) {");
     o.f("        const char* gp = xb + ((long long)row * p.ld + col) * %d;", esz());
-    coop_load("lv", false);
+    coop_load("lv");
     o.f("        const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);");
     for (int j = 0; j < pv; ++j) o.f("        KA_STD(a, %d, %d, %s);", j, eoff(j), elem("lv", j).c_str());
     o.f("      }");
@@ -704,88 +952,40 @@ struct Gen {
     o.f("    }");
     o.f("}");
 
-    // ---- the row function: one thread, one row, straight-line ----
-    o.f("KA_DEV void ka_row(const KAParams& p, long long row, long long yy, KA_XSB xsb, u32 zr, float& loss_acc) {");
-    if (loss_mode()) {
-      // rows with an out-of-range target are ignored: zero loss, zero gradient (nn.CrossEntropyLoss's ignore_index
-      // rows; the reference's class_index_to_child_index has no entry for them either)
-      o.f("    if ((unsigned long long)yy >= %dull) {", C);
-      o.f("      for (int c = 0; c < KA_C; ++c) KA_STX_DYN(c, 0.f);");
-      o.f("      return;");
-      o.f("    }");
-      o.f("    const int y = (int)(unsigned)yy;");
-      o.f("    const int posy = ka_pos[y];");
-      o.f("    const float kx = p.w_xent * p.inv_rows, kt = p.w_tree * p.inv_rows;");
-      // max of the row (thread-private sweep over the slots)
-      o.f("    float m0 = -3.0e38f, m1 = m0, m2 = m0, m3 = m0;");
-      for (int c = 0; c < C; ++c) {
-        const std::string xv = ldx(c);
-        o.f("    m%d = fmaxf(m%d, %s);", c & 3, c & 3, xv.c_str());
-      }
-      o.f("    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));");
-      o.f("    const float nm = -mx * kLog2e;");
-      o.f("    float zx0 = 0.f, zx1 = 0.f, zx2 = 0.f, zx3 = 0.f;");
-      o.f("    KA_LDX_DYN(xy, y);");
-    }
-    // ---- pass 1 ----
-    declare_kary();
-    acc = 0;
-    up(t.root);
-    if (loss_mode()) {
-      o.f("    const float l2zx = lg2((zx0 + zx1) + (zx2 + zx3));");
-      o.f("    const float lse1 = fmaf(l2zx, kLn2, mx);");
-    }
-    if (v.mode == kSpecSoftFwd) {
-      acc = 0;
-      down(t.root, "", "P", 0);
-      o.f("}");
-    } else {
-      o.f("    const float cx = kx * p.grad_scale;");
-      o.f("    const float nl = -fmaf(mx, kLog2e, l2zx);");
-      if (v.mode == kSpecSoftLoss) {
-        o.f("    float z20 = 0.f, z21 = 0.f, z22 = 0.f, z23 = 0.f, pry = 0.f;");
-        acc = 0;
-        down(t.root, "", "P", 1);
-        o.f("    const float Z = (z20 + z21) + (z22 + z23);");
-        o.f("    loss_acc += kx * (lse1 - xy) + kt * (kLn2 * lg2(Z) - pry);");
-        o.f("    if (!p.grad) return;");
-        o.f("    const float cA = kt * p.grad_scale * rcp(Z);");
-        updown(t.root, "");
-        back(t.root, "");
-      } else {
-        o.f("    float lp = 0.f;");
-        o.f("    const float nkg = -kt * p.grad_scale;");
-        hard(t.root, "", "");
-        o.f("    loss_acc += kx * (lse1 - xy) + kt * kLn2 * lp;");
-        o.f("    if (!p.grad) return;");
-      }
-      // the slots now hold dL/dx except for the one-hot of the plain cross-entropy term
-      o.f("    KA_ADDX_DYN(y, -cx);");
-      o.f("}");
-    }
+    // ---- the row code, one function per warp of the team ----
+    for (int w = 0; w < W; ++w) emit_part(w);
+    o.f("#ifdef KA_HOST");
+    o.f("static void ka_part(int w, const KAParams& p, long long yy, bool live, KA_XSB xsb, u32 zr, float& loss_acc) {");
+    o.f("  switch (w) {");
+    for (int w = 0; w < W; ++w) o.f("    case %d: ka_part%d(p, yy, live, xsb, zr, loss_acc); break;", w, w);
+    o.f("  }");
+    o.f("}");
+    o.f("#endif");
 
     // ---- sweep B: coalesced write of the block's gradient rows / class probabilities (the slots hold the final values) ----
-    o.f("KA_DEV void ka_sweep_b(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int lane) {");
+    o.f("KA_DEV void ka_sweep_b(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int tid) {");
     {
       const bool fwd = v.mode == kSpecSoftFwd;
       const int ov = fwd ? v.ovec : v.vec;          // bytes per output vector
       const int po = fwd ? v.ovec / 4 : pv;         // elements per output vector
       const int oesz = fwd ? 4 : esz();
-      const int nito = C / po;
+      const int nvo = 32 * C / po;
+      const int nito = (nvo + kTPB * W - 1) / (kTPB * W);
       if (fwd) o.f("    char* ob = reinterpret_cast<char*>(p.class_probs + row0 * KA_C); const long long old = KA_C;");
       else o.f("    char* ob = reinterpret_cast<char*>(p.grad) + row0 * p.ld * %d; const long long old = p.ld;", oesz);
-      o.f("    int row = (lane * %d) / KA_C, col = (lane * %d) %% KA_C;", po, po);
+      o.f("    int row = (tid * %d) / KA_C, col = (tid * %d) %% KA_C;", po, po);
       o.f("#ifndef KA_HOST");
-      o.f("    if (nrows == KA_TPB && old == KA_C) {");
-      o.f("      char* op = ob + lane * %d;", ov);
+      o.f("    if (nrows == 32 && old == KA_C) {");
+      o.f("      char* op = ob + tid * %d;", ov);
       for (int it = 0; it < nito; ++it) {
-        o.f("      { const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);");
+        const bool guard = (it + 1) * kTPB * W > nvo;
+        o.f("      %s{ const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);", guard ? "if (row < 32) " : "");
         std::vector<std::string> vals;
         for (int j = 0; j < po; ++j) {
           o.f("        KA_LDD(q%d, a, %d, %d);", j, j, eoff(j));
           vals.push_back("q" + std::to_string(j));
         }
-        store_out("    op", it * kTPB, ov, fwd || v.dtype == NBDT_F32, vals);
+        store_out("    op", it * kTPB * W, ov, fwd || v.dtype == NBDT_F32, vals);
         o.f("      }");
         coop_step(po);
       }
@@ -793,7 +993,8 @@ struct Gen {
       o.f("    }");
       o.f("#endif");
       if (plan.knobs.unroll > 0) o.f("#pragma unroll %d", plan.knobs.unroll); else o.f("#pragma unroll");
-      o.f("    for (int it = 0; it < %d; ++it) {", nito);
+      o.f("#ifdef KA_HOST\n    const int nit = %d;\n#else\n    const int nit = %d;\n#endif", C / po, nito);
+      o.f("    for (int it = 0; it < nit; ++it) {");
       o.f("      if (row < nrows) {");
       o.f("        const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);");
       std::vector<std::string> vals;
@@ -809,42 +1010,51 @@ struct Gen {
     }
     o.f("}");
 
-    // ---- kernel: one warp per CTA, 32 rows per iteration ----
+    // ---- kernel: one team per CTA, 32 rows per iteration ----
     o.f("#ifndef KA_HOST");
     o.f("extern \"C\" __global__ void __launch_bounds__(KA_TPB, %d) nbdt_tree_ka(const KAParams p) {", plan.min_blocks);
     o.f("  extern __shared__ float ka_smem[];");
-    o.f("  const int lane = threadIdx.x;");
+    o.f("  const int tid = threadIdx.x, lane = tid & 31;");
     o.f("  const u32 xsw = (u32)__cvta_generic_to_shared(ka_smem);");
     o.f("  const u32 xsb = xsw + ((lane * KA_K) & 31u) * 4u;");
     o.f("  float loss_acc = 0.f;");
     o.f("  const u32 zr = (u32)((unsigned long long)p.B >> 48);  // zero at run time, unknown at compile time (scheduling fences)");
-    o.f("  for (long long row0 = (long long)blockIdx.x * KA_TPB; row0 < p.B; row0 += (long long)gridDim.x * KA_TPB) {");
-    o.f("    const int nrows = (int)(p.B - row0 < KA_TPB ? p.B - row0 : KA_TPB);");
+    o.f("  for (long long row0 = (long long)blockIdx.x * 32; row0 < p.B; row0 += (long long)gridDim.x * 32) {");
+    o.f("    const int nrows = (int)(p.B - row0 < 32 ? p.B - row0 : 32);");
     o.f("    long long yy = 0;");
     if (loss_mode()) o.f("    if (lane < nrows) yy = p.targets[row0 + lane];");
     if (plan.knobs.prefetch > 0) {
       // the lines of a block further ahead go to L2 now, so that its sweep A pays an L2 hit instead of an HBM access
       o.f("    {");
-      o.f("      const long long pr0 = row0 + %dll * gridDim.x * KA_TPB;", plan.knobs.prefetch);
+      o.f("      const long long pr0 = row0 + %dll * gridDim.x * 32;", plan.knobs.prefetch);
       o.f("      if (pr0 < p.B && p.ld <= 2 * KA_C) {");
-      o.f("        const long long pn = p.B - pr0 < KA_TPB ? p.B - pr0 : KA_TPB;");
+      o.f("        const long long pn = p.B - pr0 < 32 ? p.B - pr0 : 32;");
       o.f("        const char* pb = reinterpret_cast<const char*>(p.x) + pr0 * p.ld * %d;", esz());
       o.f("        const long long plen = ((pn - 1) * p.ld + KA_C) * %d;", esz());
-      o.f("        for (long long po = lane * 128; po < plen; po += KA_TPB * 128) asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(pb + po));");
+      o.f("        for (long long po = tid * 128; po < plen; po += KA_TPB * 128) asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(pb + po));");
       o.f("      }");
       o.f("    }");
     }
-    o.f("    ka_sweep_a(p, row0, nrows, xsw, lane);");
-    o.f("    __syncwarp();");
-    o.f("    if (lane < nrows) ka_row(p, row0 + lane, yy, xsb, zr, loss_acc);");
-    o.f("    __syncwarp();");
-    if (loss_mode()) o.f("    if (p.grad) ka_sweep_b(p, row0, nrows, xsw, lane);");
-    else o.f("    ka_sweep_b(p, row0, nrows, xsw, lane);");
-    o.f("    __syncwarp();");
+    o.f("    ka_sweep_a(p, row0, nrows, xsw, tid);");
+    o.f("    %s;", W > 1 ? "__syncthreads()" : "__syncwarp()");
+    if (W > 1) {
+      o.f("    switch (tid >> 5) {");
+      for (int w = 0; w < W; ++w) o.f("      case %d: ka_part%d(p, yy, lane < nrows, xsb, zr, loss_acc); break;", w, w);
+      o.f("    }");
+    } else {
+      // a single warp has no barriers inside the row function: threads without a row skip it
+      o.f("    if (lane < nrows) ka_part0(p, yy, true, xsb, zr, loss_acc);");
+    }
+    o.f("    %s;", W > 1 ? "__syncthreads()" : "__syncwarp()");
+    if (loss_mode()) o.f("    if (p.grad) ka_sweep_b(p, row0, nrows, xsw, tid);");
+    else o.f("    ka_sweep_b(p, row0, nrows, xsw, tid);");
+    o.f("    %s;", W > 1 ? "__syncthreads()" : "__syncwarp()");
     o.f("  }");
     if (loss_mode()) {
-      o.f("  for (int s = 16; s > 0; s >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, s);");
-      o.f("  if (lane == 0) atomicAdd(p.loss, loss_acc);");
+      o.f("  if (tid < 32) {");
+      o.f("    for (int s = 16; s > 0; s >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, s);");
+      o.f("    if (tid == 0) atomicAdd(p.loss, loss_acc);");
+      o.f("  }");
     }
     o.f("}");
     o.f("#endif");
@@ -852,11 +1062,81 @@ struct Gen {
   }
 };
 
+// cut the hierarchy for a team of W warps
+Team make_team(const KTree& t, int W) {
+  Team tm;
+  tm.W = std::max(1, W);
+  tm.cut_id.assign(t.NV, -1);
+  tm.part_of_node.assign(t.NV, 0);
+  tm.is_top.assign(t.NV, 0);
+  if (tm.W == 1) {
+    tm.cut_id[t.root] = 0;
+    tm.cut_nodes.push_back(t.root);
+    tm.part_of_cut.push_back(0);
+    tm.cuts_of_part.assign(1, std::vector<int>(1, 0));
+    return tm;
+  }
+  const int limit = std::max(1, (t.C + 2 * tm.W - 1) / (2 * tm.W));  // leaves per cut subtree at most
+  std::vector<int> st(1, t.root);
+  while (!st.empty()) {  // DFS, children pushed in reverse so that cut subtrees come out in DFS order
+    const int n = st.back();
+    st.pop_back();
+    if (t.cnt[n] <= limit || n < t.C) {
+      tm.cut_id[n] = (int)tm.cut_nodes.size();
+      tm.cut_nodes.push_back(n);
+      continue;
+    }
+    tm.is_top[n] = 1;
+    ++tm.ntop;
+    const std::vector<int>& c = t.ch[n - t.C];
+    for (size_t k = c.size(); k-- > 0;) st.push_back(c[k]);
+  }
+  // longest-processing-time packing; warp 0 starts with the top tree on its account
+  std::vector<int> order(tm.cut_nodes.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return t.cnt[tm.cut_nodes[a]] > t.cnt[tm.cut_nodes[b]]; });
+  std::vector<int> load(tm.W, 0);
+  load[0] = tm.ntop;
+  tm.part_of_cut.assign(tm.cut_nodes.size(), 0);
+  for (int k : order) {
+    int best = 0;
+    for (int w = 1; w < tm.W; ++w) if (load[w] < load[best]) best = w;
+    tm.part_of_cut[k] = best;
+    load[best] += t.cnt[tm.cut_nodes[k]];
+  }
+  tm.cuts_of_part.assign(tm.W, std::vector<int>());
+  for (size_t k = 0; k < tm.cut_nodes.size(); ++k) tm.cuts_of_part[tm.part_of_cut[k]].push_back((int)k);
+  // owner of every node
+  for (size_t k = 0; k < tm.cut_nodes.size(); ++k) {
+    std::vector<int> q(1, tm.cut_nodes[k]);
+    while (!q.empty()) {
+      const int n = q.back();
+      q.pop_back();
+      tm.part_of_node[n] = tm.part_of_cut[k];
+      if (n >= t.C) for (int c : t.ch[n - t.C]) q.push_back(c);
+    }
+  }
+  return tm;
+}
+
+int auto_warps(const KTree& t) {
+  // measured on B200 (gpurun_out/tune_v5.jsonl): one warp per row block is fastest up to ~128 leaves (12 resident warps
+  // per SM); at 200 leaves one warp needs 255 registers and 30 KB (7 warps per SM) and a team of 4 wins
+  if (t.C <= 128) return 1;
+  if (t.C <= 256) return 4;
+  int w = 4;
+  while (w < 16 && t.C > 64 * w) w *= 2;
+  return w;
+}
+
 Plan make_plan(const KTree& t, int max_smem, const Knobs& knobs) {
   Plan p;
   p.knobs = knobs;
+  p.team = make_team(t, knobs.warps > 0 ? knobs.warps : auto_warps(t));
+  const int W = p.team.W;
+  p.threads = kTPB * W;
   p.value_slot.assign(t.NV, -1);
-  // values in post-order (the order pass 1 produces them): the first kRegValueCap stay in registers
+  // values in post-order (the order pass 1 produces them)
   std::vector<int> order;  // inner nodes, post-order
   {
     struct Frame { int v; size_t k; };
@@ -870,16 +1150,28 @@ Plan make_plan(const KTree& t, int max_smem, const Knobs& knobs) {
       if (u >= t.C) st.push_back({u, 0});
     }
   }
+  // register budget per thread: what a full SM of resident teams allows, minus the working set of the passes
+  const int regcap = W == 1 ? knobs.regcap : std::min(knobs.regcap, std::max(16, 65536 / (kTPB * W) - 72));
+  std::vector<int> in_regs(W, 0), nspill(W, 0);
   for (int n : order) {
     const size_t k = t.ch[n - t.C].size();
     if (k <= 1) continue;
     p.value_slot[n] = p.nvalues;
-    p.nvalues += k == 2 ? 1 : (int)k;
+    const int cnt = k == 2 ? 1 : (int)k;
+    const int w = p.team.part_of_node[n];
+    for (int j = 0; j < cnt; ++j) {
+      p.value_part.push_back(w);
+      if (in_regs[w] < regcap) { ++in_regs[w]; p.value_spill.push_back(-1); }
+      else p.value_spill.push_back(nspill[w]++);
+    }
+    p.nvalues += cnt;
   }
-  p.nspill = std::max(0, p.nvalues - knobs.regcap);
-  p.smem_bytes = (t.C * 32 + t.C + 36 + p.nspill * 32) * 4;
-  const int regs = std::min(255, ((p.nvalues - p.nspill) + 64 + 7) / 8 * 8);
-  int by_regs = 65536 / (kTPB * regs);
+  int maxregs = 0;
+  for (int w = 0; w < W; ++w) { p.maxspill = std::max(p.maxspill, nspill[w]); maxregs = std::max(maxregs, in_regs[w]); }
+  const int slots = t.C + W * p.maxspill + 2 * p.team.ncut() + 4 * W;
+  p.smem_bytes = (t.C * 32 + t.C + 36 + (slots - t.C) * 32) * 4;
+  const int regs = std::min(255, (maxregs + 64 + 7) / 8 * 8);
+  int by_regs = 65536 / (kTPB * W * regs);
   int by_smem = (max_smem > 0 ? max_smem : 227 * 1024) / std::max(1, p.smem_bytes + 1024);
   p.min_blocks = std::max(1, std::min(32, std::min(by_regs, by_smem)));
   if (knobs.minb > 0) p.min_blocks = knobs.minb;
@@ -1006,7 +1298,7 @@ std::vector<std::string> cache_read_dirs() {
 std::string variant_name(const KTree& t, const Variant& v, const Knobs& k) {
   char b[192];
   int n = snprintf(b, sizeof b, "ka%d_%016llx_m%d_t%d_v%d_o%d", kGeneratorVersion, t.hash, v.mode, v.dtype, v.vec, v.ovec);
-  if (!k.is_default()) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence);
+  if (!k.is_default()) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d_w%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence, k.warps);
   return b;
 }
 
@@ -1150,7 +1442,7 @@ int tree_jit_launch(TreeJit* t, int mode, int dtype, const SpecParams& p, void* 
         e = cudaFuncSetAttribute((const void*)L->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, t->plan.smem_bytes);
       if (e == cudaSuccess) {
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)L->kern, kTPB, t->plan.smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)L->kern, t->plan.threads, t->plan.smem_bytes);
         L->blocks_per_sm = std::max(1, nb);
       }
       if (e != cudaSuccess) {
@@ -1163,12 +1455,12 @@ int tree_jit_launch(TreeJit* t, int mode, int dtype, const SpecParams& p, void* 
     }
     t->last_variant = variant_name(t->tree, v, t->plan.knobs);
   }
-  long long grid = (p.B + kTPB - 1) / kTPB;
+  long long grid = (p.B + 31) / 32;
   grid = std::min<long long>(grid, (long long)t->sm_count * L->blocks_per_sm);
   if (grid < 1) grid = 1;
   SpecParams sp = p;
   void* args[1] = {&sp};
-  NBDT_CUDA_OK(cudaLaunchKernel((const void*)L->kern, dim3((unsigned)grid), dim3(kTPB), args, (size_t)t->plan.smem_bytes, (cudaStream_t)stream));
+  NBDT_CUDA_OK(cudaLaunchKernel((const void*)L->kern, dim3((unsigned)grid), dim3(t->plan.threads), args, (size_t)t->plan.smem_bytes, (cudaStream_t)stream));
   return NBDT_OK;
 }
 

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
     }
     float lse1 = 0.f, inv_s1 = 0.f, xy = 0.f;
     int y = 0, pos_y = 0;
+    bool ign = false;  // target outside [0, C): the row is ignored (zero loss, zero gradient), like nn.CrossEntropyLoss's ignore_index
     if (MODE != kSpecSoftFwd) {
       m1 = group_max<G>(m1);
       const float nm = -m1 * kLog2e;
@@ -189,7 +190,9 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
       lse1 = fmaf(lg2(s1), kLn2, m1);
       inv_s1 = rcp(s1);
       if (valid) {
-        y = (int)p.targets[row];
+        const long long yy = p.targets[row];
+        ign = (unsigned long long)yy >= (unsigned long long)C;
+        y = ign ? 0 : (int)yy;
         xy = to_f<T>(xr[y]);
       }
       pos_y = __ldg(t.class_pos + y);
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
       const float lpy = P_(__ldg(t.class_edge + y));
       row_loss = kx * (lse1 - xy) - kt * kLn2 * lpy;
     }
-    if (j == 0 && valid) loss_acc += row_loss;
+    if (j == 0 && valid && !ign) loss_acc += row_loss;
     if (gout == nullptr) {
       __syncwarp();
       continue;
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(256, 3) tree_v2_kernel(const V2Params q) {
     for (int k = 0; k < EPT; ++k) {
       const int c = j + k * G;
       if (c < C && valid)
-        gout[row * p.ld + c] = from_f<T>(fmaf(kgx, fmaf(ev[k], inv_s1, c == y ? -1.f : 0.f), P_(__ldg(t.class_edge + c))));
+        gout[row * p.ld + c] = from_f<T>(ign ? 0.f : fmaf(kgx, fmaf(ev[k], inv_s1, c == y ? -1.f : 0.f), P_(__ldg(t.class_edge + c))));
     }
     __syncwarp();
   }

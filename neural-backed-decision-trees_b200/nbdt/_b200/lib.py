@@ -37,6 +37,9 @@ SIGNATURES = {
     "nbdt_tree_destroy": (None, [c_ptr]),
     "nbdt_tree_max_depth": (ctypes.c_int, [c_ptr]),
     "nbdt_tree_num_slots": (ctypes.c_int, [c_ptr]),
+    "nbdt_tree_kernel_variant": (ctypes.c_char_p, [c_ptr]),
+    "nbdt_tree_jit_source": (ctypes.c_longlong, [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_longlong]),
+    "nbdt_tree_jit_precompile": (ctypes.c_int, [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.c_int]),
     "nbdt_soft_forward": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_i64, c_i64, c_ptr, c_ptr]),
     "nbdt_soft_backward": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_i64, c_i64, c_ptr, c_f32, c_ptr, c_ptr]),
     "nbdt_hard_forward": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

@@ -12,16 +12,21 @@ import torch  # noqa: E402
 from bench_tree import peaks, time_point  # noqa: E402
 from nbdt.tree import Tree  # noqa: E402
 
-KNOBS = ["NBDT_B200_KA_REGCAP", "NBDT_B200_KA_MINB", "NBDT_B200_KA_UNROLL", "NBDT_B200_KA_PREFETCH", "NBDT_B200_KA_MAXLD", "NBDT_B200_KA_FENCE"]
-GRID = [(168, 0, 8, 1, 24, 8), (168, 0, 8, 1, 24, 4), (168, 0, 8, 1, 24, 16), (168, 0, 8, 0, 24, 8), (168, 0, 8, 1, 8, 8),
-        (168, 8, 8, 1, 24, 16), (168, 8, 8, 1, 24, 32), (96, 0, 8, 1, 24, 8), (96, 12, 8, 1, 24, 16), (64, 12, 8, 1, 24, 16),
-        (128, 10, 8, 1, 24, 16)]
+KNOBS = ["NBDT_B200_KA_REGCAP", "NBDT_B200_KA_MINB", "NBDT_B200_KA_UNROLL", "NBDT_B200_KA_PREFETCH", "NBDT_B200_KA_MAXLD", "NBDT_B200_KA_FENCE", "NBDT_B200_KA_WARPS"]
+# (regcap, minb, unroll, prefetch, maxld, fence, warps)
+D = (168, 0, 8, 1, 24, 8, 0)
+GRIDS = {
+    100: [D, (168, 0, 8, 0, 24, 8, 0), (168, 0, 8, 0, 24, 8, 2), (168, 0, 8, 0, 24, 16, 2), (168, 0, 8, 0, 24, 8, 4)],
+    200: [D, (168, 0, 8, 0, 24, 8, 0), (168, 0, 8, 0, 24, 8, 4), (168, 0, 8, 0, 24, 16, 2), (168, 0, 8, 0, 24, 8, 1)],
+    1000: [D, (168, 0, 8, 0, 24, 8, 0)],
+}
 if len(sys.argv) > 1:
-    GRID = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+    g = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+    GRIDS = {100: g, 200: g, 1000: g}
 pk, src = peaks()
-cases = [("CIFAR100", "induced", 100, 1 << 20), ("TinyImagenet200", "induced", 200, 1 << 19)]
+cases = [("CIFAR100", "induced", 100, 1 << 20), ("TinyImagenet200", "induced", 200, 1 << 19), ("Imagenet1000", "induced", 1000, 1 << 17)]
 for dataset, hierarchy, C, rows in cases:
-    for g in GRID:
+    for g in GRIDS[C]:
         for k, v in zip(KNOBS, g):
             os.environ[k] = str(v)
         tree = Tree(dataset, hierarchy=hierarchy)

@@ -59,6 +59,13 @@ KA_DEV void st8(char* p, u32 a, u32 b) { u32 v[2] = {a, b}; memcpy(p, v, 8); }
 KA_DEV void st4(char* p, u32 a) { memcpy(p, &a, 4); }
 KA_DEV void st2(char* p, u32 a) { u16 v = (u16)a; memcpy(p, &v, 2); }
 typedef float* KA_XSB;
+#include <pthread.h>
+#include <thread>
+#include <vector>
+static pthread_barrier_t ka_bar;
+static bool ka_bar_on = false;
+static void ka_host_bar() { if (ka_bar_on) pthread_barrier_wait(&ka_bar); }
+#define KA_BAR() ka_host_bar()
 #define KA_LDX(dst, base, slot, off) const float dst = (base)[slot]
 #define KA_STX(base, slot, off, val) (base)[slot] = (val)
 #define KA_ADDX_DYN(idx, val) xsb[idx] += (val)
@@ -68,23 +75,27 @@ typedef float* KA_XSB;
 #define KA_SLOT_ADDR(base, col, row) ((base) + (col))
 #define KA_STD(a, k, off, val) (a)[k] = (val)
 #define KA_LDD(dst, a, k, off) const float dst = (a)[k]
-#define KA_STS2(rsb, v0, v1) { (rsb)[0] = (v0); (rsb)[1] = (v1); }
-#define KA_LDS2(rsw, row, d0, d1) const float d0 = (rsw)[0], d1 = (rsw)[1]
-#define ld16b ld16
-#define ld8b ld8
-#define ld4b ld4
-#define ld2b ld2
 #include "gen.cu"
 extern "C" void ka_run(const KAParams* p, float* loss) {
-  static float Xs[KA_C + 8192];
-  float rs[2] = {0.f, 0.f};
-  float acc = 0.f;
-  for (long long row = 0; row < p->B; ++row) {  // KA_TPB == 1 on the host: a "block" is one row
+  static float Xs[65536];
+  float total = 0.f;
+  if (KA_W > 1) { pthread_barrier_init(&ka_bar, nullptr, KA_W); ka_bar_on = true; }
+  for (long long row = 0; row < p->B; ++row) {  // KA_TPB == 1 on the host: a "block" is one row, its warps are host threads
     ka_sweep_a(*p, row, 1, Xs, 0);
-    ka_row(*p, row, p->targets ? p->targets[row] : 0, Xs, 0u, acc);
+    const long long yy = p->targets ? p->targets[row] : 0;
+    float acc[KA_W] = {0.f};
+    if (KA_W == 1) {
+      ka_part(0, *p, yy, true, Xs, 0u, acc[0]);
+    } else {
+      std::vector<std::thread> th;
+      for (int w = 0; w < KA_W; ++w) th.emplace_back([&, w] { ka_part(w, *p, yy, true, Xs, 0u, acc[w]); });
+      for (auto& t : th) t.join();
+    }
+    for (int w = 0; w < KA_W; ++w) total += acc[w];
     if (p->grad || p->class_probs) ka_sweep_b(*p, row, 1, Xs, 0);
   }
-  if (loss) *loss = acc;
+  if (KA_W > 1) { pthread_barrier_destroy(&ka_bar); ka_bar_on = false; }
+  if (loss) *loss = total;
 }
 '''
 
@@ -140,7 +151,7 @@ def host_kernel(tree, mode, dtype, vec):
         f.write(HARNESS)
     so = os.path.join(d, "ka.so")
     # -O1 -ffp-contract=off: fmaf() stays a real fused multiply-add, a*b+c is not contracted behind our back
-    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-o", so,
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", so,
                     os.path.join(d, "harness.cpp")], check=True, cwd=d)
     lib = ctypes.CDLL(so)
     lib.ka_run.argtypes = [ctypes.POINTER(KAParams), ctypes.POINTER(ctypes.c_float)]

@@ -318,3 +318,61 @@ def test_generic_criterion_uses_differentiable_rules(structure):
     want_l, want_g = O.soft_tree_sup_loss(ot, g["logits"].astype(np.float64), y)
     assert abs(loss.item() - B * want_l) <= 2e-5 * abs(B * want_l)
     close(x.grad, B * want_g, rtol=2e-4, atol=2e-6 * B * np.abs(want_g).max())
+
+
+@pytest.mark.parametrize("case", ["cifar10_induced", "cifar100_wordnet", "tiny200_induced_resnet18", "imagenet1000_induced"])
+def test_out_of_range_targets_are_ignored_rows(case, structure):
+    """A target outside [0, C) (nn.CrossEntropyLoss's ignore_index = -100, or a corrupt label) must not index memory: the row
+    contributes nothing to the loss and gets a zero gradient row; with batch_rows = the number of valid rows the result is the
+    oracle's on the valid rows alone.  Every kernel family: specialised (AOT + run-time compiled) and table-driven."""
+    from nbdt._b200 import ops
+
+    g = load_golden(case)
+    ot = O.OracleTree(*case_paths(structure, case))
+    x = g["logits"][:16].astype(np.float32)
+    C = x.shape[1]
+    y = g["targets"][:16].copy()
+    bad = y.copy()
+    bad[[0, 7, 15]] = [-100, C, 1 << 40]
+    keep = np.array([i for i in range(16) if i not in (0, 7, 15)])
+    for group in (None, 4):  # None: specialised kernel where there is one; 4: the table-driven kernel
+        tree = case_tree(structure, case, group)
+        for kind, fn in (("soft", O.soft_tree_sup_loss), ("hard", O.hard_tree_sup_loss)):
+            want_l, want_g = fn(ot, x[keep].astype(np.float64), y[keep])
+            loss, grad = ops.tree_loss(tree, t(x), t(bad, torch.int64), kind, 1.0, 1.0, 1.0, batch_rows=len(keep))
+            assert abs(loss.item() - want_l) <= 2e-5 * abs(want_l)
+            assert (grad[[0, 7, 15]] == 0).all()
+            close(grad[keep], want_g, rtol=2e-4, atol=2e-6 * np.abs(want_g).max())
+
+
+@pytest.mark.parametrize("case", ["cifar100_induced", "tiny200_wordnet", "ade20k_induced", "imagenet1000_induced"])
+def test_specialised_kernel_is_the_one_that_runs(case, structure):
+    """The loss / soft-forward launches of a hierarchy with up to 1536 leaves go to its run-time specialised kernel (from the
+    cubin cache the build populated, or compiled on the spot), not to the table-driven fallback."""
+    from nbdt._b200 import lib as L
+    from nbdt._b200 import ops
+
+    g = load_golden(case)
+    tree = case_tree(structure, case)
+    ops.tree_loss(tree, t(g["logits"]), t(g["targets"], torch.int64), "soft", 1.0, 1.0)
+    name = L.load().nbdt_tree_kernel_variant(tree.device_tree(torch.device(DEV)).handle).decode()
+    assert name.startswith("ka") and "_m0_t0_" in name, name
+
+
+def test_unseen_hierarchy_is_compiled_at_run_time(tmp_path):
+    """A hierarchy nobody shipped (what SoftTreeLoss's re-induction produces) gets its own kernel: compile, cache, reuse."""
+    from nbdt._b200 import lib as L
+    from nbdt._b200 import ops
+
+    pg, pw = write_random_hierarchy(tmp_path, 37, 3, seed=4242, chain_bias=0.4)
+    ot = O.OracleTree(pg, pw)
+    rng = np.random.default_rng(1)
+    x = (3 * rng.standard_normal((50, 37))).astype(np.float32)
+    y = rng.integers(0, 37, 50)
+    for attempt in range(2):  # second tree object: same hash -> served from the on-disk cache
+        tree = make_tree(None, path_graph=pg, path_wnids=pw, classes=[f"c{i}" for i in range(37)])
+        loss, grad = ops.tree_loss(tree, t(x), t(y, torch.int64), "soft", 1.0, 1.0)
+        want_l, want_g = O.soft_tree_sup_loss(ot, x.astype(np.float64), y)
+        assert abs(loss.item() - want_l) <= 2e-5 * abs(want_l)
+        close(grad, want_g, rtol=2e-4, atol=2e-6 * np.abs(want_g).max())
+        assert L.load().nbdt_tree_kernel_variant(tree.device_tree(torch.device(DEV)).handle).decode().startswith("ka")
