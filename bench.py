@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- the headline benchmark of BASELINE.json: images/sec of one WideResNet-28-10 +
-SoftTreeSupLoss (CIFAR10 induced hierarchy) train step, batch 512 per GPU, bf16, synthetic 32x32.
+SoftTreeSupLoss (CIFAR10 induced hierarchy) train step, batch 512 per GPU, bf16, synthetic 32x32 (--config 2, the default);
+--config 3 / 4 / 5 run BASELINE's other configs (WRN + CIFAR100; ResNet18 + HardTreeSupLoss TinyImagenet200 at a fixed
+global batch of 1024; EfficientNet-B0 + SoftTreeSupLoss ImageNet-1k at 256 images per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2|3|4|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W
 
@@ -11,9 +13,9 @@ update -- nothing skipped.  `value` is timed with CUDA events on device-resident
 barrier + synchronize, max over ranks.  `e2e` repeats the measurement through the public API with
 pinned HOST batches copied in every step and the loss read back every step.
 
-`--impl reference` times the reference's own CPU code path (oracle/torch_port.py, the pinned port of
-the reference's per-node PyTorch implementation + the eager WRN-28-10 restatement; /root/reference is
-Python and cannot travel to the GPU box) on the host cores, on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (vendored by oracle/make_ref.py into the git-ignored oracle/_ref, which
+travels to the GPU box): its own nbdt.loss and, where it builds offline, its own backbone, on all host cores, same config,
+each step a bounded sample of the per-GPU batch (the full batch when it fits the time budget).
 """
 import argparse
 import json
@@ -29,9 +31,22 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "images/sec SoftNBDT WRN-28-10 train step"
-WORKLOAD = "WideResNet-28-10 + SoftTreeSupLoss CIFAR10 (induced-wrn28_10_cifar10), batch=512/GPU synthetic 32x32 bf16"
-FLOPS_PER_IMAGE = 31.46e9  # 6 x 5.243 GMAC forward
+# BASELINE.json configs.  `batch` is per GPU (weak scaling); config 4 fixes the GLOBAL batch (strong scaling).
+# flops: algorithmic FLOPs per image of one train step = 6 x forward MACs (first-layer dgrad counted, not executed).
+CONFIGS = {
+    2: dict(metric="images/sec SoftNBDT WRN-28-10 train step", arch="wrn28_10_cifar10", dataset="CIFAR10",
+            hierarchy="induced-wrn28_10_cifar10", loss="SoftTreeSupLoss", classes=10, hw=32, batch=512, scaling="weak", flops=31.46e9,
+            workload="WideResNet-28-10 + SoftTreeSupLoss CIFAR10 (induced-wrn28_10_cifar10), batch=512/GPU synthetic 32x32 bf16"),
+    3: dict(metric="images/sec SoftNBDT WRN-28-10 CIFAR100 train step", arch="wrn28_10_cifar100", dataset="CIFAR100",
+            hierarchy="induced-wrn28_10_cifar100", loss="SoftTreeSupLoss", classes=100, hw=32, batch=512, scaling="weak", flops=31.46e9,
+            workload="WideResNet-28-10 + SoftTreeSupLoss CIFAR100 (100-leaf induced-wrn28_10_cifar100), batch=512/GPU synthetic 32x32 bf16"),
+    4: dict(metric="images/sec ResNet18 + HardTreeSupLoss TinyImagenet200 train step", arch="ResNet18", dataset="TinyImagenet200",
+            hierarchy="induced-ResNet18", loss="HardTreeSupLoss", classes=200, hw=64, global_batch=1024, scaling="strong", flops=13.33e9,
+            workload="ResNet18 + HardTreeSupLoss TinyImagenet200 (200-leaf induced-ResNet18), GLOBAL batch=1024 synthetic 64x64 bf16, gradient all-reduce"),
+    5: dict(metric="images/sec EfficientNet-B0 + SoftTreeSupLoss ImageNet-1k train step", arch="efficientnet_b0", dataset="Imagenet1000",
+            hierarchy="induced", loss="SoftTreeSupLoss", classes=1000, hw=224, batch=256, scaling="weak", flops=2.31e9,
+            workload="EfficientNet-B0 + SoftTreeSupLoss ImageNet-1k (1000-leaf induced hierarchy), batch=256/GPU (2048 on 8 GPUs) synthetic 224x224 bf16"),
+}
 
 
 def load_peaks():
@@ -45,26 +60,22 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's CPU implementation on the host cores
 # ------------------------------------------------------------------------------------------------
-def saturating_tree_point():
-    """The committed bench_tree.py measurement of the same kernel at a saturating size (profiles/r01_tree_sweep_v7.jsonl):
-    reported next to the latency-bound launch of the BASELINE batch, not re-measured here."""
-    path = os.path.join(ROOT, "profiles", "r01_tree_sweep_v7.jsonl")
-    try:
-        with open(path) as f:
-            for line in f:
-                r = json.loads(line)
-                if r.get("dataset") == "CIFAR10" and r.get("dtype") == "float32" and r.get("kind") == "soft":
-                    return {"rows": r["rows"], "classes": r["C"], "gbs": r["gbs"], "frac": r["frac"], "ms": r["ms"],
-                            "source": "profiles/r01_tree_sweep_v7.jsonl (python bench_tree.py --quick on a B200 of this pool)"}
-    except (OSError, ValueError, KeyError):
-        pass
-    return None
+def saturating_tree_point(tree, kind, classes, dtype):
+    """BASELINE's second metric, measured IN THIS RUN: the fused tree-loss kernel of this config's hierarchy on a row count that
+    saturates HBM (logits + gradient sets larger than the 126 MB L2, rotated so that no launch finds its data cached)."""
+    from bench_tree import time_point
+    from nbdt._b200 import lib as L
+
+    esz = torch.empty((), dtype=dtype).element_size()
+    rows = max(1 << 14, int(420e6 // (2 * classes * esz + 8)) // 4096 * 4096)
+    r = time_point(tree, kind, rows, classes, dtype, iters=12, warmup=3)
+    name = L.load().nbdt_tree_kernel_variant(tree.device_tree(torch.device("cuda", torch.cuda.current_device())).handle).decode()
+    return {"rows": rows, "classes": classes, "dtype": r["dtype"], "kind": kind, "ms": r["ms"], "alg_bytes": r["alg_bytes"], "gbs": r["gbs"],
+            "kernel": name or "table-driven (tree.cu / tree_v2.cu)", "l2": r["l2"], "measured": "in this run (CUDA events, 12 back-to-back launches)"}
 
 
 def usable_cores():
-    """Host threads the CPU arm should use: the cores this process may actually run on (affinity mask and cgroup CPU
-    quota), then a 1-second calibration -- on a box whose container is throttled below os.cpu_count() an
-    oversubscribed intra-op pool runs the convolutions ~10x slower, which would flatter the GPU arm."""
+    """Fixed thread policy of the CPU arm: every core this process may run on (affinity mask, cgroup CPU quota)."""
     n = os.cpu_count() or 1
     try:
         n = min(n, len(os.sched_getaffinity(0)))
@@ -77,73 +88,121 @@ def usable_cores():
             n = max(1, min(n, int(float(quota) / float(period))))
     except (OSError, ValueError):
         pass
-    import torch.nn.functional as F
-
-    x, w = torch.randn(8, 160, 32, 32), torch.randn(160, 160, 3, 3)  # the dominant WRN-28-10 layer shape
-    best, best_t = n, None
-    cand = sorted({c for c in (n, n // 2, n // 4, 32, 16, 8) if 1 <= c <= n}, reverse=True)
-    for c in cand:
-        torch.set_num_threads(c)
-        F.conv2d(x, w, padding=1)
-        t0 = time.time()
-        for _ in range(3):
-            F.conv2d(x, w, padding=1)
-        dt = time.time() - t0
-        if best_t is None or dt < 0.9 * best_t:
-            best, best_t = c, dt
-    return best
+    return n
 
 
-def cpu_reference_run(steps, warmup, batch, budget_s=120.0):
-    """Returns (images/sec, cores, sample description).  Bounded: stops early past `budget_s`."""
+def reference_workload(cfg):
+    """(net, criterion, kind, note) of the CPU arm for a config.  Runs in its own process (`--impl reference`, or a subprocess
+    of the b200 arm): `import nbdt` here is the UNMODIFIED reference vendored under oracle/_ref (oracle/make_ref.py), its loss
+    (reference nbdt/loss.py:191-266) and, where the reference can build it offline, its backbone.  Reference train step:
+    main.py:233-239."""
     import torch.nn as nn
+    from oracle import ref_shims
+
+    root = ref_shims.vendored_root()
+    if root is None and ref_shims.reference_available():
+        root = ref_shims.REFERENCE_ROOT
+    torch.manual_seed(0)
+    if root is not None:
+        for m in [m for m in sys.modules if m == "nbdt" or m.startswith("nbdt.")]:
+            del sys.modules[m]
+        sys.path[:] = [p for p in sys.path if not p.rstrip("/").endswith("neural-backed-decision-trees_b200")]
+        import contextlib
+
+        with contextlib.redirect_stdout(sys.stderr):  # the reference prints a `stty size` complaint at import (utils.py:175-180)
+            ref_shims.install(root, strict_hash=False)
+            import nbdt.loss as RL
+            import nbdt.models as RM
+
+        crit = getattr(RL, cfg["loss"])(dataset=cfg["dataset"], criterion=nn.CrossEntropyLoss(), hierarchy=cfg["hierarchy"])
+        if cfg["arch"] == "ResNet18":
+            net, bb = RM.ResNet18(num_classes=cfg["classes"]), "reference nbdt.models.ResNet18"
+        elif cfg["arch"] == "efficientnet_b0":
+            import torchvision
+
+            net, bb = torchvision.models.efficientnet_b0(num_classes=cfg["classes"]), "torchvision efficientnet_b0 (what the reference imports)"
+        else:
+            from oracle import torch_port as P
+
+            net, bb = P.EagerWRN(num_classes=cfg["classes"]), "eager WRN-28-10 restatement (pytorchcv is not installed offline)"
+        return net, crit, "reference", f"unmodified reference {cfg['loss']} from oracle/_ref + {bb}"
+    # no vendored reference: the pinned torch-CPU port of the same per-node algorithm
     from oracle import torch_port as P
     from oracle.tree_oracle import OracleTree
 
+    pkg = os.path.join(ROOT, "neural-backed-decision-trees_b200", "nbdt")
+    hier = cfg["hierarchy"]
+    tree = OracleTree(os.path.join(pkg, f"hierarchies/{cfg['dataset']}/graph-{hier}.json"), os.path.join(pkg, f"wnids/{cfg['dataset']}.txt"))
+    ce = nn.CrossEntropyLoss()
+    fn = P.soft_tree_sup_loss if cfg["loss"].startswith("Soft") else P.hard_tree_sup_loss
+    crit = lambda out, tgt: fn(tree, ce, out, tgt)  # noqa: E731
+    if cfg["arch"] == "ResNet18":
+        net = P.EagerResNet18(num_classes=cfg["classes"]) if hasattr(P, "EagerResNet18") else P.EagerResNet(num_classes=cfg["classes"])
+    elif cfg["arch"] == "efficientnet_b0":
+        import torchvision
+
+        net = torchvision.models.efficientnet_b0(num_classes=cfg["classes"])
+    else:
+        net = P.EagerWRN(num_classes=cfg["classes"])
+    return net, crit, "port", "oracle/torch_port.py (pinned port of the reference's per-node PyTorch path)"
+
+
+def cpu_reference_run(cfg, steps, warmup, batch, budget_s=150.0):
+    """Times `steps` train steps (after `warmup`) of the reference on the host cores.  Each step is a bounded sample of the
+    config's per-GPU batch: the sample batch is the full batch when (steps + warmup) of them fit in `budget_s`, else the
+    largest multiple of 8 that does (probed with one small step).  Returns a dict."""
     cores = usable_cores()
     torch.set_num_threads(cores)
-    pkg = os.path.join(ROOT, "neural-backed-decision-trees_b200", "nbdt")
-    tree = OracleTree(os.path.join(pkg, "hierarchies/CIFAR10/graph-induced-wrn28_10_cifar10.json"),
-                      os.path.join(pkg, "wnids/CIFAR10.txt"))
-    torch.manual_seed(0)
-    net = P.EagerWRN(num_classes=10)
+    net, crit, kind, note = reference_workload(cfg)
     net.train()
     opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
-    crit = nn.CrossEntropyLoss()
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(batch, 3, 32, 32, generator=g)
-    y = torch.randint(10, (batch,), generator=g)
-    loss_fn = lambda out, tgt: P.soft_tree_sup_loss(tree, crit, out, tgt)  # noqa: E731
-    t_begin = time.time()
+
+    def make(b):
+        return torch.randn(b, 3, cfg["hw"], cfg["hw"], generator=g), torch.randint(cfg["classes"], (b,), generator=g)
+
+    def one(x, y):  # reference main.py:233-239
+        opt.zero_grad()
+        loss = crit(net(x), y)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    probe_b = min(batch, 16)
+    x, y = make(probe_b)
+    one(x, y)  # first call pays allocator / thread-pool start-up
+    t0 = time.time()
+    one(x, y)
+    rate = probe_b / max(time.time() - t0, 1e-3)  # images/s at a small batch (a lower bound for larger ones)
+    fit = int(rate * budget_s / max(1, steps + warmup))
+    b = batch if fit >= batch else max(8, fit // 8 * 8)
+    x, y = make(b)
     for _ in range(warmup):
-        P.train_step(net, opt, loss_fn, x, y)
-        if time.time() - t_begin > budget_s / 2:
-            break
+        one(x, y)
     times = []
     for _ in range(steps):
         t0 = time.time()
-        P.train_step(net, opt, loss_fn, x, y)
+        one(x, y)
         times.append(time.time() - t0)
-        if time.time() - t_begin > budget_s:
-            break
-    times.sort()
-    med = times[len(times) // 2]
-    sample = (f"{len(times)} train steps of batch {batch} (fp32, torch {torch.__version__} CPU, "
-              f"{torch.get_num_threads()} threads); port of the reference's per-node PyTorch path + eager WRN-28-10")
-    return batch / med, torch.get_num_threads(), sample, med * 1e3
+    total = sum(times)
+    sample = (f"{steps} timed train steps (+{warmup} warm-up) of batch {b} of {batch} (fp32, torch {torch.__version__} CPU, {cores} threads, "
+              f"{total:.1f} s): {note}; zero_grad/forward/loss/backward/SGD as in reference main.py:233-239")
+    return {"value": b * steps / total, "cores": cores, "kind": kind, "sample": sample, "ms_per_step": total / steps * 1e3, "batch": b}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    val, cores, sample, ms = cpu_reference_run(args.steps, min(args.warmup, 1), args.cpu_batch)
+    cfg = CONFIGS[args.config]
+    batch = cfg.get("batch") or max(1, cfg["global_batch"] // max(1, args.gpus))
+    r = cpu_reference_run(cfg, args.steps, max(1, min(args.warmup, 2)), batch, budget_s=args.cpu_budget)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": cfg["metric"], "value": r["value"], "unit": "images/sec", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": cfg["scaling"],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cpu_sample_batch": args.cpu_batch},
-        "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": cfg["workload"], "config": args.config},
+        "cpu_baseline": {"value": r["value"], "unit": "images/sec", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -209,8 +268,8 @@ def run_b200(args, rank, world, local_rank):
     import torch.nn as nn
     from nbdt._b200 import ops
     from nbdt._b200 import parallel
-    from nbdt.loss import SoftTreeSupLoss
-    from nbdt.models import wrn28_10_cifar10
+    import nbdt.loss as NL
+    import nbdt.models as NM
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback); "
@@ -219,16 +278,25 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch  # per GPU (weak scaling)
+    cfg = CONFIGS[args.config]
+    if cfg["scaling"] == "strong":
+        if cfg["global_batch"] % world:
+            raise SystemExit(f"config {args.config}: global batch {cfg['global_batch']} is not divisible by {world} GPUs")
+        B = cfg["global_batch"] // world  # fixed global batch, split over the ranks
+    else:
+        B = args.batch or cfg["batch"]    # per GPU (weak scaling)
+    NC, HW = cfg["classes"], cfg["hw"]
     from nbdt._b200 import conv_ops, nn_ops
     from nbdt._b200.optim import FusedSGD
 
     if os.environ.get("NBDT_B200_WGRAD_STREAM", "1") != "0":
         nn_ops.enable_wgrad_overlap(True)  # weight-gradient kernels on a side stream; joined before all-reduce / SGD
     torch.manual_seed(0)
-    net = wrn28_10_cifar10().to(dev)
+    factory = getattr(NM, cfg["arch"])
+    net = (factory(num_classes=NC) if cfg["arch"] in ("ResNet18", "efficientnet_b0") else factory()).to(dev)
     net.train()
-    crit = SoftTreeSupLoss(dataset="CIFAR10", criterion=nn.CrossEntropyLoss(), hierarchy="induced-wrn28_10_cifar10")
+    crit = getattr(NL, cfg["loss"])(dataset=cfg["dataset"], criterion=nn.CrossEntropyLoss(), hierarchy=cfg["hierarchy"])
+    kind = "soft" if cfg["loss"].startswith("Soft") else "hard"
     crit.batch_rows = B * world  # the mean runs over the global batch; shards add up under all-reduce(sum)
     if world > 1:
         parallel.broadcast_parameters(net)
@@ -236,8 +304,8 @@ def run_b200(args, rank, world, local_rank):
     reducer = parallel.FlatGradientAllReduce(opt, world) if world > 1 else None
 
     g = torch.Generator().manual_seed(1234 + rank)
-    host_x = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
-    host_y = torch.randint(10, (B,), generator=g).pin_memory()
+    host_x = torch.randn(B, 3, HW, HW, generator=g).pin_memory()
+    host_y = torch.randint(NC, (B,), generator=g).pin_memory()
     dev_x = host_x.to(dev, non_blocking=True)
     dev_y = host_y.to(dev, non_blocking=True)
     tree_ev = []
@@ -347,14 +415,14 @@ def run_b200(args, rank, world, local_rank):
     # around single eager launches measure the Python launch path once the GPU has caught up with the CPU).
     tree_ms = sum(a.elapsed_time(b) for a, b in tree_ev) / max(len(tree_ev), 1)
     try:
-        tl = torch.randn(B, 10, device=dev)
+        tl = torch.randn(B, NC, device=dev)
         tout = (torch.empty((), dtype=torch.float32, device=dev), torch.empty_like(tl))
-        ops.tree_loss(crit.tree, tl, dev_y, "soft", 1.0, 1.0, out=tout)
+        ops.tree_loss(crit.tree, tl, dev_y, kind, 1.0, 1.0, out=tout)
         torch.cuda.synchronize(dev)
         tg = torch.cuda.CUDAGraph()
         with torch.cuda.graph(tg):
             for _ in range(50):
-                ops.tree_loss(crit.tree, tl, dev_y, "soft", 1.0, 1.0, out=tout)
+                ops.tree_loss(crit.tree, tl, dev_y, kind, 1.0, 1.0, out=tout)
         tg.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -365,8 +433,8 @@ def run_b200(args, rank, world, local_rank):
     except Exception:  # noqa: BLE001  (keep the eager number)
         torch.cuda.synchronize(dev)
     conv_stats = {}
-    for kind, flops, e0, e1 in conv_prof:
-        st = conv_stats.setdefault(kind, [0.0, 0.0, 0])
+    for ckind, flops, e0, e1 in conv_prof:
+        st = conv_stats.setdefault(ckind, [0.0, 0.0, 0])
         st[0] += flops
         st[1] += e0.elapsed_time(e1)
         st[2] += 1
@@ -403,7 +471,15 @@ def run_b200(args, rank, world, local_rank):
     value = B * world / (ms_per_step / 1e3)
     e2e_value = B * world / (e2e_ms / args.steps / 1e3)
     esz = 4  # the classifier GEMM emits fp32 logits
-    tree_bytes = 2 * B * 10 * esz + 8 * B + 4
+    tree_bytes = 2 * B * NC * esz + 8 * B + 4
+    try:
+        sat = saturating_tree_point(crit.tree, kind, NC, torch.float32)
+        sat["frac"] = sat["gbs"] / peaks["hbm_gbs"]
+    except Exception as e:  # noqa: BLE001
+        sat = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+    from nbdt._b200 import lib as L_
+
+    tree_kernel = L_.load().nbdt_tree_kernel_variant(crit.tree.device_tree(dev).handle).decode() or "tree_spec (AOT) / table-driven"
     conv_flops = sum(v[0] for v in conv_stats.values())
     conv_ms = sum(v[1] for v in conv_stats.values())
     conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -415,10 +491,10 @@ def run_b200(args, rank, world, local_rank):
             tj = json.load(f)
         traffic, traffic_src = tj["mean_bytes_per_launch"], tj["source"]
     line = {
-        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": cfg["metric"], "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": cfg["scaling"],
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
+        "config": {"workload": cfg["workload"], "config": args.config, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "l2": "working set (activations ~5 GB/step) >> L2; no flush needed",
                    "backbone": parallel.BACKBONE_STATUS, "optimizer": "fused SGD momentum 0.9 wd 5e-4 (fp32 master weights)",
                    "cuda_graph": graph_note},
@@ -426,24 +502,32 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": host_x.numel() * 4 + host_y.numel() * 8,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "roofline": {"kernel": "tap_gemm2h / tap_gemm2 / tap_gemm / wgrad kernels (tcgen05 implicit-GEMM conv fwd + dgrad + wgrad, all 81 launches of a step)",
+        "roofline": {"kernel": "tap_gemm2h / tap_gemm2 / tap_gemm / wgrad kernels (tcgen05 implicit-GEMM conv fwd + dgrad + wgrad, every conv launch of a step)",
                      "bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": conv_tflops / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src + " (bf16_tflops_sustained)",
+                     "frac": conv_tflops / peak_tf, "flops": "algorithmic: 2*N*Ho*Wo*Cout*Cin*k*k with the layers' real channel counts (padding channels not counted)",
+                     "step_frac": cfg["flops"] * B * world / (ms_per_step / 1e3) / 1e12 / world / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src + " (bf16_tflops_sustained)",
                      "per_kind": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12, "ms_per_step": v[1] / prof_steps,
                                       "launches_per_step": v[2] / prof_steps} for k, v in conv_stats.items()},
                      "conv_share_of_step": (conv_ms / prof_steps) / ms_per_step,
                      "timed_with": f"CUDA events around each launch, {prof_steps} eager steps right after the timed region"},
-        "tree_roofline": {"kernel": "tree_spec_<hash><float, soft loss fwd+bwd> (memset of the loss scalar + kernel, 50 launches in a CUDA graph)", "bound": "hbm",
+        "tree_roofline": {"kernel": tree_kernel + f" ({kind} loss fwd+bwd; memset of the loss scalar + kernel, 50 launches in a CUDA graph)", "bound": "hbm",
                           "achieved": tree_bytes / (tree_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                           "frac": tree_bytes / (tree_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_us": tree_ms * 1e3,
-                          "note": "45 KB per launch at the BASELINE batch: latency-bound; saturating sweep in profiles/",
-                          "saturating_sweep": saturating_tree_point()},
-        "step_tflops": FLOPS_PER_IMAGE * B * world / (ms_per_step / 1e3) / 1e12,
+                          "note": f"{tree_bytes} B per launch at the BASELINE batch: latency-bound; `saturating` is the same kernel on rows that fill HBM",
+                          "saturating": sat},
+        "step_tflops": cfg["flops"] * B * world / (ms_per_step / 1e3) / 1e12,
         "loss": {"first_step": loss_first, "after_timed_steps": loss_last},  # sanity: the same synthetic batch is being fitted
     }
     if world == 1 and not args.no_cpu_baseline:
-        val, cores, sample, _ = cpu_reference_run(3, 1, args.cpu_batch, budget_s=60.0)
-        line["cpu_baseline"] = {"value": val, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample}
+        # the reference needs `import nbdt` to be ITS package: a subprocess (this one has the product's nbdt loaded)
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", str(args.config), "--steps", "2",
+                                  "--warmup", "1", "--cpu-budget", "40"], capture_output=True, text=True, timeout=600)
+            ref = json.loads(out.stdout.strip().splitlines()[-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "images/sec", "cores": usable_cores(), "kind": "reference",
+                                    "sample": f"failed: {type(e).__name__}: {str(e)[:100]}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -455,8 +539,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
-    ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (BASELINE config 2: 512)")
-    ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU sample")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (2 = the headline)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (weak-scaling configs)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the whole CPU arm may take")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="launch every kernel eagerly (no CUDA graph)")
     args = ap.parse_args()

@@ -53,7 +53,8 @@ def pack_weights(weight, cin_pad=None, cout_pad=None, want=(True, True)):
     return wp, wpt
 
 
-def conv_fwd(x, wp, ksize, stride, residual=None):
+def conv_fwd(x, wp, ksize, stride, residual=None, real=None):
+    """real = (Cout, Cin) of the layer: the FLOP count bench.py reports is the algorithmic one, not that of the padded channels."""
     _check_act(x, "conv_fwd input")
     N, H, W, cin = x.shape
     taps, cout, cin_w = wp.shape
@@ -62,7 +63,7 @@ def conv_fwd(x, wp, ksize, stride, residual=None):
     if residual is not None:
         _check_act(residual, "conv_fwd residual")
         assert residual.shape == y.shape
-    flops = 2.0 * y.numel() * cin * ksize * ksize
+    flops = 2.0 * y.numel() * cin * ksize * ksize if real is None else 2.0 * N * (H // stride) * (W // stride) * real[0] * real[1] * ksize * ksize
     with torch.cuda.device(x.device), _timed("fwd", flops):
         L.check(L.load().nbdt_conv2d_fwd(_p(x), _p(wp), _p(y), _p(residual), N, H, W, cin, cout, ksize, stride,
                                          L.stream_ptr(x.device)))
@@ -70,7 +71,7 @@ def conv_fwd(x, wp, ksize, stride, residual=None):
     return y
 
 
-def conv_dgrad(dy, wpt, in_hw, ksize, stride, accumulate=None):
+def conv_dgrad(dy, wpt, in_hw, ksize, stride, accumulate=None, real=None):
     """dx (N, H, W, Cin) for dy (N, H/s, W/s, Cout); `accumulate` (same shape as dx) is added and
     overwritten in place."""
     _check_act(dy, "conv_dgrad dy")
@@ -82,7 +83,7 @@ def conv_dgrad(dy, wpt, in_hw, ksize, stride, accumulate=None):
     if accumulate is not None:
         _check_act(accumulate, "conv_dgrad accumulate")
         assert accumulate.shape == (N, H, W, cin)
-    flops = 2.0 * dy.numel() * cin * ksize * ksize
+    flops = 2.0 * dy.numel() * cin * ksize * ksize if real is None else 2.0 * N * Ho * Wo * real[0] * real[1] * ksize * ksize
     with torch.cuda.device(dy.device), _timed("dgrad", flops):
         L.check(L.load().nbdt_conv2d_dgrad(_p(dy), _p(wpt), _p(dx), _p(accumulate), N, H, W, cin, cout, ksize, stride,
                                            L.stream_ptr(dy.device)))
@@ -90,7 +91,7 @@ def conv_dgrad(dy, wpt, in_hw, ksize, stride, accumulate=None):
     return dx
 
 
-def conv_wgrad(x, dy, ksize, stride):
+def conv_wgrad(x, dy, ksize, stride, real=None):
     """fp32 [taps][Cout][Cin] weight gradient (padded channel counts, as the activations carry them)."""
     _check_act(x, "conv_wgrad x")
     _check_act(dy, "conv_wgrad dy")
@@ -98,7 +99,7 @@ def conv_wgrad(x, dy, ksize, stride):
     cout = dy.shape[3]
     assert dy.shape == (N, H // stride, W // stride, cout)
     dwp = torch.empty((ksize * ksize, cout, cin), dtype=torch.float32, device=x.device)
-    flops = 2.0 * dy.numel() * cin * ksize * ksize
+    flops = 2.0 * dy.numel() * cin * ksize * ksize if real is None else 2.0 * N * (H // stride) * (W // stride) * real[0] * real[1] * ksize * ksize
     with torch.cuda.device(x.device), _timed("wgrad", flops):
         L.check(L.load().nbdt_conv2d_wgrad(_p(x), _p(dy), _p(dwp), N, H, W, cin, cout, ksize, stride,
                                            L.stream_ptr(x.device)))

@@ -103,7 +103,7 @@ class ConvFunction(torch.autograd.Function):
         # output channels the GEMM tiles can cover (multiples of 64 / 128 / 160); others are zero-padded to 64s
         cout_phys = cout if (cout % 64 == 0 or cout % 160 == 0) else C.pad64(cout)
         wp, wpt = C.pack_weights(weight, cin_pad=cin_phys, cout_pad=cout_phys)
-        y = C.conv_fwd(x, wp, k, stride, residual)
+        y = C.conv_fwd(x, wp, k, stride, residual, real=(cout, cin))
         ctx.save_for_backward(x, wpt)
         ctx.meta = (tuple(weight.shape), k, stride, residual is not None)
         ctx.direct_grad = weight.grad if getattr(weight, "_nbdt_direct_grad", False) else None
@@ -116,20 +116,20 @@ class ConvFunction(torch.autograd.Function):
         dy = dy.contiguous()
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = C.conv_dgrad(dy, wpt, (x.shape[1], x.shape[2]), k, stride)
+            dx = C.conv_dgrad(dy, wpt, (x.shape[1], x.shape[2]), k, stride, real=wshape[:2])
         if ctx.needs_input_grad[1]:
             if ctx.direct_grad is not None and _OVERLAP_WGRAD:
                 main, side = torch.cuda.current_stream(x.device), wgrad_stream(x.device)
                 side.wait_stream(main)  # x and dy are complete on the main stream at this point
                 with torch.cuda.stream(side):
-                    dwp = C.conv_wgrad(x, dy, k, stride)
+                    dwp = C.conv_wgrad(x, dy, k, stride, real=wshape[:2])
                     C.unpack_wgrad(dwp, wshape, out=ctx.direct_grad, accumulate=True)
                 x.record_stream(side)
                 dy.record_stream(side)
             elif ctx.direct_grad is not None:
-                C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride), wshape, out=ctx.direct_grad, accumulate=True)
+                C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride, real=wshape[:2]), wshape, out=ctx.direct_grad, accumulate=True)
             else:
-                dw = C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride), wshape)
+                dw = C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride, real=wshape[:2]), wshape)
         return dx, dw, None, (dy if has_res else None)
 
 

@@ -27,11 +27,22 @@ def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "nbdt"))
 
 
-def install():
-    """Make `import nbdt` resolve to the executing reference.  Idempotent."""
+def vendored_root():
+    """oracle/_ref (made by oracle/make_ref.py: an unmodified copy of the reference that travels to the GPU box), or None."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    return p if os.path.isdir(os.path.join(p, "nbdt")) else None
+
+
+def install(root=None, strict_hash=True):
+    """Make `import nbdt` resolve to the executing reference.  Idempotent.
+    root: tree to import from (default /root/reference; bench.py passes the vendored copy).  strict_hash=False drops the
+    PYTHONHASHSEED requirement (timing runs: the leaf order inside a child's set does not change the arithmetic volume)."""
+    global REFERENCE_ROOT
+    if root is not None:
+        REFERENCE_ROOT = root
     if not reference_available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
-    if os.environ.get("PYTHONHASHSEED") != "0":
+    if strict_hash and os.environ.get("PYTHONHASHSEED") != "0":
         raise RuntimeError(
             "run with PYTHONHASHSEED=0: the reference's leaf ordering per child comes "
             "from a Python set of strings (nbdt/thirdparty/nx.py:21-25)"
