@@ -222,6 +222,30 @@ int nbdt_dwconv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
                       void* stream);
 int nbdt_se_dscale(const void* x, const void* dy, float* ds, int N, int HW, int C, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Either side of the hot path (csrc/aux_ops.cu): evaluation counters, hierarchy induction, batch augmentation.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Top-k accuracy without a host sync per batch (reference nbdt/metrics.py:16-20, fed by nbdt/analysis.py:224-229 with the
+ * decision rules' output): counters[0] += #rows whose target is among the k largest scores (ties: lower index first, as
+ * torch.topk lists them), counters[1] += #rows with a target in [0, C).  counters: two device uint64, zeroed by the caller. */
+int nbdt_topk_count(const void* scores, int dtype, const int64_t* targets, int64_t B, int64_t C, int64_t ld, int k,
+                    unsigned long long* counters, void* stream);
+
+/* Ward agglomerative clustering of C points (the classifier rows, fp32 [C][D]) on the device: what
+ * sklearn.cluster.AgglomerativeClustering(linkage="ward").fit(X).children_ returns in the reference's build_induced_graph
+ * (nbdt/graph.py:434-438).  children: int32 [C-1][2], ids < C are points, C + s the cluster made by merge s (smaller id
+ * first); heights: fp64 [C-1] merge distances (nondecreasing).  workspace: nbdt_ward_workspace_bytes(C) device bytes.
+ * C <= 1024. */
+long long nbdt_ward_workspace_bytes(int C);
+int nbdt_ward_linkage(const float* centers, int C, int D, int32_t* children, double* heights, void* workspace, void* stream);
+
+/* RandomCrop(H, padding=pad) + RandomHorizontalFlip + ToTensor + Normalize (reference nbdt/data/cifar.py:10-21) for a batch of
+ * uint8 images resident on the device.  src: uint8 [N][H][W][3]; params: device int32 [N][3] = (dx, dy in [0, 2*pad], flip 0/1)
+ * drawn by the caller; dst: fp32 [N][3][H][W]; mean3 / std3: HOST pointers to three floats. */
+int nbdt_augment_crop_flip(const void* src_u8_nhwc, const int32_t* params, float* dst_nchw, int N, int H, int W, int pad,
+                           const float* mean3, const float* std3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
