@@ -222,6 +222,13 @@ int nbdt_dwconv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
                       void* stream);
 int nbdt_se_dscale(const void* x, const void* dy, float* ds, int N, int HW, int C, void* stream);
 
+/* Classifier head (csrc/linear.cu): C[M,N] = A B (+ bias[n]) (+ C) in fp32 with element strides A(m,k) = A[m*a_row_stride +
+ * k*a_col_stride], B(k,n) = B[k*b_row_stride + n*b_col_stride] -- logits = feat W^T + b and its gradients
+ * (reference nbdt/models/resnet.py:142-148) without copies for the transposes; nbdt_colsum: out[n] = sum_m X[m,n] (bias gradient). */
+int nbdt_sgemm(int M, int N, int K, const float* A, long long a_row_stride, long long a_col_stride, const float* B, long long b_row_stride,
+               long long b_col_stride, float* C, long long ldc, const float* bias_n, int accumulate, void* stream);
+int nbdt_colsum(const float* X, int M, int N, long long ld, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Either side of the hot path (csrc/aux_ops.cu): evaluation counters, hierarchy induction, batch augmentation.
  * ------------------------------------------------------------------------------------------- */

@@ -63,7 +63,6 @@ struct TapGemmParams {
   int tap_dh[kMaxTaps];
   int tap_dw[kMaxTaps];
   int tap_wrow[kMaxTaps];  // first row of this tap's [Cout x Cin] slice in the packed weight matrix
-  int exp;  // perf experiments only (env NBDT_B200_CONV_EXP): 1 skip B loads, 2 skip A loads, 4 skip stores, 8 one MMA per stage
   // H-halo pair kernel (tap_gemm2h_kernel): the 9 taps as 3 column groups (same dw) of 3 taps (dh = -1, 0, +1 in any order)
   int grp_dw[3];
   int grp_dh[3][3];
@@ -193,7 +192,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
         for (int j = 0; j < Cfg::kUnits; ++j) {
           if (j < nu) {
             // channels past Cin in a tap's last k-block are TMA zero fill; do not spend MMAs on them
-            const int ksteps = (p.exp & 8) ? 1 : ((kb == p.kblocks - 1) ? p.last_ksteps : kBlockK / 16);
+            const int ksteps = (kb == p.kblocks - 1) ? p.last_ksteps : kBlockK / 16;
             const uint64_t adesc = sdesc + (uint64_t)((j * Cfg::kUnitBytes) >> 4);
             const uint64_t bdesc = adesc + (uint64_t)(Cfg::kABytes >> 4);
             if (leader) {
@@ -233,7 +232,7 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
       const int pw = w0 + row % p.box_w;
       const int ph = h0 + (row / p.box_w) % p.box_h;
       const int pn = n0 + row / (p.box_w * p.box_h);
-      const bool in_range = pw < p.W_out && ph < p.H_out && pn < p.N_img && !(p.exp & 4);
+      const bool in_range = pw < p.W_out && ph < p.H_out && pn < p.N_img;
       const long long off = pn * p.out_sn + ph * p.out_sh + pw * p.out_sw + (long long)n_tile * BLOCK_N;
 
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
@@ -820,7 +819,6 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
   p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
   p.out = const_cast<__nv_bfloat16*>(out.base);
   p.residual = residual;
-  p.exp = getenv("NBDT_B200_CONV_EXP") ? atoi(getenv("NBDT_B200_CONV_EXP")) : 0;
   for (int t = 0; t < num_taps; ++t) {
     p.tap_map[t] = taps[t].map; p.tap_dh[t] = taps[t].dh; p.tap_dw[t] = taps[t].dw; p.tap_wrow[t] = taps[t].wrow;
   }
@@ -847,7 +845,7 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
   // pair kernels from this many pair tiles on (default: one per SM pair); NBDT_B200_CONV_PAIR_MIN lowers it for tests
   const int pair_min = getenv("NBDT_B200_CONV_PAIR_MIN") ? atoi(getenv("NBDT_B200_CONV_PAIR_MIN")) : info.sm_count / 2;
   // H-halo variant: 3x3 taps on ONE dense view, tiles = box_w x box_h pixels of one image with box_w in {16, 32}
-  bool halo = pair_enabled && p.exp == 0 && total_pairs >= pair_min && num_taps == 9 && num_views == 1 &&
+  bool halo = pair_enabled && total_pairs >= pair_min && num_taps == 9 && num_views == 1 &&
               p.box_n == 1 && (p.box_w == 16 || p.box_w == 32) && p.box_w * (p.box_h + 2) <= 192 &&
               !getenv("NBDT_B200_CONV_NOHALO");
   if (halo) {  // group the taps by dw; every group must hold dh = -1, 0, +1
@@ -889,7 +887,7 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
     NBDT_CUDA_OK(cudaGetLastError());
     return NBDT_OK;
   }
-  if (pair_enabled && p.exp == 0 && total_pairs >= pair_min) {
+  if (pair_enabled && total_pairs >= pair_min) {
     CUtensorMap tm_w2;
     {
       cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)w_rows};

@@ -1,14 +1,13 @@
 """Functional backbone ops used by nbdt.models: every conv / batch-norm / activation / pool runs as a
 hand-written sm_100a kernel (tcgen05 implicit-GEMM convolutions, fused BN(+ReLU,+residual) passes) on
-NHWC bf16 activations.  The classifier GEMM (features x FC weight) is a plain library GEMM (cuBLAS via
-F.linear) in fp32.  CUDA tensors only; there is no CPU or ATen/cuDNN convolution path behind these.
+NHWC bf16 activations; the classifier (features x FC weight, fp32) on the small SGEMM of csrc/linear.cu.  CUDA tensors only;
+there is no CPU or ATen/cuDNN/cuBLAS path behind these.
 """
 import torch
-import torch.nn.functional as F
 
 from . import lib as L
 from .conv_ops import pad64
-from .nn_ops import AvgPoolFunction, BatchNormActFunction, ConvFunction, StemFunction
+from .nn_ops import AvgPoolFunction, BatchNormActFunction, ConvFunction, LinearFunction, StemFunction
 
 BACKBONE_STATUS = "own kernels: tcgen05/TMA implicit-GEMM conv fwd/dgrad/wgrad, fused BN+ReLU(+residual), pool, stem"
 
@@ -69,6 +68,5 @@ def avg_pool(x, pool):
 
 
 def linear(feat, lin):
-    """Classifier: fp32 features (N, C_phys) x FC weight -- a plain library GEMM."""
-    c = lin.in_features
-    return F.linear(feat[:, :c], lin.weight, lin.bias)
+    """Classifier: fp32 features (N, C_phys) x FC weight (reads the first in_features columns; no copy)."""
+    return LinearFunction.apply(feat, lin.weight, lin.bias)

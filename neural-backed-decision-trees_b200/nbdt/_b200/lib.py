@@ -68,6 +68,9 @@ SIGNATURES = {
     "nbdt_bn_backward_silu": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nbdt_se_scale": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 3 + [c_ptr]),
     "nbdt_stem_wgrad": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 5 + [c_ptr]),
+    "nbdt_sgemm": (ctypes.c_int, [ctypes.c_int] * 3 + [c_ptr, ctypes.c_longlong, ctypes.c_longlong, c_ptr, ctypes.c_longlong, ctypes.c_longlong,
+                                  c_ptr, ctypes.c_longlong, c_ptr, ctypes.c_int, c_ptr]),
+    "nbdt_colsum": (ctypes.c_int, [c_ptr, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, c_ptr, c_ptr]),
     "nbdt_topk_count": (ctypes.c_int, [c_ptr, ctypes.c_int, c_ptr, c_i64, c_i64, c_i64, ctypes.c_int, c_ptr, c_ptr]),
     "nbdt_ward_workspace_bytes": (ctypes.c_longlong, [ctypes.c_int]),
     "nbdt_ward_linkage": (ctypes.c_int, [c_ptr, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),

@@ -228,3 +228,46 @@ class AvgPoolFunction(torch.autograd.Function):
             L.check(L.load().nbdt_avgpool_bwd(_p(dfeat), _p(da), N, H * W, Cp, _stream(dfeat)))
         _count()
         return da
+
+
+class LinearFunction(torch.autograd.Function):
+    """y = x W^T (+ b) in fp32 on this repository's SGEMM kernel (csrc/linear.cu): the classifier head and the squeeze-excitation
+    layers.  x: (N, D_phys >= D) -- only the first D columns are read (padding channels of the pooled features); W: (C, D)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        L.require_cuda(x, "linear input")
+        x = x.float()
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        w = weight.float().contiguous() if (weight.dtype != torch.float32 or not weight.is_contiguous()) else weight
+        N, (C, D) = x.shape[0], w.shape
+        y = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.load().nbdt_sgemm(N, C, D, _p(x), x.stride(0), 1, _p(w), 1, D, _p(y), C, _p(bias), 0, _stream(x)))
+        _count()
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        N, (C, D) = x.shape[0], w.shape
+        dx = dw = db = None
+        lib = L.load()
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[0]:
+                dx = torch.zeros_like(x) if x.shape[1] != D else torch.empty_like(x)
+                L.check(lib.nbdt_sgemm(N, D, C, _p(dy), C, 1, _p(w), D, 1, _p(dx), dx.stride(0), None, 0, _stream(x)))
+                _count()
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty_like(w)
+                L.check(lib.nbdt_sgemm(C, D, N, _p(dy), 1, C, _p(x), x.stride(0), 1, _p(dw), D, None, 0, _stream(x)))
+                _count()
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = torch.empty((C,), dtype=torch.float32, device=x.device)
+                L.check(lib.nbdt_colsum(_p(dy), N, C, C, _p(db), _stream(x)))
+                _count()
+        return dx, dw, db

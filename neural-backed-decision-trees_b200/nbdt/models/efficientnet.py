@@ -9,9 +9,9 @@ checkpoints load with `load_state_dict(strict=True)` -- and runs the forward pas
   stem      3x3/s2 conv (csrc/bn_ops.cu: stem_fwd_kernel) -> folded BN + SiLU (bn_apply_kernel)
   MBConv    [1x1 expand conv on tcgen05 (csrc/conv_gemm.cu) -> BN + SiLU]
             -> depthwise k x k conv with BN + SiLU fused (csrc/mbconv_ops.cu: dwconv_fwd_kernel)
-            -> squeeze-excitation: global average pool kernel, two tiny FC layers (library GEMMs), scale kernel
+            -> squeeze-excitation: global average pool kernel, two tiny FC layers (SGEMM kernel of csrc/linear.cu), scale kernel
             -> 1x1 project conv on tcgen05 -> BN (+ residual) in one pass
-  head      1x1 conv 320 -> 1280 -> BN + SiLU -> global average pool -> Linear (library GEMM)
+  head      1x1 conv 320 -> 1280 -> BN + SiLU -> global average pool -> Linear (SGEMM kernel of csrc/linear.cu)
 
 Activations are NHWC bf16 with channel counts padded to multiples of 64.  Eval mode: folded BatchNorm (running statistics),
 depthwise conv + BN + SiLU in one kernel, cached packed weights; StochasticDepth / Dropout are identities.  Training mode:
@@ -29,7 +29,7 @@ import torch.nn.functional as F
 from nbdt._b200 import backbone as B
 from nbdt._b200 import conv_ops as C
 from nbdt._b200 import mbconv_ops as M
-from nbdt._b200.nn_ops import AvgPoolFunction
+from nbdt._b200.nn_ops import AvgPoolFunction, LinearFunction
 
 __all__ = ("efficientnet_b0", "EfficientNet")
 
@@ -60,11 +60,11 @@ class SqueezeExcitation(nn.Module):
 
     def forward(self, x):
         """x: NHWC bf16 (N, H, W, C_phys) -> x * sigmoid(fc2(silu(fc1(mean_hw x)))).  Differentiable: the pooling and the
-        scaling are own kernels with backward kernels, the two tiny FC layers are library GEMMs under autograd."""
+        scaling are own kernels with backward kernels, the two tiny FC layers run on the small SGEMM of csrc/linear.cu."""
         c = self.fc1.in_channels
         pooled = AvgPoolFunction.apply(x)  # (N, C_phys) fp32
-        s = F.linear(pooled[:, :c], self.fc1.weight.flatten(1), self.fc1.bias)
-        s = F.linear(F.silu(s), self.fc2.weight.flatten(1), self.fc2.bias)
+        s = LinearFunction.apply(pooled, self.fc1.weight.flatten(1), self.fc1.bias)
+        s = LinearFunction.apply(F.silu(s), self.fc2.weight.flatten(1), self.fc2.bias)
         scale = F.pad(torch.sigmoid(s), (0, pooled.shape[1] - c))  # padding channels stay zero
         return M.SEScaleFunction.apply(x, scale)
 
@@ -169,7 +169,7 @@ class EfficientNet(nn.Module):
         feat = feat[:, : lin.in_features]
         if self.training:
             feat = F.dropout(feat, p=self.classifier[0].p, training=True)
-        return F.linear(feat, lin.weight, lin.bias)
+        return LinearFunction.apply(feat, lin.weight, lin.bias)
 
 
 def efficientnet_b0(pretrained=False, progress=True, num_classes=1000, weights=None, **kwargs):

@@ -55,23 +55,21 @@ def test_soft_tree_loss_reinduces_and_lands_on_a_specialised_kernel(monkeypatch,
     monkeypatch.chdir(PKG)
     torch.manual_seed(0)
     net = ResNet18(num_classes=10).to(DEV)
-    crit = SoftTreeLoss(dataset="CIFAR10", criterion=nn.CrossEntropyLoss(), hierarchy="induced-ResNet18", arch="ResNet18", model=net,
-                        tree_start_epochs=1, tree_update_every_epochs=1, tree_update_end_epochs=3)
+    crit = SoftTreeLoss(dataset="CIFAR10", criterion=nn.CrossEntropyLoss(), hierarchy="induced-ResNet18", arch="ResNet18", net=net,
+                        checkpoint_path=str(tmp_path / "ckpt.pth"), tree_start_epochs=1, tree_update_every_epochs=1, tree_update_end_epochs=3)
     x = torch.randn(16, 3, 32, 32, device=DEV)
     y = torch.randint(10, (16,), device=DEV)
-    crit.set_epoch(0, 4)
+    crit.set_epoch(0, 4)                 # before tree_start_epochs: plain cross-entropy, shipped hierarchy untouched
     l0 = crit(net(x), y)
-    before = [n.wnid for n in crit.tree.inodes]
-    crit.tree.path_graph = str(tmp_path / "graph-induced-live.json")  # do not overwrite the shipped file
-    monkeypatch.setattr("nbdt.graph.get_graph_path_from_args", lambda **k: str(tmp_path / "graph-induced-live.json"))
-    monkeypatch.setattr("nbdt.hierarchy.get_graph_path_from_args", lambda **k: str(tmp_path / "graph-induced-live.json"))
-    crit.set_epoch(1, 4)  # re-induction from the (random) live classifier
+    shipped = crit.tree.path_graph
+    crit.set_epoch(1, 4)                 # re-induction from the live (random) classifier -> <checkpoint dir>/graph-epoch1.json
     l1 = crit(net(x), y)
     l1.backward()
     assert torch.isfinite(l0) and torch.isfinite(l1)
-    assert len(crit.tree.inodes) == 9 and os.path.exists(tmp_path / "graph-induced-live.json")
+    assert crit.tree.path_graph != shipped and os.path.exists(tmp_path / "ckpt" / "graph-epoch1.json")
+    assert len(crit.tree.inodes) == 9 and all(p.grad is not None for p in net.parameters())
     name = L.load().nbdt_tree_kernel_variant(crit.tree.device_tree(torch.device(DEV)).handle).decode()
-    assert name.startswith("ka") or len(before) == 9
+    assert name.startswith("ka"), name
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
