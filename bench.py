@@ -301,7 +301,13 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         parallel.broadcast_parameters(net)
     opt = FusedSGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
-    reducer = parallel.FlatGradientAllReduce(opt, world) if world > 1 else None
+    # gradient all-reduce: in pieces during backward (captured in the CUDA graph with it) unless NBDT_B200_ALLREDUCE_OVERLAP=0
+    overlapped = world > 1 and os.environ.get("NBDT_B200_ALLREDUCE_OVERLAP", "1") != "0"
+    reducer = None
+    if world > 1:
+        reducer = (parallel.OverlappedGradientAllReduce(opt, world, pieces=int(os.environ.get("NBDT_B200_ALLREDUCE_PIECES", "4")),
+                                                        bf16=os.environ.get("NBDT_B200_ALLREDUCE_BF16", "0") == "1")
+                   if overlapped else parallel.FlatGradientAllReduce(opt, world))
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_x = torch.randn(B, 3, HW, HW, generator=g).pin_memory()
@@ -322,10 +328,12 @@ def run_b200(args, rank, world, local_rank):
             tree_ev.append((e0, e1))
         loss.backward()
         nn_ops.join_wgrad_streams(dev)  # weight-gradient kernels run on a side stream: join before capture ends / SGD
+        if overlapped:
+            reducer.finish()  # the pieces were sent from autograd hooks while backward ran; send the head, join the comm stream
         return loss
 
     def finish():
-        if reducer is not None:
+        if reducer is not None and not overlapped:
             reducer.reduce()
         opt.step()
 
@@ -497,7 +505,9 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": cfg["workload"], "config": args.config, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "l2": "working set (activations ~5 GB/step) >> L2; no flush needed",
                    "backbone": parallel.BACKBONE_STATUS, "optimizer": "fused SGD momentum 0.9 wd 5e-4 (fp32 master weights)",
-                   "cuda_graph": graph_note},
+                   "cuda_graph": graph_note,
+                   "allreduce": ("none (1 GPU)" if world == 1 else (f"fp32 flat gradient in {len(reducer.bounds) + 1} pieces issued during backward "
+                                 f"(boundaries at elements {reducer.bounds})" if overlapped else "one fp32 all-reduce after backward"))},
         "clocks": clock_summary,
         "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": host_x.numel() * 4 + host_y.numel() * 8,
                 "d2h_bytes_per_step": 4},

@@ -14,9 +14,12 @@ BACKBONE_STATUS = "own kernels: tcgen05/TMA implicit-GEMM conv fwd/dgrad/wgrad, 
 
 def _bn_args(bn):
     training = bn.training or not bn.track_running_stats
-    momentum = 0.1 if bn.momentum is None else bn.momentum
     if training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
+    if bn.momentum is None:  # cumulative moving average (nn.BatchNorm2d semantics): 1 / number of batches seen
+        momentum = 1.0 / float(bn.num_batches_tracked) if (training and bn.track_running_stats and bn.num_batches_tracked is not None) else 0.0
+    else:
+        momentum = bn.momentum
     return bn.weight, bn.bias, bn.running_mean, bn.running_var, training, momentum, bn.eps
 
 

@@ -49,17 +49,49 @@ class FusedSGD(torch.optim.Optimizer):
             off += n
 
     @torch.no_grad()
-    def step(self, closure=None):
-        loss = closure() if closure is not None else None
-        g = self.param_groups[0]
-        # autograd may have REPLACED p.grad (first backward after None) instead of accumulating in place
+    def reseat_grads(self):
+        """autograd REPLACES p.grad when it was None (model.zero_grad() with set_to_none=True) instead of accumulating into the flat
+        buffer's view: copy such gradients back and restore the views.  Called by step() and by the gradient all-reduce, which both
+        work on the flat buffer."""
         off = 0
-        for p in g["params"]:
+        for p in self.param_groups[0]["params"]:
             n = p.numel()
             if p.grad is not None and p.grad.data_ptr() != self.flat_grad[off:off + n].data_ptr():
                 self.flat_grad[off:off + n].copy_(p.grad.reshape(-1))
                 p.grad = self.flat_grad[off:off + n].view_as(p)
             off += n
+
+    def assert_grads_are_views(self):
+        off = 0
+        for p in self.param_groups[0]["params"]:
+            n = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad[off:off + n].data_ptr():
+                raise RuntimeError("a parameter's .grad is not a view of FusedSGD's flat gradient buffer any more: clear gradients with "
+                                   "optimizer.zero_grad() (not model.zero_grad(set_to_none=True)) when gradients are all-reduced during backward")
+            off += n
+
+    def state_dict(self):
+        """torch.optim's state_dict plus the flat momentum buffer and the step count (resume keeps the momentum)."""
+        sd = super().state_dict()
+        sd["nbdt_flat_momentum"] = self.flat_momentum.detach().clone()
+        sd["nbdt_steps"] = self._steps
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        mom = state_dict.pop("nbdt_flat_momentum", None)
+        steps = state_dict.pop("nbdt_steps", None)
+        super().load_state_dict(state_dict)
+        if mom is not None:
+            self.flat_momentum.copy_(mom.to(self.flat_momentum.device))
+        if steps is not None:
+            self._steps = int(steps)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        g = self.param_groups[0]
+        self.reseat_grads()
         from .nn_ops import join_wgrad_streams
 
         join_wgrad_streams(self.flat_param.device)  # weight-gradient kernels run on a side stream

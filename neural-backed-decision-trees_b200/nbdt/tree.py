@@ -163,6 +163,13 @@ class Tree:
         self.leaves = [self.wnid_to_node[wnid] for wnid in self.wnids_leaves]
         self.__dict__.pop("_b200_device_trees", None)  # device tables belong to the old hierarchy
 
+    def __getstate__(self):
+        """Copies / pickles (copy.deepcopy of a criterion, torch.save of a model that holds its tree) drop the device-side tables:
+        they hold raw library handles and are rebuilt on first use."""
+        state = self.__dict__.copy()
+        state.pop("_b200_device_trees", None)
+        return state
+
     def _collect_leaves(self):
         """wnid -> tuple of leaf wnids below it (depth-first, child order); one post-order pass."""
         G = self.G

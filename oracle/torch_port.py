@@ -95,21 +95,46 @@ class _BasicBlock(nn.Module):
         return F.relu(out + self.shortcut(x))
 
 
-class EagerResNet(nn.Module):
-    """reference: nbdt/models/resnet.py:115-149 with BasicBlock (:42-74)."""
+class _Bottleneck(nn.Module):
+    """reference: nbdt/models/resnet.py:77-112 (1x1 -> 3x3 (stride) -> 1x1 x4, projection shortcut when the shape changes)."""
 
-    def __init__(self, depths=(2, 2, 2, 2), num_classes=10):
+    expansion = 4
+
+    def __init__(self, cin, planes, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, 4 * planes, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(4 * planes)
+        self.shortcut = nn.Sequential()
+        if stride != 1 or cin != 4 * planes:
+            self.shortcut = nn.Sequential(nn.Conv2d(cin, 4 * planes, 1, stride, bias=False), nn.BatchNorm2d(4 * planes))
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = F.relu(self.bn2(self.conv2(out)))
+        out = self.bn3(self.conv3(out))
+        return F.relu(out + self.shortcut(x))
+
+
+class EagerResNet(nn.Module):
+    """reference: nbdt/models/resnet.py:115-149 with BasicBlock (:42-74) or Bottleneck (:77-112)."""
+
+    def __init__(self, depths=(2, 2, 2, 2), num_classes=10, bottleneck=False):
         super().__init__()
         self.conv1 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         cin = 64
+        exp = 4 if bottleneck else 1
         for i, (planes, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2))):
             blocks = []
             for s in [stride] + [1] * (depths[i] - 1):
-                blocks.append(_BasicBlock(cin, planes, s))
-                cin = planes
+                blocks.append(_Bottleneck(cin, planes, s) if bottleneck else _BasicBlock(cin, planes, s))
+                cin = planes * exp
             setattr(self, f"layer{i + 1}", nn.Sequential(*blocks))
-        self.linear = nn.Linear(512, num_classes)
+        self.linear = nn.Linear(512 * exp, num_classes)
 
     def forward(self, x):
         out = F.relu(self.bn1(self.conv1(x)))
@@ -153,6 +178,10 @@ class _PostActiv(nn.Module):
     def __init__(self, c):
         super().__init__()
         self.bn = nn.BatchNorm2d(c)
+
+
+def EagerResNet50(num_classes=10):
+    return EagerResNet(depths=(3, 4, 6, 3), num_classes=num_classes, bottleneck=True)
 
 
 class EagerWRN(nn.Module):

@@ -9,7 +9,7 @@ sys.path[:0] = [os.path.join(ROOT, "neural-backed-decision-trees_b200"), ROOT, o
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from test_parity_gpu import rel, train_step  # noqa: E402
+from test_parity_gpu import autocast_floor, rel, train_step  # noqa: E402
 
 out = {}
 for arch, golden in (("ResNet18", "backbone_resnet18.npz"), ("ResNet50", "backbone_resnet50.npz")):
@@ -24,6 +24,9 @@ for arch, golden in (("ResNet18", "backbone_resnet18.npz"), ("ResNet50", "backbo
                  "cos_grad_linear": cos(net.linear.weight.grad.double().cpu(), torch.as_tensor(g["grad_linear_weight"]).double()),
                  "cos_grad_conv1": cos(net.conv1.weight.grad.double().cpu(), torch.as_tensor(g["grad_conv1_weight"]).double()),
                  "batch": int(x.shape[0])}
+    fl, floss = autocast_floor(arch, g)
+    out[arch]["eager_bf16_autocast_logits_rel_of_scale"] = rel(fl.cpu(), g["train_logits"])
+    out[arch]["eager_bf16_autocast_loss_rel"] = abs(floss - float(g["train_loss"])) / abs(float(g["train_loss"]))
     if "eval_logits" in g.files:
         net.eval()
         with torch.no_grad():

@@ -41,7 +41,7 @@ def _make(dev):
     return net, crit, x, y
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlapped=False, graph=False):
     _setup_path()
     import torch.distributed as dist
     from nbdt._b200 import parallel
@@ -54,13 +54,39 @@ def _worker(rank, world, port, out):
     net, crit, x, y = _make(dev)
     parallel.broadcast_parameters(net)
     opt = FusedSGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
-    red = parallel.FlatGradientAllReduce(opt, world)
+    red = parallel.OverlappedGradientAllReduce(opt, world, pieces=4) if overlapped else parallel.FlatGradientAllReduce(opt, world)
+    if overlapped:
+        assert len(red.bounds) >= 2, red.bounds  # pieces were found (BatchNorm biases as triggers)
     crit.batch_rows = x.shape[0]
     lo, hi = parallel.shard_rows(x.shape[0], rank, world)
-    opt.zero_grad()
-    loss = crit(net(x[lo:hi].to(dev)), y[lo:hi].to(dev))
-    loss.backward()
-    red.reduce()
+    xs, ys = x[lo:hi].to(dev), y[lo:hi].to(dev)
+
+    def fwd_bwd():
+        opt.zero_grad()
+        loss = crit(net(xs), ys)
+        loss.backward()
+        red.reduce()   # overlapped: sends the head piece and joins the communication stream
+        return loss
+
+    if graph:  # the collectives are captured together with forward + backward
+        import gc
+
+        state = {k: v.clone() for k, v in net.state_dict().items()}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fwd_bwd()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        gc.collect()
+        net.load_state_dict(state)  # the warm-up step moved the BatchNorm running statistics
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            loss = fwd_bwd()
+        net.load_state_dict(state)
+        g.replay()
+    else:
+        loss = fwd_bwd()
     grad = opt.flat_grad.clone()
     opt.step()
     total = loss.detach().clone()
@@ -72,14 +98,15 @@ def _worker(rank, world, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_step_equals_sharded_single_process(tmp_path):
+@pytest.mark.parametrize("overlapped,graph", [(False, False), (True, False), (True, True)])
+def test_two_rank_step_equals_sharded_single_process(tmp_path, overlapped, graph):
     _setup_path()
     import torch.multiprocessing as mp
     from nbdt._b200 import parallel
     from nbdt._b200.optim import FusedSGD
 
     out = str(tmp_path / "rank0.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, overlapped, graph), nprocs=2, join=True)
     got = torch.load(out)
 
     dev = torch.device("cuda", 0)

@@ -195,3 +195,27 @@ def test_torch_port_resnet18_train_step(oracle_trees):
     net.eval()
     with torch.no_grad():
         np.testing.assert_allclose(net(x).numpy(), g["eval_logits_after_step"], rtol=1e-3, atol=1e-4)
+
+
+def test_eager_resnet50_pinned_to_reference_golden(oracle_trees):
+    """oracle/torch_port.EagerResNet50 (Bottleneck restatement) == the reference's ResNet50 on the seeded golden train step."""
+    import os
+    import torch
+    import torch.nn as nn
+    from conftest import GOLDEN
+    from oracle import torch_port as P
+
+    g = np.load(os.path.join(GOLDEN, "backbone_resnet50.npz"))
+    torch.manual_seed(0)
+    net = P.EagerResNet50(num_classes=10)
+    assert [k for k, _ in net.named_parameters()] == list(g["param_names"])
+    tree = oracle_trees["cifar10_induced_resnet18"]
+    x, y = torch.as_tensor(g["x"]), torch.as_tensor(g["y"])
+    net.train()
+    logits = net(x)
+    loss = P.soft_tree_sup_loss(tree, nn.CrossEntropyLoss(), logits, y)
+    loss.backward()
+    np.testing.assert_allclose(logits.detach().numpy(), g["train_logits"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(loss.item(), g["train_loss"], rtol=1e-5)
+    norms = np.array([float(p.grad.double().norm()) for p in net.parameters()])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=5e-3)
