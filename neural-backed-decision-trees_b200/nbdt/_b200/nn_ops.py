@@ -22,6 +22,9 @@ def _stream(t):
 # join_wgrad_streams() -- FusedSGD.step() and FlatGradientAllReduce.reduce() call it, code that reads .grad right after
 # backward() (gradient clipping, logging) must call it itself.  bench.py turns it on.
 _SIDE_STREAMS = {}
+# callables told about every convolution weight whose gradient kernel has just been enqueued into the optimizer's flat buffer
+# (autograd sees no gradient for those parameters, so no accumulate hook fires): the overlapped all-reduce listens here
+GRAD_WRITTEN_CALLBACKS = []
 _OVERLAP_WGRAD = os.environ.get("NBDT_B200_WGRAD_STREAM", "0") == "1"
 
 
@@ -107,6 +110,7 @@ class ConvFunction(torch.autograd.Function):
         ctx.save_for_backward(x, wpt)
         ctx.meta = (tuple(weight.shape), k, stride, residual is not None)
         ctx.direct_grad = weight.grad if getattr(weight, "_nbdt_direct_grad", False) else None
+        ctx.param = weight if ctx.direct_grad is not None else None
         return y
 
     @staticmethod
@@ -130,6 +134,9 @@ class ConvFunction(torch.autograd.Function):
                 C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride, real=wshape[:2]), wshape, out=ctx.direct_grad, accumulate=True)
             else:
                 dw = C.unpack_wgrad(C.conv_wgrad(x, dy, k, stride, real=wshape[:2]), wshape)
+            if ctx.param is not None:
+                for cb in GRAD_WRITTEN_CALLBACKS:
+                    cb(ctx.param)
         return dx, dw, None, (dy if has_res else None)
 
 

@@ -79,12 +79,14 @@ class FlatGradientAllReduce:
 class OverlappedGradientAllReduce:
     """The same sum, issued in a few contiguous pieces of the flat gradient buffer WHILE backward is still running.
 
-    Parameters sit in the flat buffer in definition order and backward finishes them back to front, so at any moment a tail of the
-    buffer is final.  A post-accumulate hook on a BatchNorm bias marks the moment everything behind it is complete: the piece
-    [offset after that bias, previous boundary) goes to NCCL on a communication stream that waits for the main stream (and the
-    weight-gradient side stream) at that point; `finish()` after backward sends the head piece and joins.  For WRN-28-10 the last
-    stage holds 71 % of the gradient bytes and is in flight before the first two stages have started their backward.
-    Everything is stream-ordered (events, no host sync), so it can be captured in a CUDA graph together with forward + backward.
+    Parameters sit in the flat buffer in definition order and backward finishes them roughly back to front.  Every parameter
+    reports once per backward that its gradient has been written -- a post-accumulate hook for the gradients autograd
+    accumulates (BatchNorm, classifier), a callback from ConvFunction.backward for the convolution weights, whose gradient kernel
+    adds straight into the flat buffer -- and a piece goes to NCCL as soon as all of its parameters (and all pieces behind it:
+    the collectives must be issued in the same order on every rank) have reported.  The communication stream waits for the main
+    stream and the weight-gradient side stream at that moment; `finish()` after backward sends whatever is left and joins.  For
+    WRN-28-10 the last stage holds 71 % of the gradient bytes and is in flight before the first two stages start their backward.
+    Everything is stream-ordered (no host sync), so it is captured in a CUDA graph together with forward + backward.
     Needs FusedSGD (flat buffer) and its zero_grad (which keeps every .grad a view of that buffer)."""
 
     def __init__(self, optimizer, world_size, pieces=4, bf16=False):
@@ -93,49 +95,73 @@ class OverlappedGradientAllReduce:
         self.bf16 = bf16
         self.stream = None
         self.pending = []
-        self.bounds = []       # element offsets of the piece boundaries, descending; the head piece [0, bounds[-1]) goes last
-        self._hooks = []
-        self._upper = None
+        self.issued = []       # (lower, upper) element ranges sent in the current step, in order
+        self.last_issued = []
         params = optimizer.param_groups[0]["params"]
         total = optimizer.flat_grad.numel()
         offs, off = [], 0
         for p in params:
             offs.append(off)
             off += p.numel()
-        if world_size > 1 and pieces > 1:
-            # candidate triggers: 1-D parameters directly followed by another parameter (BatchNorm bias: its hook fires after the layers
-            # behind it have finished); one per `total / pieces` elements, scanning from the back
-            want = [total * k // pieces for k in range(pieces - 1, 0, -1)]
-            cands = [i for i, p in enumerate(params) if p.dim() == 1 and i + 1 < len(params) and i > 0 and params[i - 1].dim() == 1]
-            for w in want:
-                best = min(cands, key=lambda i: abs(offs[i + 1] - w), default=None)
-                if best is not None and offs[best + 1] not in self.bounds and 0 < offs[best + 1] < total:
-                    self.bounds.append(offs[best + 1])
-                    self._hooks.append(params[best].register_post_accumulate_grad_hook(self._make_hook(offs[best + 1])))
-            self.bounds.sort(reverse=True)
+        # piece k = parameters [starts[k], starts[k+1]); cut where the running size passes k/pieces of the buffer
+        self.starts = [0]
+        if world_size > 1:
+            for k in range(1, max(1, pieces)):
+                want = total * k // pieces
+                i = min(range(len(params)), key=lambda j: abs(offs[j] - want))
+                if i > self.starts[-1]:
+                    self.starts.append(i)
+        self.piece_of = [0] * len(params)
+        for k, st in enumerate(self.starts):
+            for i in range(st, len(params)):
+                self.piece_of[i] = k
+        self.bounds = [offs[i] for i in self.starts[1:]][::-1]   # element offsets of the cuts, descending (for logs / tests)
+        self._elem = [offs[i] for i in self.starts] + [total]
+        self._index = {id(p): i for i, p in enumerate(params)}
+        self._reset()
+        self._hooks = []
+        if world_size > 1:
+            from . import nn_ops
 
-    def _make_hook(self, bound):
-        def hook(param):
-            self._issue(bound)
+            for i, p in enumerate(params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(lambda param, i=i: self._fired(i)))
+            nn_ops.GRAD_WRITTEN_CALLBACKS.append(self._param_written)
 
-        return hook
+    def _reset(self):
+        self._remaining = [0] * len(self.starts)
+        for k in self.piece_of:
+            self._remaining[k] += 1
+        self._seen = set()
+        self._next = len(self.starts) - 1   # pieces are issued back to front
 
-    def _issue(self, lower):
-        """all-reduce flat_grad[lower, upper) where upper is the previous boundary; ordered after everything enqueued so far."""
-        if self.world_size == 1:
+    def _param_written(self, param):
+        i = self._index.get(id(param))
+        if i is not None:
+            self._fired(i)
+
+    def _fired(self, i):
+        if self.world_size == 1 or i in self._seen:
             return
+        self._seen.add(i)
+        self._remaining[self.piece_of[i]] -= 1
+        while self._next > 0 and self._remaining[self._next] == 0:   # piece 0 (the head) always goes in finish()
+            self._issue(self._next)
+            self._next -= 1
+
+    def _issue(self, k):
+        """all-reduce piece k of the flat buffer, ordered after everything enqueued so far on the main and weight-gradient streams."""
         from .nn_ops import _SIDE_STREAMS
 
         flat = self.optimizer.flat_grad
-        upper = flat.numel() if self._upper is None else self._upper
-        if lower >= upper:
-            return
-        self._upper = lower
+        lower, upper = self._elem[k], self._elem[k + 1]
+        self.issued.append((lower, upper))
         dev = flat.device
+        if dev.type != "cuda":  # host tensors (gloo, the CPU test of the piece logic): nothing to overlap with
+            dist.all_reduce(flat[lower:upper], op=dist.ReduceOp.SUM)
+            return
         if self.stream is None:
             self.stream = torch.cuda.Stream(device=dev)
-        main = torch.cuda.current_stream(dev)
-        self.stream.wait_stream(main)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
         for key, st in _SIDE_STREAMS.items():
             if dev.index in (None, key):
                 self.stream.wait_stream(st)   # weight-gradient kernels of the finished layers
@@ -143,19 +169,23 @@ class OverlappedGradientAllReduce:
         with torch.cuda.stream(self.stream):
             if self.bf16:
                 low = piece.to(torch.bfloat16)
-                work = dist.all_reduce(low, op=dist.ReduceOp.SUM, async_op=True)
-                self.pending.append((work, piece, low))
+                self.pending.append((dist.all_reduce(low, op=dist.ReduceOp.SUM, async_op=True), piece, low))
             else:
-                work = dist.all_reduce(piece, op=dist.ReduceOp.SUM, async_op=True)
-                self.pending.append((work, piece, None))
+                self.pending.append((dist.all_reduce(piece, op=dist.ReduceOp.SUM, async_op=True), piece, None))
 
     def finish(self):
-        """After backward: send what is left (the head of the buffer), then make the current stream wait for every piece."""
+        """After backward: send what is left (at least the head of the buffer), then make the current stream wait for every piece."""
         if self.world_size == 1:
             return
         self.optimizer.assert_grads_are_views()
-        self._issue(0)
+        while self._next >= 0:   # parameters that got no gradient this step never report: their pieces go now
+            self._issue(self._next)
+            self._next -= 1
         dev = self.optimizer.flat_grad.device
+        self.last_issued, self.issued = self.issued, []
+        self._reset()
+        if dev.type != "cuda":
+            return
         for work, piece, low in self.pending:
             work.wait()
             if low is not None:
@@ -163,7 +193,6 @@ class OverlappedGradientAllReduce:
                     piece.copy_(low)
         torch.cuda.current_stream(dev).wait_stream(self.stream)
         self.pending = []
-        self._upper = None
 
     reduce = finish
 
