@@ -301,8 +301,13 @@ def run_b200(args, rank, world, local_rank):
     if world > 1:
         parallel.broadcast_parameters(net)
     opt = FusedSGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
-    # gradient all-reduce: in pieces during backward (captured in the CUDA graph with it) unless NBDT_B200_ALLREDUCE_OVERLAP=0
-    overlapped = world > 1 and os.environ.get("NBDT_B200_ALLREDUCE_OVERLAP", "1") != "0"
+    # gradient all-reduce: ONE collective on the flat buffer after backward.  NBDT_B200_ALLREDUCE_OVERLAP=1 sends it in pieces during
+    # backward instead (eager launches only: hooks issuing NCCL inside a CUDA-graph capture hang the watchdog).  Measured at N=2
+    # (profiles/r02_bench_n2_*.json): 18.92 ms/step for the single collective, 19.50 ms for four overlapped pieces -- NCCL's CTAs take
+    # SMs from the persistent convolution kernels for longer than the 0.5 ms of exposed all-reduce they hide.
+    overlapped = world > 1 and os.environ.get("NBDT_B200_ALLREDUCE_OVERLAP", "0") == "1"
+    if overlapped:
+        args.graph = False
     reducer = None
     if world > 1:
         reducer = (parallel.OverlappedGradientAllReduce(opt, world, pieces=int(os.environ.get("NBDT_B200_ALLREDUCE_PIECES", "4")),
