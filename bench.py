@@ -333,6 +333,7 @@ def run_b200(args, rank, world, local_rank):
             tree_ev.append((e0, e1))
         loss.backward()
         nn_ops.join_wgrad_streams(dev)  # weight-gradient kernels run on a side stream: join before capture ends / SGD
+        opt.flush_grads()               # packed convolution gradients -> flat gradient buffer, one launch (inside the captured region)
         if overlapped:
             reducer.finish()  # the pieces were sent from autograd hooks while backward ran; send the head, join the comm stream
         return loss

@@ -151,6 +151,14 @@ int nbdt_conv_pack_weights(const float* w_oihw, void* wpack, void* wpack_t, int 
 int nbdt_conv_unpack_wgrad(const float* dwp, float* dw_oihw, int Cout, int Cin, int cout_pad, int cin_pad,
                            int ksize, int accumulate, void* stream);
 
+/* The same two conversions for EVERY convolution layer of a network in one launch each (one pack and one unpack launch per train step
+ * instead of one per layer).  jobs_device: device array of njobs x 8 int64:
+ *   pack:   {w_oihw, wpack, wpack_t, Cout, Cin, cout_pad, cin_pad, taps | first_tile << 32}, tiles = ceil(cin_pad/32) * ceil(cout_pad/32)
+ *   unpack: {dw_oihw (accumulated into), dwp, 0, Cout, Cin, cout_pad, cin_pad, taps | first_tile << 32}, tiles = ceil(Cin/32) * ceil(Cout/32)
+ * first_tile = running sum of the previous jobs' tile counts, total_tiles = the sum over all jobs. */
+int nbdt_conv_pack_weights_batch(const void* jobs_device, int njobs, int total_tiles, void* stream);
+int nbdt_conv_unpack_wgrad_batch(const void* jobs_device, int njobs, int total_tiles, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Backbone: memory-bound kernels around the convolutions (csrc/bn_ops.cu).  Activations bf16 [M][C]
  * (M = N*H*W rows of an NHWC tensor), parameters / statistics fp32.  They replace nn.BatchNorm2d,

@@ -1271,13 +1271,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ 
 // (0.76 ms per step for 2 x 27 launches, profiles/r01_bench_launches_v3.md).
 constexpr int kPackTile = 32;
 
-__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
-                                                           __nv_bfloat16* __restrict__ wpt, int Cout, int Cin,
-                                                           int cin_pad, int cout_pad, int taps) {
+__device__ __forceinline__ void pack_weights_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                  __nv_bfloat16* __restrict__ wpt, int Cout, int Cin, int cin_pad, int cout_pad, int taps,
+                                                  int bx, int by) {
   // w: [Cout][Cin][taps] (OIHW);  wp: [taps][cout_pad][cin_pad];  wpt: [taps][cin_pad][cout_pad]  (zero padded)
   extern __shared__ float tile[];  // [32 co][32 * taps + 1]
   const int row_len = kPackTile * taps + 1;
-  const int ci0 = blockIdx.x * kPackTile, co0 = blockIdx.y * kPackTile;
+  const int ci0 = bx * kPackTile, co0 = by * kPackTile;
   const int per_row = kPackTile * taps;
   for (int i = threadIdx.x; i < kPackTile * per_row; i += blockDim.x) {
     const int co_l = i / per_row, rem = i - co_l * per_row;
@@ -1304,12 +1304,31 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout,
-                                                           int Cin, int cin_pad, int cout_pad, int taps, int accumulate) {
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp,
+                                                           __nv_bfloat16* __restrict__ wpt, int Cout, int Cin,
+                                                           int cin_pad, int cout_pad, int taps) {
+  pack_weights_tile(w, wp, wpt, Cout, Cin, cin_pad, cout_pad, taps, blockIdx.x, blockIdx.y);
+}
+
+// One launch for every convolution layer of the network (instead of one per layer: 28 + 28 small launches per WRN-28-10 step were
+// launch-latency bound, 1.3 ms).  job = 8 x int64: {fp32 OIHW tensor, packed tensor 0, packed tensor 1, Cout, Cin, cout_pad, cin_pad,
+// taps | first tile << 32}; tiles of a job: (cin tiles) x (cout tiles), numbered x-major from `first tile`.
+struct PackJob { long long a, b, c, Cout, Cin, cout_pad, cin_pad, taps_first; };
+__device__ __forceinline__ const PackJob& find_job(const PackJob* __restrict__ jobs, int njobs, int tile_id) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {  // last job whose first tile <= tile_id
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int)(jobs[mid].taps_first >> 32) <= tile_id) lo = mid; else hi = mid - 1;
+  }
+  return jobs[lo];
+}
+
+__device__ __forceinline__ void unpack_wgrad_tile(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin, int cin_pad,
+                                                  int cout_pad, int taps, int accumulate, int bx, int by) {
   // dwp: [taps][cout_pad][cin_pad] fp32  ->  dw: [Cout][Cin][taps] (OIHW)
   extern __shared__ float tile[];  // [32 co][32 * taps + 1]
   const int row_len = kPackTile * taps + 1;
-  const int ci0 = blockIdx.x * kPackTile, co0 = blockIdx.y * kPackTile;
+  const int ci0 = bx * kPackTile, co0 = by * kPackTile;
   const int n = kPackTile * kPackTile * taps;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int ci_l = i % kPackTile, co_l = (i / kPackTile) % kPackTile, tp = i / (kPackTile * kPackTile);
@@ -1328,6 +1347,27 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
       *dst = accumulate ? *dst + v : v;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout,
+                                                           int Cin, int cin_pad, int cout_pad, int taps, int accumulate) {
+  unpack_wgrad_tile(dwp, dw, Cout, Cin, cin_pad, cout_pad, taps, accumulate, blockIdx.x, blockIdx.y);
+}
+
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  const PackJob& j = find_job(jobs, njobs, blockIdx.x);
+  const int local = blockIdx.x - (int)(j.taps_first >> 32);
+  const int tx = ((int)j.cin_pad + kPackTile - 1) / kPackTile;
+  pack_weights_tile(reinterpret_cast<const float*>(j.a), reinterpret_cast<__nv_bfloat16*>(j.b), reinterpret_cast<__nv_bfloat16*>(j.c),
+                    (int)j.Cout, (int)j.Cin, (int)j.cin_pad, (int)j.cout_pad, (int)(j.taps_first & 0xffffffff), local % tx, local / tx);
+}
+
+__global__ void __launch_bounds__(256) unpack_wgrad_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  const PackJob& j = find_job(jobs, njobs, blockIdx.x);
+  const int local = blockIdx.x - (int)(j.taps_first >> 32);
+  const int tx = ((int)j.Cin + kPackTile - 1) / kPackTile;
+  unpack_wgrad_tile(reinterpret_cast<const float*>(j.b), reinterpret_cast<float*>(j.a), (int)j.Cout, (int)j.Cin, (int)j.cin_pad,
+                    (int)j.cout_pad, (int)(j.taps_first & 0xffffffff), 1, local % tx, local / tx);
 }
 
 }  // namespace
@@ -1564,6 +1604,29 @@ int nbdt_conv_unpack_wgrad(const float* dwp, float* dw_oihw, int Cout, int Cin, 
   const dim3 grid((Cin + kPackTile - 1) / kPackTile, (Cout + kPackTile - 1) / kPackTile);
   unpack_wgrad_kernel<<<grid, 256, kPackTile * (kPackTile * taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
       dwp, dw_oihw, Cout, Cin, cin_pad, cout_pad, taps, accumulate);
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+// Batched forms over a device table of jobs (8 x int64 each, see PackJob): total_tiles = sum of the jobs' tile counts.
+// pack: job = {w_oihw, wpack, wpack_t, Cout, Cin, cout_pad, cin_pad, taps | first_tile << 32}, tiles over (cin_pad, cout_pad);
+// unpack (accumulating): job = {dw_oihw, dwp, 0, ...}, tiles over (Cin, Cout).
+int nbdt_conv_pack_weights_batch(const void* jobs_device, int njobs, int total_tiles, void* stream) {
+  NBDT_REQUIRE(njobs >= 0 && total_tiles >= 0, "negative count");
+  if (njobs == 0 || total_tiles == 0) return NBDT_OK;
+  NBDT_REQUIRE(jobs_device != nullptr, "NULL job table");
+  pack_weights_batch_kernel<<<total_tiles, 256, kPackTile * (kPackTile * 9 + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const PackJob*>(jobs_device), njobs);
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+int nbdt_conv_unpack_wgrad_batch(const void* jobs_device, int njobs, int total_tiles, void* stream) {
+  NBDT_REQUIRE(njobs >= 0 && total_tiles >= 0, "negative count");
+  if (njobs == 0 || total_tiles == 0) return NBDT_OK;
+  NBDT_REQUIRE(jobs_device != nullptr, "NULL job table");
+  unpack_wgrad_batch_kernel<<<total_tiles, 256, kPackTile * (kPackTile * 9 + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      reinterpret_cast<const PackJob*>(jobs_device), njobs);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }

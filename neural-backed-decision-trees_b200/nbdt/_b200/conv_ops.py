@@ -91,14 +91,15 @@ def conv_dgrad(dy, wpt, in_hw, ksize, stride, accumulate=None, real=None):
     return dx
 
 
-def conv_wgrad(x, dy, ksize, stride, real=None):
-    """fp32 [taps][Cout][Cin] weight gradient (padded channel counts, as the activations carry them)."""
+def conv_wgrad(x, dy, ksize, stride, real=None, out=None):
+    """fp32 [taps][Cout][Cin] weight gradient (padded channel counts, as the activations carry them); `out`: buffer to overwrite."""
     _check_act(x, "conv_wgrad x")
     _check_act(dy, "conv_wgrad dy")
     N, H, W, cin = x.shape
     cout = dy.shape[3]
     assert dy.shape == (N, H // stride, W // stride, cout)
-    dwp = torch.empty((ksize * ksize, cout, cin), dtype=torch.float32, device=x.device)
+    dwp = out if out is not None else torch.empty((ksize * ksize, cout, cin), dtype=torch.float32, device=x.device)
+    assert dwp.shape == (ksize * ksize, cout, cin) and dwp.dtype == torch.float32 and dwp.is_contiguous()
     flops = 2.0 * dy.numel() * cin * ksize * ksize if real is None else 2.0 * N * (H // stride) * (W // stride) * real[0] * real[1] * ksize * ksize
     with torch.cuda.device(x.device), _timed("wgrad", flops):
         L.check(L.load().nbdt_conv2d_wgrad(_p(x), _p(dy), _p(dwp), N, H, W, cin, cout, ksize, stride,
@@ -118,3 +119,104 @@ def unpack_wgrad(dwp, weight_shape, out=None, accumulate=False):
                                                 L.stream_ptr(dwp.device)))
     _count()
     return out
+
+
+class ConvWeightBank:
+    """Persistent packed forms of every convolution weight a FusedSGD owns, maintained with ONE launch per step each way:
+
+      * bf16 tap-major matrices wp / wpt (what the tcgen05 kernels read), re-packed from the fp32 master weights by
+        nbdt_conv_pack_weights_batch at the first convolution of the next forward after an optimizer step;
+      * fp32 tap-major gradient buffers the weight-gradient kernels overwrite, added into the optimizer's flat (OIHW) gradient
+        buffer by nbdt_conv_unpack_wgrad_batch when the gradients are needed (all-reduce / optimizer step / flush()).
+
+    Before: one pack and one unpack launch per layer per step -- 56 launch-bound kernels, 1.3 ms of a WRN-28-10 step
+    (profiles/r01_bench_launches_final.md)."""
+
+    def __init__(self):
+        self.entries = {}      # (id(param), cin_pad, cout_pad) -> dict
+        self.valid = False     # packed copies match the master weights
+        self.pending = []      # entries whose gradient buffer holds a not yet unpacked gradient
+        self.defer_unpack = True
+        self._pack_table = None
+        self._unpack_tables = {}
+
+    @staticmethod
+    def _table(rows, device):
+        return torch.tensor(rows, dtype=torch.int64, device=device)
+
+    def _entry(self, weight, cin_pad, cout_pad):
+        key = (id(weight), cin_pad, cout_pad)
+        e = self.entries.get(key)
+        if e is None:
+            cout, cin, k, _ = weight.shape
+            dev = weight.device
+            e = self.entries[key] = dict(
+                key=key, weight=weight, shape=(cout, cin, k), pads=(cout_pad, cin_pad),
+                wp=torch.zeros((k * k, cout_pad, cin_pad), dtype=torch.bfloat16, device=dev),
+                wpt=torch.zeros((k * k, cin_pad, cout_pad), dtype=torch.bfloat16, device=dev),
+                dwp=torch.zeros((k * k, cout_pad, cin_pad), dtype=torch.float32, device=dev))
+            self._pack_table = None
+            self.valid = False
+        return e
+
+    def packed(self, weight, cin_pad, cout_pad):
+        e = self._entry(weight, cin_pad, cout_pad)
+        if not self.valid:
+            self._pack_all(weight.device)
+        return e["wp"], e["wpt"]
+
+    def _pack_all(self, device):
+        if self._pack_table is None:
+            rows, first = [], 0
+            for e in self.entries.values():
+                cout, cin, k = e["shape"]
+                cout_pad, cin_pad = e["pads"]
+                rows.append([e["weight"].data_ptr(), e["wp"].data_ptr(), e["wpt"].data_ptr(), cout, cin, cout_pad, cin_pad, (k * k) | (first << 32)])
+                first += ((cin_pad + 31) // 32) * ((cout_pad + 31) // 32)
+            self._pack_table = (self._table(rows, device), len(rows), first)
+        tab, n, tiles = self._pack_table
+        with torch.cuda.device(device):
+            L.check(L.load().nbdt_conv_pack_weights_batch(_p(tab), n, tiles, L.stream_ptr(device)))
+        _count()
+        self.valid = True
+
+    def invalidate(self):
+        """The master weights changed (optimizer step, load_state_dict): re-pack at the next forward."""
+        self.valid = False
+
+    def grad_buffer(self, weight, cin_pad, cout_pad):
+        e = self._entry(weight, cin_pad, cout_pad)
+        if any(p is e for p in self.pending):
+            self.flush()  # a second backward before the first gradient was consumed (gradient accumulation)
+        self.pending.append(e)
+        return e["dwp"]
+
+    def discard(self):
+        self.pending = []
+
+    def flush(self):
+        """Add every pending packed gradient into its parameter's .grad (the optimizer's flat buffer)."""
+        if not self.pending:
+            return
+        from .nn_ops import join_wgrad_streams
+
+        dev = self.pending[0]["weight"].device
+        join_wgrad_streams(dev)
+        key = tuple(e["key"] for e in self.pending)
+        cached = self._unpack_tables.get(key)
+        if cached is None or any(e["weight"].grad is None or e["weight"].grad.data_ptr() != g for e, g in zip(self.pending, cached[3])):
+            rows, first, gptrs = [], 0, []
+            for e in self.pending:
+                cout, cin, k = e["shape"]
+                cout_pad, cin_pad = e["pads"]
+                if e["weight"].grad is None:
+                    e["weight"].grad = torch.zeros_like(e["weight"])
+                gptrs.append(e["weight"].grad.data_ptr())
+                rows.append([gptrs[-1], e["dwp"].data_ptr(), 0, cout, cin, cout_pad, cin_pad, (k * k) | (first << 32)])
+                first += ((cin + 31) // 32) * ((cout + 31) // 32)
+            cached = self._unpack_tables[key] = (self._table(rows, dev), len(rows), first, gptrs)
+        tab, n, tiles, _ = cached
+        with torch.cuda.device(dev):
+            L.check(L.load().nbdt_conv_unpack_wgrad_batch(_p(tab), n, tiles, L.stream_ptr(dev)))
+        _count()
+        self.pending = []

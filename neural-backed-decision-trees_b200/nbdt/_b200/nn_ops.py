@@ -105,12 +105,18 @@ class ConvFunction(torch.autograd.Function):
         assert cin_phys >= cin
         # output channels the GEMM tiles can cover (multiples of 64 / 128 / 160); others are zero-padded to 64s
         cout_phys = cout if (cout % 64 == 0 or cout % 160 == 0) else C.pad64(cout)
-        wp, wpt = C.pack_weights(weight, cin_pad=cin_phys, cout_pad=cout_phys)
+        bank = getattr(weight, "_nbdt_bank", None)
+        if bank is not None:  # persistent packed copies, refreshed by one launch per optimizer step
+            wp, wpt = bank.packed(weight, cin_phys, cout_phys)
+        else:
+            wp, wpt = C.pack_weights(weight, cin_pad=cin_phys, cout_pad=cout_phys)
         y = C.conv_fwd(x, wp, k, stride, residual, real=(cout, cin))
         ctx.save_for_backward(x, wpt)
         ctx.meta = (tuple(weight.shape), k, stride, residual is not None)
         ctx.direct_grad = weight.grad if getattr(weight, "_nbdt_direct_grad", False) else None
         ctx.param = weight if ctx.direct_grad is not None else None
+        ctx.bank = bank if (bank is not None and ctx.direct_grad is not None and bank.defer_unpack) else None
+        ctx.pads = (cin_phys, cout_phys)
         return y
 
     @staticmethod
@@ -122,7 +128,20 @@ class ConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = C.conv_dgrad(dy, wpt, (x.shape[1], x.shape[2]), k, stride, real=wshape[:2])
         if ctx.needs_input_grad[1]:
-            if ctx.direct_grad is not None and _OVERLAP_WGRAD:
+            if ctx.bank is not None:
+                # the gradient kernel overwrites the layer's persistent tap-major buffer; ConvWeightBank.flush() adds all of them
+                # into the flat gradient buffer with one launch when they are needed (all-reduce / optimizer step)
+                dwp = ctx.bank.grad_buffer(ctx.param, *ctx.pads)
+                if _OVERLAP_WGRAD:
+                    main, side = torch.cuda.current_stream(x.device), wgrad_stream(x.device)
+                    side.wait_stream(main)  # x and dy are complete on the main stream at this point
+                    with torch.cuda.stream(side):
+                        C.conv_wgrad(x, dy, k, stride, real=wshape[:2], out=dwp)
+                    x.record_stream(side)
+                    dy.record_stream(side)
+                else:
+                    C.conv_wgrad(x, dy, k, stride, real=wshape[:2], out=dwp)
+            elif ctx.direct_grad is not None and _OVERLAP_WGRAD:
                 main, side = torch.cuda.current_stream(x.device), wgrad_stream(x.device)
                 side.wait_stream(main)  # x and dy are complete on the main stream at this point
                 with torch.cuda.stream(side):

@@ -34,11 +34,24 @@ class FusedSGD(torch.optim.Optimizer):
             p.grad = self.flat_grad[off:off + n].view_as(p)
             p._nbdt_direct_grad = True  # conv weight gradients are accumulated into the flat buffer by the kernel
             off += n
+        # packed bf16 copies / packed gradient buffers of the convolution weights: one pack and one unpack launch per step
+        from .conv_ops import ConvWeightBank
+
+        self.bank = ConvWeightBank()
+        for p in ps:
+            if p.dim() == 4:
+                p._nbdt_bank = self.bank
         self._steps = 0
         self.grad_scale = 1.0
 
+    def flush_grads(self):
+        """Make every .grad complete: the convolution weight gradients sit in packed per-layer buffers until they are needed.
+        step() and the gradient all-reduce call this; code that reads .grad right after backward() must call it itself."""
+        self.bank.flush()
+
     def zero_grad(self, set_to_none=False):
         # gradients live in the flat buffer: keep the views, clear the storage with one memset
+        self.bank.discard()
         self.flat_grad.zero_()
         off = 0
         for p in self.param_groups[0]["params"]:
@@ -82,6 +95,7 @@ class FusedSGD(torch.optim.Optimizer):
         mom = state_dict.pop("nbdt_flat_momentum", None)
         steps = state_dict.pop("nbdt_steps", None)
         super().load_state_dict(state_dict)
+        self.bank.invalidate()
         if mom is not None:
             self.flat_momentum.copy_(mom.to(self.flat_momentum.device))
         if steps is not None:
@@ -92,6 +106,7 @@ class FusedSGD(torch.optim.Optimizer):
         loss = closure() if closure is not None else None
         g = self.param_groups[0]
         self.reseat_grads()
+        self.bank.flush()
         from .nn_ops import join_wgrad_streams
 
         join_wgrad_streams(self.flat_param.device)  # weight-gradient kernels run on a side stream
@@ -101,5 +116,6 @@ class FusedSGD(torch.optim.Optimizer):
                                            float(g["weight_decay"]), float(self.grad_scale), int(self._steps == 0),
                                            L.stream_ptr(self.flat_param.device)))
         _count()
+        self.bank.invalidate()  # the master weights changed: the packed bf16 copies are re-made at the next forward
         self._steps += 1
         return loss

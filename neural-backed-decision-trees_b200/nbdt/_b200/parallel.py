@@ -73,6 +73,8 @@ class FlatGradientAllReduce:
 
             self.optimizer.reseat_grads()  # a .grad that autograd replaced (zero_grad(set_to_none=True)) goes back into the flat buffer first
             join_wgrad_streams(self.optimizer.flat_grad.device)  # weight gradients are written on a side stream
+            if hasattr(self.optimizer, "flush_grads"):
+                self.optimizer.flush_grads()  # packed convolution gradients -> flat buffer (one launch)
             dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
 
 
@@ -126,6 +128,8 @@ class OverlappedGradientAllReduce:
             for i, p in enumerate(params):
                 self._hooks.append(p.register_post_accumulate_grad_hook(lambda param, i=i: self._fired(i)))
             nn_ops.GRAD_WRITTEN_CALLBACKS.append(self._param_written)
+            if hasattr(optimizer, "bank"):
+                optimizer.bank.defer_unpack = False  # pieces go out during backward: every layer adds its gradient into the flat buffer at once
 
     def _reset(self):
         self._remaining = [0] * len(self.starts)

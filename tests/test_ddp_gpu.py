@@ -124,6 +124,7 @@ def test_two_rank_step_equals_sharded_single_process(tmp_path, overlapped, graph
         loss = crit(net(x[lo:hi].to(dev)), y[lo:hi].to(dev))
         loss.backward()
         losses.append(loss.detach())
+        opt.flush_grads()  # packed convolution gradients -> flat buffer (step() / the all-reduce do this themselves)
     grad = opt.flat_grad.clone().cpu()
     assert torch.allclose(got["loss"], (losses[0] + losses[1]).cpu(), rtol=1e-4)
     cos = torch.nn.functional.cosine_similarity(got["grad"].double(), grad.double(), dim=0)
