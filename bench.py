@@ -71,7 +71,7 @@ def saturating_tree_point(tree, kind, classes, dtype):
     r = time_point(tree, kind, rows, classes, dtype, iters=12, warmup=3)
     name = L.load().nbdt_tree_kernel_variant(tree.device_tree(torch.device("cuda", torch.cuda.current_device())).handle).decode()
     return {"rows": rows, "classes": classes, "dtype": r["dtype"], "kind": kind, "ms": r["ms"], "alg_bytes": r["alg_bytes"], "gbs": r["gbs"],
-            "kernel": name or "table-driven (tree.cu / tree_v2.cu)", "l2": r["l2"], "measured": "in this run (CUDA events, 12 back-to-back launches)"}
+            "kernel": name, "l2": r["l2"], "measured": "in this run (CUDA events, 12 back-to-back launches)"}
 
 
 def usable_cores():
@@ -493,7 +493,7 @@ def run_b200(args, rank, world, local_rank):
         sat = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
     from nbdt._b200 import lib as L_
 
-    tree_kernel = L_.load().nbdt_tree_kernel_variant(crit.tree.device_tree(dev).handle).decode() or "tree_spec (AOT) / table-driven"
+    tree_kernel = L_.load().nbdt_tree_kernel_variant(crit.tree.device_tree(dev).handle).decode()
     conv_flops = sum(v[0] for v in conv_stats.values())
     conv_ms = sum(v[1] for v in conv_stats.values())
     conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0

@@ -27,6 +27,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -432,7 +433,8 @@ struct nbdt_tree {
   int force_g;  // env NBDT_B200_TREE_G (0 = heuristic)
   const SpecEntry* spec;  // hierarchy-specialised straight-line kernels, when generated for this tree
   TreeV2* v2;             // second-generation generic kernel (tree_v2.cu) for the loss / soft-forward modes
-  TreeJit* jit;           // run-time compiled straight-line kernels (tree_jit.cu), any hierarchy up to 256 leaves
+  TreeJit* jit;           // run-time compiled straight-line kernels (tree_jit.cu), any hierarchy up to 1536 leaves
+  mutable char last_kernel[96];  // kernel family of the last soft-forward / loss launch (bench lines, tests)
 };
 
 namespace {
@@ -527,12 +529,14 @@ int launch(const nbdt_tree* t, int dtype, const Params& p, cudaStream_t stream) 
   if (MODE == kSoftLoss) rc = try_launch_spec(t, kSpecSoftLoss, dtype, p, stream);
   if (MODE == kHardLoss) rc = try_launch_spec(t, kSpecHardLoss, dtype, p, stream);
   if (MODE == kSoftFwd) rc = try_launch_spec(t, kSpecSoftFwd, dtype, p, stream);
+  int which = rc >= 0 ? 1 : 0;  // 1 build-time specialised, 2 run-time specialised, 3 tree_v2, 0 generic
   if (rc < 0 && t->jit && !t->force_g && (MODE == kSoftLoss || MODE == kHardLoss || MODE == kSoftFwd)) {
     SpecParams sp;
     sp.x = p.x; sp.B = p.B; sp.ld = p.ld; sp.targets = p.targets; sp.class_probs = p.class_probs; sp.loss = p.loss;
     sp.grad = p.grad; sp.w_xent = p.w_xent; sp.w_tree = p.w_tree; sp.inv_rows = p.inv_rows; sp.grad_scale = p.grad_scale;
     rc = tree_jit_launch(t->jit, MODE == kSoftLoss ? kSpecSoftLoss : (MODE == kHardLoss ? kSpecHardLoss : kSpecSoftFwd),
                          dtype, sp, stream);
+    if (rc >= 0) which = 2;
   }
   if (rc < 0 && t->v2 && !t->force_g && (MODE == kSoftLoss || MODE == kHardLoss || MODE == kSoftFwd)) {
     SpecParams sp;
@@ -542,9 +546,13 @@ int launch(const nbdt_tree* t, int dtype, const Params& p, cudaStream_t stream) 
                         dtype, sp, stream);
   }
   if (rc >= 0) {
+    if (which == 1) snprintf(t->last_kernel, sizeof t->last_kernel, "tree_spec_%016llx (build-time generated, <= 24 leaves)", t->spec ? t->spec->hash : 0ull);
+    else if (which == 2) snprintf(t->last_kernel, sizeof t->last_kernel, "%s", tree_jit_last_variant(t->jit));
+    else snprintf(t->last_kernel, sizeof t->last_kernel, "tree_v2_kernel (table-driven)");
     if (cur != t->device) cudaSetDevice(cur);
     return rc;
   }
+  snprintf(t->last_kernel, sizeof t->last_kernel, "tree_kernel (table-driven)");
   switch (dtype) {
     case NBDT_F32: rc = launch_t<MODE, float>(t, p, stream); break;
     case NBDT_BF16: rc = launch_t<MODE, __nv_bfloat16>(t, p, stream); break;
@@ -710,6 +718,7 @@ int nbdt_tree_create(const nbdt_tree_desc* d, int device, nbdt_tree** out) {
   }
   t->v2 = nullptr;
   t->jit = nullptr;
+  t->last_kernel[0] = 0;
   if (!getenv("NBDT_B200_TREE_GENERIC"))
     if (int rc3 = tree_jit_create(d, device, t->sm_count, t->max_smem, &t->jit)) {
       nbdt_tree_destroy(t);
@@ -739,7 +748,7 @@ void nbdt_tree_destroy(nbdt_tree* t) {
 
 int nbdt_tree_max_depth(const nbdt_tree* t) { return t ? t->dev.Dmax : -1; }
 int nbdt_tree_num_slots(const nbdt_tree* t) { return t ? t->dev.S : -1; }
-const char* nbdt_tree_kernel_variant(const nbdt_tree* t) { return t ? tree_jit_last_variant(t->jit) : ""; }
+const char* nbdt_tree_kernel_variant(const nbdt_tree* t) { return t ? t->last_kernel : ""; }
 
 int nbdt_soft_forward(const nbdt_tree* tree, const void* logits, int dtype, int64_t B, int64_t ld,
                       float* class_probs, void* stream) {

@@ -356,7 +356,7 @@ def test_specialised_kernel_is_the_one_that_runs(case, structure):
     tree = case_tree(structure, case)
     ops.tree_loss(tree, t(g["logits"]), t(g["targets"], torch.int64), "soft", 1.0, 1.0)
     name = L.load().nbdt_tree_kernel_variant(tree.device_tree(torch.device(DEV)).handle).decode()
-    assert name.startswith("ka") and "_m0_t0_" in name, name
+    assert name.startswith("ka") and "_m0_t0_" in name, name   # "ka<generator version>_<hierarchy hash>_m<mode>_t<dtype>_...": csrc/tree_jit.cu
 
 
 def test_unseen_hierarchy_is_compiled_at_run_time(tmp_path):
