@@ -94,25 +94,40 @@ def _precompile_one(job):
     return name, mode, dtype, rc, (lib.nbdt_last_error() or b"").decode() if rc else ""
 
 
+def _precompile_jobs():
+    return [(name, C, ptr, nodes, root, mode, dtype) for name, C, ptr, nodes, root in _shipped_descs() if 2 <= C <= 1536
+            for mode in (0, 1, 2) for dtype in (0, 1, 2)]
+
+
+def _precompile_shard(index, count, verbose=False):
+    """Compile jobs[index::count] in this process; the number that failed is the exit status of the worker."""
+    failed = 0
+    for job in _precompile_jobs()[index::count]:
+        name, mode, dtype, rc, err = _precompile_one(job)
+        if rc != 0:
+            failed += 1
+            sys.stderr.write(f"tree JIT precompile failed for {name} mode {mode} dtype {dtype}: {err}\n")
+        elif verbose:
+            sys.stderr.write(f"tree JIT precompiled {name} mode {mode} dtype {dtype}\n")
+    return failed
+
+
 def precompile_tree_kernels(verbose=False):
     """Populate lib/tree_cache/ with the run-time-specialised tree kernels (csrc/tree_jit.cu) of every shipped hierarchy with
     at most 1536 leaves: soft loss, hard loss, soft forward x fp32, bf16, fp16.  NVRTC needs no GPU.  Any other hierarchy is
-    compiled on first use at run time; this only moves the few seconds per kernel to build time."""
-    from concurrent.futures import ProcessPoolExecutor
-
-    jobs = [(name, C, ptr, nodes, root, mode, dtype) for name, C, ptr, nodes, root in _shipped_descs() if 2 <= C <= 1536
-            for mode in (0, 1, 2) for dtype in (0, 1, 2)]
+    compiled on first use at run time; this only moves the few seconds per kernel to build time.  The work is sharded over
+    worker processes started from this file by path, so it does not matter how the caller imported it."""
+    total = len(_precompile_jobs())
+    count = max(1, min(8, os.cpu_count() or 1))
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--precompile-shard", str(i), str(count)]
+                              + (["--verbose"] if verbose else [])) for i in range(count)]
     failed = 0
-    with ProcessPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        for name, mode, dtype, rc, err in ex.map(_precompile_one, jobs):
-            if rc != 0:
-                failed += 1
-                sys.stderr.write(f"tree JIT precompile failed for {name} mode {mode} dtype {dtype}: {err}\n")
-            elif verbose:
-                sys.stderr.write(f"tree JIT precompiled {name} mode {mode} dtype {dtype}\n")
+    for p in procs:
+        rc = p.wait()
+        failed += rc if 0 <= rc < 250 else total // count  # a crashed worker counts as its whole shard
     if failed:
-        sys.stderr.write(f"{failed} of {len(jobs)} tree kernels were not precompiled (they compile at first use instead)\n")
-    return len(jobs) - failed
+        sys.stderr.write(f"{failed} of {total} tree kernels were not precompiled (they compile at first use instead)\n")
+    return total - failed
 
 
 def build(force=False, verbose=False, precompile=True):
@@ -155,4 +170,7 @@ def _build_lib(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--precompile-shard" in sys.argv:
+        at = sys.argv.index("--precompile-shard")
+        sys.exit(min(249, _precompile_shard(int(sys.argv[at + 1]), int(sys.argv[at + 2]), "--verbose" in sys.argv)))
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, precompile="--no-precompile" not in sys.argv))
