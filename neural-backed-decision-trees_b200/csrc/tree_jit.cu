@@ -70,7 +70,9 @@ struct Knobs {
   int maxld = 24;             // NBDT_B200_KA_MAXLD: 16-byte loads a lane keeps in flight in sweep A before their stores
   int fence = 8;              // NBDT_B200_KA_FENCE: nodes between scheduling fences of the straight-line passes (0 = none)
   int warps = 0;              // NBDT_B200_KA_WARPS: warps per row block (0 = by leaf count)
-  bool is_default() const { return regcap == kRegValueCap && minb == 0 && unroll == 8 && prefetch == 0 && maxld == 24 && fence == 8 && warps == 0; }
+  int expm = 0;               // NBDT_B200_KA_EXPMUFU: exp(class probability) as one FMUL + MUFU.EX2 instead of the degree-6 polynomial
+                              //   (6 FFMA): bit 0 in the Z traversal, bit 1 in the gradient traversal
+  bool is_default() const { return regcap == kRegValueCap && minb == 0 && unroll == 8 && prefetch == 0 && maxld == 24 && fence == 8 && warps == 0 && expm == 0; }
 };
 Knobs read_knobs() {
   Knobs k;
@@ -82,6 +84,7 @@ Knobs read_knobs() {
   k.maxld = std::max(1, std::min(64, geti("NBDT_B200_KA_MAXLD", k.maxld)));
   k.fence = std::max(0, geti("NBDT_B200_KA_FENCE", k.fence));
   k.warps = std::max(0, std::min(16, geti("NBDT_B200_KA_WARPS", k.warps)));
+  k.expm = std::max(0, std::min(3, geti("NBDT_B200_KA_EXPMUFU", k.expm)));
   return k;
 }
 
@@ -273,6 +276,7 @@ KA_DEV float exp01(float t) {
   r = fmaf(r, t, 0.9999963045120239f);
   return fmaf(r, t, 1.0f);
 }
+KA_DEV float exp01m(float t) { return ex2(t * 1.4426950408889634f); }  // the same on the MUFU pipe (2 ulp)
 // smaller child probability of a binary node with the sign bit set when it belongs to the SECOND child
 // (t = node logit of the first child minus that of the second, in log2 units)
 KA_DEV float signed_lo(float t) {
@@ -481,7 +485,7 @@ struct Gen {
       stx(c, std::string(pre) + std::to_string(c));
       note(std::string(pre) + std::to_string(c));
     } else {
-      o.f("    { const float e = exp01(%s%d); z2%d += e; pry = (posy == %d) ? %s%d : pry; }", pre, c, acc & 3, t.pos[c], pre, c);
+      o.f("    { const float e = %s(%s%d); z2%d += e; pry = (posy == %d) ? %s%d : pry; }", (plan.knobs.expm & 1) ? "exp01m" : "exp01", pre, c, acc & 3, t.pos[c], pre, c);
       note("z2" + std::to_string(acc & 3));
       ++acc;
     }
@@ -528,7 +532,7 @@ struct Gen {
   // logits dm[c] = H[c] - p[c]*H[v], which REPLACES the node's probability value (register or slot).  Returns the name of
   // H[n].  Nothing is stored per leaf: the row's x stays in its slots for the final pass.
   std::string leaf_g(int k, const std::string& Q) {
-    o.f("    const float G%d = %s * (exp01(%s) - ((posy == %d) ? Z : 0.f));", k, Q.c_str(), Q.c_str(), t.pos[k]);
+    o.f("    const float G%d = %s * (%s(%s) - ((posy == %d) ? Z : 0.f));", k, Q.c_str(), (plan.knobs.expm & 2) ? "exp01m" : "exp01", Q.c_str(), t.pos[k]);
     return "G" + std::to_string(k);
   }
   void node_grad(int n, const std::string& H, const std::vector<std::string>& h, bool opaque) {
@@ -1298,7 +1302,7 @@ std::vector<std::string> cache_read_dirs() {
 std::string variant_name(const KTree& t, const Variant& v, const Knobs& k) {
   char b[192];
   int n = snprintf(b, sizeof b, "ka%d_%016llx_m%d_t%d_v%d_o%d", kGeneratorVersion, t.hash, v.mode, v.dtype, v.vec, v.ovec);
-  if (!k.is_default()) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d_w%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence, k.warps);
+  if (!k.is_default()) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d_w%d_e%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence, k.warps, k.expm);
   return b;
 }
 

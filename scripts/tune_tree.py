@@ -12,14 +12,11 @@ import torch  # noqa: E402
 from bench_tree import peaks, time_point  # noqa: E402
 from nbdt.tree import Tree  # noqa: E402
 
-KNOBS = ["NBDT_B200_KA_REGCAP", "NBDT_B200_KA_MINB", "NBDT_B200_KA_UNROLL", "NBDT_B200_KA_PREFETCH", "NBDT_B200_KA_MAXLD", "NBDT_B200_KA_FENCE", "NBDT_B200_KA_WARPS"]
-# (regcap, minb, unroll, prefetch, maxld, fence, warps)
-D = (168, 0, 8, 1, 24, 8, 0)
-GRIDS = {
-    100: [D, (168, 0, 8, 0, 24, 8, 0), (168, 0, 8, 0, 24, 8, 2), (168, 0, 8, 0, 24, 16, 2), (168, 0, 8, 0, 24, 8, 4)],
-    200: [D, (168, 0, 8, 0, 24, 8, 0), (168, 0, 8, 0, 24, 8, 4), (168, 0, 8, 0, 24, 16, 2), (168, 0, 8, 0, 24, 8, 1)],
-    1000: [D, (168, 0, 8, 0, 24, 8, 0)],
-}
+KNOBS = ["NBDT_B200_KA_REGCAP", "NBDT_B200_KA_MINB", "NBDT_B200_KA_UNROLL", "NBDT_B200_KA_PREFETCH", "NBDT_B200_KA_MAXLD", "NBDT_B200_KA_FENCE", "NBDT_B200_KA_WARPS", "NBDT_B200_KA_EXPMUFU"]
+# (regcap, minb, unroll, prefetch, maxld, fence, warps, expmufu)
+D = (168, 0, 8, 0, 24, 8, 0, 0)
+E = [D, D[:7] + (1,), D[:7] + (2,), D[:7] + (3,)]
+GRIDS = {100: E, 200: E, 1000: [D, D[:7] + (3,)]}
 if len(sys.argv) > 1:
     g = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
     GRIDS = {100: g, 200: g, 1000: g}
@@ -27,7 +24,7 @@ pk, src = peaks()
 cases = [("CIFAR100", "induced", 100, 1 << 20), ("TinyImagenet200", "induced", 200, 1 << 19), ("Imagenet1000", "induced", 1000, 1 << 17)]
 for dataset, hierarchy, C, rows in cases:
     for g in GRIDS[C]:
-        for k, v in zip(KNOBS, g):
+        for k, v in zip(KNOBS, tuple(g) + D[len(g):]):
             os.environ[k] = str(v)
         tree = Tree(dataset, hierarchy=hierarchy)
         for dtype in (torch.float32, torch.bfloat16):
