@@ -48,7 +48,7 @@
 
 namespace {
 
-constexpr int kGeneratorVersion = 9;   // part of the cache key: bump when the emitted code changes
+constexpr int kGeneratorVersion = 12;   // part of the cache key: bump when the emitted code changes
 constexpr int kMaxLeaves = 1536;       // 32 rows x 132 B per leaf of shared memory per block: 1000 leaves (ImageNet) use 16 warps on 150 KB
 constexpr int kTPB = 32;               // one warp per CTA: rows are thread-private, only __syncwarp around the cooperative I/O sweeps
 // Shared-memory layout of a 32-row block: slot c (class c, later prefix / gradient) of row r lives at word
@@ -68,11 +68,14 @@ struct Knobs {
   int unroll = 8;             // NBDT_B200_KA_UNROLL: unroll factor of the I/O sweeps (0 = full)
   int prefetch = 0;           // NBDT_B200_KA_PREFETCH: row blocks ahead whose lines are prefetched into L2 (0 = off; measured: no gain)
   int maxld = 24;             // NBDT_B200_KA_MAXLD: 16-byte loads a lane keeps in flight in sweep A before their stores
-  int fence = 8;              // NBDT_B200_KA_FENCE: nodes between scheduling fences of the straight-line passes (0 = none)
+  int fence = -1;             // NBDT_B200_KA_FENCE: nodes between scheduling fences of the straight-line passes (0 = none; -1 = by
+                              //   hierarchy size, measured in profiles/r02_tree_tune_v8.jsonl)
   int warps = 0;              // NBDT_B200_KA_WARPS: warps per row block (0 = by leaf count)
-  int expm = 0;               // NBDT_B200_KA_EXPMUFU: exp(class probability) as one FMUL + MUFU.EX2 instead of the degree-6 polynomial
-                              //   (6 FFMA): bit 0 in the Z traversal, bit 1 in the gradient traversal
-  bool is_default() const { return regcap == kRegValueCap && minb == 0 && unroll == 8 && prefetch == 0 && maxld == 24 && fence == 8 && warps == 0 && expm == 0; }
+  int expm = -1;              // NBDT_B200_KA_EXPMUFU: exp(class probability) as one FMUL + MUFU.EX2 instead of the degree-6 polynomial
+                              //   (6 FFMA): bit 0 in the Z traversal, bit 1 in the gradient traversal; -1 = by team size (measured,
+                              //   profiles/r02_tree_tune_v6.jsonl: one warp per block 1, teams 3)
+  int rows = 0;               // NBDT_B200_KA_ROWS: rows per thread (1, or 2 = packed f32x2 arithmetic; 0 = by leaf count)
+  bool is_default() const { return regcap == kRegValueCap && minb == 0 && unroll == 8 && prefetch == 0 && maxld == 24 && fence == -1 && warps == 0 && expm == -1 && rows == 0; }
 };
 Knobs read_knobs() {
   Knobs k;
@@ -82,9 +85,10 @@ Knobs read_knobs() {
   k.unroll = std::max(0, geti("NBDT_B200_KA_UNROLL", k.unroll));
   k.prefetch = std::max(0, std::min(8, geti("NBDT_B200_KA_PREFETCH", k.prefetch)));
   k.maxld = std::max(1, std::min(64, geti("NBDT_B200_KA_MAXLD", k.maxld)));
-  k.fence = std::max(0, geti("NBDT_B200_KA_FENCE", k.fence));
+  k.fence = std::max(-1, geti("NBDT_B200_KA_FENCE", k.fence));
   k.warps = std::max(0, std::min(16, geti("NBDT_B200_KA_WARPS", k.warps)));
-  k.expm = std::max(0, std::min(3, geti("NBDT_B200_KA_EXPMUFU", k.expm)));
+  k.expm = std::max(-1, std::min(3, geti("NBDT_B200_KA_EXPMUFU", k.expm)));
+  k.rows = std::max(0, std::min(2, geti("NBDT_B200_KA_ROWS", k.rows)));
   return k;
 }
 
@@ -187,8 +191,10 @@ struct Plan {
   int smem_bytes = 0;              // per CTA (upper bound over the variants' skew)
   int min_blocks = 1;              // __launch_bounds__ second argument
   int threads = kTPB;              // 32 * W
+  int rows = 1;                    // rows per thread (2: packed pairs); a block is 32 * rows rows
   Team team;
-  Knobs knobs;
+  Knobs knobs;                     // with the automatic choices resolved
+  bool default_knobs = true;       // nothing set in the environment: the variant name carries no knob suffix
 };
 
 struct Out {
@@ -232,6 +238,7 @@ struct KAParams {
 typedef unsigned int u32;
 typedef u32 KA_XSB;  // shared-memory byte address of the thread's slot 0
 typedef unsigned short u16;
+typedef unsigned long long u64;
 KA_DEV float ex2(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 KA_DEV float lg2(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
 KA_DEV float rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
@@ -244,15 +251,161 @@ KA_DEV uint4 ld16(const char* p) { return __ldg(reinterpret_cast<const uint4*>(p
 KA_DEV uint2 ld8(const char* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 KA_DEV u32 ld4(const char* p) { return __ldg(reinterpret_cast<const u32*>(p)); }
 KA_DEV u32 ld2(const char* p) { return __ldg(reinterpret_cast<const u16*>(p)); }
-#define KA_LDX(dst, base, slot, off) float dst; asm volatile("ld.shared.f32 %0, [%1+" #off "];" : "=f"(dst) : "r"(base))
-#define KA_STX(base, slot, off, val) asm volatile("st.shared.f32 [%0+" #off "], %1;" :: "r"(base), "f"(val))
+KA_DEV void st16(char* p, u32 a, u32 b, u32 c, u32 d) { *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d); }
+KA_DEV void st8(char* p, u32 a, u32 b) { *reinterpret_cast<uint2*>(p) = make_uint2(a, b); }
+KA_DEV void st4(char* p, u32 a) { *reinterpret_cast<u32*>(p) = a; }
+KA_DEV void st2(char* p, u32 a) { *reinterpret_cast<u16*>(p) = (u16)a; }
+#endif
+
+// ---- the value types of the row code: KF = one fp32 value per ROW OF THE THREAD ----
+// KA_R == 1: a thread owns one row and KF is a float.  KA_R == 2: a thread owns two rows and KF is a packed pair in a 64-bit
+// register: add / mul / fma are ONE instruction for both rows (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2 on sm_100; ptxas
+// folds negation and |.| into their operand modifiers), MUFU ops, selects and sign tricks act on the halves.  The generated
+// row code is the same text for both.
+#if KA_R == 1
+typedef float KF;
+typedef bool KB;
+typedef int KI;
+typedef long long KY;
+KA_DEV KF sel(KB c, KF a, KF b) { return c ? a : b; }
+KA_DEV KF sel_neg(KF s, KF a, KF b) { return (int)f2u(s) < 0 ? a : b; }   // sign bit of s set
+KA_DEV KF sel_ge0(KF t, KF a, KF b) { return t >= 0.f ? a : b; }
+KA_DEV KF sel_eq(KI p, int k, KF a, KF b) { return p == k ? a : b; }
+KA_DEV KF sel_lt(KI p, int k, KF a, KF b) { return p < k ? a : b; }
+KA_DEV KF sel_in(KI p, int b0, int n, KF a, KF b) { return (unsigned)(p - b0) < (unsigned)n ? a : b; }
+KA_DEV KB both(KB a, KB b) { return a && b; }
+KA_DEV KB ka_true() { return true; }
+KA_DEV bool ka_all(KB a) { return a; }
+KA_DEV KB ka_not(KB a) { return !a; }
+KA_DEV KF or_not_sign(KF v, KF t) { return u2f(f2u(v) | (~f2u(t) & 0x80000000u)); }
+KA_DEV KF ka_fence(KF a, KF b, u32 zr) { return u2f(f2u(a) | (f2u(b) & zr)); }
+KA_DEV u32 ka_bits(KF a) { return f2u(a); }
+KA_DEV float ka_hsum(KF a) { return a; }
+KA_DEV KB ka_valid(KY yy) { return (unsigned long long)yy < (unsigned long long)KA_C; }
+KA_DEV KI ka_target(KY yy, KB valid) { return valid ? (int)(unsigned)yy : 0; }
+KA_DEV KI ka_lookup(const unsigned short* tab, KI y) { return tab[y]; }
+KA_DEV KB ka_owned(const unsigned char* tab, KI y, int w) { return tab[y] == w; }
+#else
+#ifdef KA_HOST
+struct KF {
+  float a, b;
+  KF() {}
+  KF(float f) : a(f), b(f) {}
+  KF(float x, float y) : a(x), b(y) {}
+};
+KA_DEV float lo(KF v) { return v.a; }
+KA_DEV float hi(KF v) { return v.b; }
+KA_DEV KF operator+(KF x, KF y) { return KF(x.a + y.a, x.b + y.b); }
+KA_DEV KF operator-(KF x, KF y) { return KF(x.a - y.a, x.b - y.b); }
+KA_DEV KF operator*(KF x, KF y) { return KF(x.a * y.a, x.b * y.b); }
+KA_DEV KF fmaf(KF x, KF y, KF z) { return KF(::fmaf(x.a, y.a, z.a), ::fmaf(x.b, y.b, z.b)); }
+#else
+struct KF {
+  u64 v;
+  KA_DEV KF() {}
+  KA_DEV KF(float f) { asm("mov.b64 %0, {%1,%1};" : "=l"(v) : "f"(f)); }
+  KA_DEV KF(float x, float y) { asm("mov.b64 %0, {%1,%2};" : "=l"(v) : "f"(x), "f"(y)); }
+};
+KA_DEV float lo(KF a) { float x, y; asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); return x; }
+KA_DEV float hi(KF a) { float x, y; asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); return y; }
+KA_DEV KF operator+(KF a, KF b) { KF r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+KA_DEV KF operator-(KF a, KF b) { KF r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+KA_DEV KF operator*(KF a, KF b) { KF r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+KA_DEV KF fmaf(KF a, KF b, KF c) { KF r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+#endif
+KA_DEV KF operator-(KF a) { return KF(-lo(a), -hi(a)); }
+KA_DEV KF& operator+=(KF& a, KF b) { a = a + b; return a; }
+KA_DEV KF fmaxf(KF a, KF b) { return KF(::fmaxf(lo(a), lo(b)), ::fmaxf(hi(a), hi(b))); }
+KA_DEV KF fabsf(KF a) { return KF(::fabsf(lo(a)), ::fabsf(hi(a))); }
+KA_DEV KF ex2(KF a) { return KF(ex2(lo(a)), ex2(hi(a))); }
+KA_DEV KF lg2(KF a) { return KF(lg2(lo(a)), lg2(hi(a))); }
+KA_DEV KF rcp(KF a) { return KF(rcp(lo(a)), rcp(hi(a))); }
+struct KB { bool a, b; };
+struct KI { int a, b; };
+struct KY { long long a, b; };
+KA_DEV KB mkb(bool a, bool b) { KB r; r.a = a; r.b = b; return r; }
+KA_DEV KI mki(int a, int b) { KI r; r.a = a; r.b = b; return r; }
+KA_DEV KF sel(KB c, KF a, KF b) { return KF(c.a ? lo(a) : lo(b), c.b ? hi(a) : hi(b)); }
+// selects of the straight-line passes, per half: setp + selp inside one asm statement so that ptxas emits ISETP + FSEL writing
+// the half of the destination pair (a C++ ternary on the halves becomes two predicated MOVs per half)
+#ifdef KA_HOST
+KA_DEV float ka_sneg(float s, float a, float b) { return (int)f2u(s) < 0 ? a : b; }
+KA_DEV float ka_sge0(float t, float a, float b) { return t >= 0.f ? a : b; }
+KA_DEV float ka_seq(int p, int k, float a, float b) { return p == k ? a : b; }
+KA_DEV float ka_slt(int p, int k, float a, float b) { return p < k ? a : b; }
+KA_DEV float ka_sltu(u32 p, u32 k, float a, float b) { return p < k ? a : b; }
+#else
+KA_DEV float ka_sneg(float s, float a, float b) { float r; asm("{ .reg .pred p; setp.lt.s32 p, %3, 0; selp.f32 %0, %1, %2, p; }" : "=f"(r) : "f"(a), "f"(b), "r"(f2u(s))); return r; }
+KA_DEV float ka_sge0(float t, float a, float b) { float r; asm("{ .reg .pred p; setp.ge.f32 p, %3, 0f00000000; selp.f32 %0, %1, %2, p; }" : "=f"(r) : "f"(a), "f"(b), "f"(t)); return r; }
+KA_DEV float ka_seq(int p_, int k, float a, float b) { float r; asm("{ .reg .pred p; setp.eq.s32 p, %3, %4; selp.f32 %0, %1, %2, p; }" : "=f"(r) : "f"(a), "f"(b), "r"(p_), "r"(k)); return r; }
+KA_DEV float ka_slt(int p_, int k, float a, float b) { float r; asm("{ .reg .pred p; setp.lt.s32 p, %3, %4; selp.f32 %0, %1, %2, p; }" : "=f"(r) : "f"(a), "f"(b), "r"(p_), "r"(k)); return r; }
+KA_DEV float ka_sltu(u32 p_, u32 k, float a, float b) { float r; asm("{ .reg .pred p; setp.lt.u32 p, %3, %4; selp.f32 %0, %1, %2, p; }" : "=f"(r) : "f"(a), "f"(b), "r"(p_), "r"(k)); return r; }
+#endif
+KA_DEV KF sel_neg(KF s, KF a, KF b) { return KF(ka_sneg(lo(s), lo(a), lo(b)), ka_sneg(hi(s), hi(a), hi(b))); }
+KA_DEV KF sel_ge0(KF t, KF a, KF b) { return KF(ka_sge0(lo(t), lo(a), lo(b)), ka_sge0(hi(t), hi(a), hi(b))); }
+KA_DEV KF sel_eq(KI p, int k, KF a, KF b) { return KF(ka_seq(p.a, k, lo(a), lo(b)), ka_seq(p.b, k, hi(a), hi(b))); }
+KA_DEV KF sel_lt(KI p, int k, KF a, KF b) { return KF(ka_slt(p.a, k, lo(a), lo(b)), ka_slt(p.b, k, hi(a), hi(b))); }
+KA_DEV KF sel_in(KI p, int b0, int n, KF a, KF b) { return KF(ka_sltu((u32)(p.a - b0), (u32)n, lo(a), lo(b)), ka_sltu((u32)(p.b - b0), (u32)n, hi(a), hi(b))); }
+KA_DEV KB both(KB a, KB b) { return mkb(a.a && b.a, a.b && b.b); }
+KA_DEV KB ka_true() { return mkb(true, true); }
+KA_DEV bool ka_all(KB a) { return a.a && a.b; }
+KA_DEV KB ka_not(KB a) { return mkb(!a.a, !a.b); }
+KA_DEV KF or_not_sign(KF v, KF t) { return KF(u2f(f2u(lo(v)) | (~f2u(lo(t)) & 0x80000000u)), u2f(f2u(hi(v)) | (~f2u(hi(t)) & 0x80000000u))); }
+// one half carries the dependency: the packed instructions that consume the pair are ordered with it
+KA_DEV KF ka_fence(KF a, KF b, u32 zr) { return KF(u2f(f2u(lo(a)) | (f2u(lo(b)) & zr)), hi(a)); }
+KA_DEV u32 ka_bits(KF a) { return f2u(lo(a)); }
+KA_DEV float ka_hsum(KF a) { return lo(a) + hi(a); }
+KA_DEV KB ka_valid(KY yy) { return mkb((unsigned long long)yy.a < (unsigned long long)KA_C, (unsigned long long)yy.b < (unsigned long long)KA_C); }
+KA_DEV KI ka_target(KY yy, KB valid) { return mki(valid.a ? (int)(unsigned)yy.a : 0, valid.b ? (int)(unsigned)yy.b : 0); }
+KA_DEV KI ka_lookup(const unsigned short* tab, KI y) { return mki(tab[y.a], tab[y.b]); }
+KA_DEV KB ka_owned(const unsigned char* tab, KI y, int w) { return mkb(tab[y.a] == w, tab[y.b] == w); }
+#endif
+
+#ifdef KA_HOST
+// host harness (tests/jit_host.py): the "shared memory" of a block is a float array, slot s of the thread's KA_R rows at s*KA_R
+#if KA_R == 1
+#define KA_LDX(dst, base, slot, off) const KF dst = (base)[slot]
+#define KA_STX(base, slot, off, val) (base)[slot] = (val)
+#define KA_LDX_DYN(dst, idx) const KF dst = xsb[idx]
+#define KA_ADDX_DYN(cond, idx, val) if (cond) xsb[idx] += (val)
+#define KA_ZERO_IF(cond, idx) if (cond) xsb[idx] = 0.f
+#else
+#define KA_LDX(dst, base, slot, off) const KF dst = KF((base)[(slot) * 2], (base)[(slot) * 2 + 1])
+#define KA_STX(base, slot, off, val) { const KF sv_ = (val); (base)[(slot) * 2] = lo(sv_); (base)[(slot) * 2 + 1] = hi(sv_); }
+#define KA_LDX_DYN(dst, idx) const KF dst = KF(xsb[(idx).a * 2], xsb[(idx).b * 2 + 1])
+#define KA_ADDX_DYN(cond, idx, val) { const KB dc_ = (cond); if (dc_.a) xsb[(idx).a * 2] += (val); if (dc_.b) xsb[(idx).b * 2 + 1] += (val); }
+#define KA_ZERO_IF(cond, idx) { const KB dc_ = (cond); if (dc_.a) xsb[(idx) * 2] = 0.f; if (dc_.b) xsb[(idx) * 2 + 1] = 0.f; }
+#endif
+#define KA_OPAQUE(x)
+#define KA_SLOT_ADDR(base, col, row) ((base) + (col) * KA_R + (row))
+#define KA_STD(a, k, off, val) (a)[(k) * KA_R] = (val)
+#define KA_LDD(dst, a, k, off) const float dst = (a)[(k) * KA_R]
+#else
+// Shared-memory accesses are volatile inline PTX with immediate offsets: plain C++ accesses get forwarded by the compiler into
+// registers and from there into local-memory spills.  Slot `idx` of the thread: KA_R floats at byte KA_DYN_OFF(idx) from xsb.
+#define KA_DYN_OFF(idx) (((u32)(idx) * 128u + ((u32)(idx) / KA_U) * 4u) * KA_R)
+#if KA_R == 1
+#define KA_LDX(dst, base, slot, off) KF dst; asm volatile("ld.shared.f32 %0, [%1+" #off "];" : "=f"(dst) : "r"(base))
+#define KA_STX(base, slot, off, val) asm volatile("st.shared.f32 [%0+" #off "], %1;" :: "r"(base), "f"((KF)(val)))
 #define KA_OPAQUE(x) asm volatile("" : "+f"(x))
-#define KA_DYN_OFF(idx) ((u32)(idx) * 128u + ((u32)(idx) / KA_U) * 4u)
-#define KA_ADDX_DYN(idx, val) { float dv_; const u32 da_ = xsb + KA_DYN_OFF(idx); asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dv_) : "r"(da_)); dv_ += (val); asm volatile("st.shared.f32 [%0], %1;" :: "r"(da_), "f"(dv_)); }
-#define KA_LDX_DYN(dst, idx) float dst; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dst) : "r"(xsb + KA_DYN_OFF(idx)))
-#define KA_STX_DYN(idx, val) asm volatile("st.shared.f32 [%0], %1;" :: "r"(xsb + KA_DYN_OFF(idx)), "f"(val))
-// cooperative sweeps: slot `col` (a multiple of the vector size) of row `row` of the block, and accesses relative to it
-#define KA_SLOT_ADDR(base, col, row) ((base) + ((u32)(col) * 32u + (u32)(col) / KA_U + (((u32)(row) * KA_K) & 31u)) * 4u)
+#define KA_LDX_DYN(dst, idx) KF dst; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dst) : "r"(xsb + KA_DYN_OFF(idx)))
+#define KA_ADDX_DYN(cond, idx, val) if (cond) { float dv_; const u32 da_ = xsb + KA_DYN_OFF(idx); asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dv_) : "r"(da_)); dv_ += (val); asm volatile("st.shared.f32 [%0], %1;" :: "r"(da_), "f"(dv_)); }
+#define KA_ZERO_IF(cond, idx) if (cond) asm volatile("st.shared.f32 [%0], %1;" :: "r"(xsb + KA_DYN_OFF(idx)), "f"(0.f))
+#else
+#define KA_LDX(dst, base, slot, off) KF dst; asm volatile("ld.shared.b64 %0, [%1+" #off "];" : "=l"(dst.v) : "r"(base))
+#define KA_STX(base, slot, off, val) { const KF sv_ = (val); asm volatile("st.shared.b64 [%0+" #off "], %1;" :: "r"(base), "l"(sv_.v)); }
+#define KA_OPAQUE(x) asm volatile("" : "+l"((x).v))
+KA_DEV float ka_lds(u32 a) { float r; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a)); return r; }
+KA_DEV void ka_sts(u32 a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v)); }
+#define KA_LDX_DYN(dst, idx) const KF dst = KF(ka_lds(xsb + KA_DYN_OFF((idx).a)), ka_lds(xsb + KA_DYN_OFF((idx).b) + 4u))
+#define KA_ADDX_DYN(cond, idx, val) { const KB dc_ = (cond); \
+    if (dc_.a) { const u32 da_ = xsb + KA_DYN_OFF((idx).a); ka_sts(da_, ka_lds(da_) + (val)); } \
+    if (dc_.b) { const u32 da_ = xsb + KA_DYN_OFF((idx).b) + 4u; ka_sts(da_, ka_lds(da_) + (val)); } }
+#define KA_ZERO_IF(cond, idx) { const KB dc_ = (cond); if (dc_.a) ka_sts(xsb + KA_DYN_OFF(idx), 0.f); if (dc_.b) ka_sts(xsb + KA_DYN_OFF(idx) + 4u, 0.f); }
+#endif
+// cooperative sweeps: slot `col` (a multiple of the vector size) of row `row` of the block (thread row / KA_R, half row % KA_R),
+// and accesses relative to it
+#define KA_SLOT_ADDR(base, col, row) ((base) + (((u32)(col) * 32u + (u32)(col) / KA_U + ((((u32)(row) / KA_R) * KA_K) & 31u)) * KA_R + (u32)(row) % KA_R) * 4u)
 #define KA_STD(a, k, off, val) asm volatile("st.shared.f32 [%0+" #off "], %1;" :: "r"(a), "f"(val))
 #define KA_LDD(dst, a, k, off) float dst; asm volatile("ld.shared.f32 %0, [%1+" #off "];" : "=f"(dst) : "r"(a))
 // the parts of a team meet here (all threads of the CTA); a single-warp kernel needs no barrier inside the row function
@@ -261,14 +414,10 @@ KA_DEV u32 ld2(const char* p) { return __ldg(reinterpret_cast<const u16*>(p)); }
 #else
 #define KA_BAR()
 #endif
-KA_DEV void st16(char* p, u32 a, u32 b, u32 c, u32 d) { *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d); }
-KA_DEV void st8(char* p, u32 a, u32 b) { *reinterpret_cast<uint2*>(p) = make_uint2(a, b); }
-KA_DEV void st4(char* p, u32 a) { *reinterpret_cast<u32*>(p) = a; }
-KA_DEV void st2(char* p, u32 a) { *reinterpret_cast<u16*>(p) = (u16)a; }
 #endif
 // exp(t), t in [0, 1] (a class probability): degree-6 interpolant on the FMA pipe, max rel. error 1.5e-7
-KA_DEV float exp01(float t) {
-  float r = 0.002307842718437314f;
+KA_DEV KF exp01(KF t) {
+  KF r = 0.002307842718437314f;
   r = fmaf(r, t, 0.0069595566019415855f);
   r = fmaf(r, t, 0.04264117032289505f);
   r = fmaf(r, t, 0.16631804406642914f);
@@ -276,15 +425,13 @@ KA_DEV float exp01(float t) {
   r = fmaf(r, t, 0.9999963045120239f);
   return fmaf(r, t, 1.0f);
 }
-KA_DEV float exp01m(float t) { return ex2(t * 1.4426950408889634f); }  // the same on the MUFU pipe (2 ulp)
+KA_DEV KF exp01m(KF t) { return ex2(t * 1.4426950408889634f); }  // the same on the MUFU pipe (2 ulp)
 // smaller child probability of a binary node with the sign bit set when it belongs to the SECOND child
 // (t = node logit of the first child minus that of the second, in log2 units)
-KA_DEV float signed_lo(float t) {
-  const float q = ex2(-fabsf(t));
-  const float lo = q * rcp(1.f + q);
-  return u2f(f2u(lo) | (~f2u(t) & 0x80000000u));
+KA_DEV KF signed_lo(KF t) {
+  const KF q = ex2(-fabsf(t));
+  return or_not_sign(q * rcp(1.f + q), t);
 }
-KA_DEV bool first_is_hi(float s) { return (int)f2u(s) < 0; }
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 )SRC";
@@ -323,7 +470,7 @@ struct Gen {
     since = 0;
     char b[32];
     snprintf(b, sizeof b, "fz%d", nfence++);
-    o.f("    const float %s = u2f(f2u(%s) | (f2u(%s) & zr));", b, val.c_str(), last.c_str());
+    o.f("    const KF %s = ka_fence(%s, %s, zr);", b, val.c_str(), last.c_str());
     return b;
   }
   void fence_base() {  // same for the shared-memory base of the following loads / stores
@@ -331,7 +478,7 @@ struct Gen {
     since = 0;
     char b[32];
     snprintf(b, sizeof b, "xb%d", nfence++);
-    o.f("    const KA_XSB %s = xsb + (f2u(%s) & zr);", b, last.c_str());
+    o.f("    const KA_XSB %s = xsb + (ka_bits(%s) & zr);", b, last.c_str());
     base = b;
   }
 
@@ -339,12 +486,13 @@ struct Gen {
   // slots 0..C-1: the row (x, later dL/dx or the class probabilities); then W spill regions of plan.maxspill slots; then the
   // exchange slots of the team.  Byte offsets are relative to the thread's base (rho(lane) words into the block).
   int U = 1, K = 1;  // skew unit and row multiplier of the layout (see the layout comment at the top of this file)
+  int R() const { return plan.rows; }  // rows per thread: every slot holds R consecutive floats
   int row_words() const { return (t.C * 32 + t.C / U + 32 + 3) & ~3; }
   int soff(int slot) const {
-    if (slot < t.C) return (slot * 32 + slot / U) * 4;
-    return (row_words() + (slot - t.C) * 32) * 4;
+    if (slot < t.C) return (slot * 32 + slot / U) * 4 * R();
+    return (row_words() + (slot - t.C) * 32) * 4 * R();
   }
-  int eoff(int k) const { return (k * 32 + k / U) * 4; }  // element k of a vector, relative to the vector's first slot
+  int eoff(int k) const { return (k * 32 + k / U) * 4 * R(); }  // element k of a vector, relative to the vector's first slot
   int spill_slot(int vid) const { return t.C + plan.value_part[vid] * plan.maxspill + plan.value_spill[vid]; }
   int ex_base() const { return t.C + team.W * plan.maxspill; }
   int ex_p(int k) const { return ex_base() + k; }                      // subtree sum S, then path probability P (hard: on-path flag)
@@ -370,7 +518,7 @@ struct Gen {
   }
   void vset(int vid, const std::string& expr) {
     if (spilled(vid)) stx(spill_slot(vid), expr);
-    else o.f("    const float nv%d = %s;", vid, expr.c_str());
+    else o.f("    const KF nv%d = %s;", vid, expr.c_str());
   }
   std::string kget(int vid) {  // k-ary child value
     if (spilled(vid)) return ldx(spill_slot(vid));
@@ -379,7 +527,7 @@ struct Gen {
   // gradient values: same placement as the probability values they replace
   void dset(int vid, const std::string& expr) {
     if (spilled(vid)) stx(spill_slot(vid), expr);
-    else o.f("    const float dv%d = %s;", vid, expr.c_str());
+    else o.f("    const KF dv%d = %s;", vid, expr.c_str());
   }
   std::string dget(int vid) {
     if (spilled(vid)) return ldx(spill_slot(vid));
@@ -434,7 +582,7 @@ struct Gen {
     if (n != t.root) {
       std::string sum;
       for (size_t k = 0; k < c.size(); ++k) sum += (k ? " + " : "") + sn(c[k]);
-      o.f("    const float s%d = %s;", n, sum.c_str());
+      o.f("    const KF s%d = %s;", n, sum.c_str());
     }
     const int vid = plan.value_slot[n];
     if (c.size() == 1) return;  // a single child has probability 1: nothing to keep
@@ -449,19 +597,19 @@ struct Gen {
     }
     // k-ary: softmax over the children (log2 domain)
     o.f("    {");
-    for (int k : c) o.f("      const float a%d = %s * %s;", k, sn(k).c_str(), lit(kLog2e / t.cnt[k]).c_str());
+    for (int k : c) o.f("      const KF a%d = %s * %s;", k, sn(k).c_str(), lit(kLog2e / t.cnt[k]).c_str());
     std::string mx = "a" + std::to_string(c[0]);
     for (size_t k = 1; k < c.size(); ++k) mx = "fmaxf(" + mx + ", a" + std::to_string(c[k]) + ")";
-    o.f("      const float mx = %s;", mx.c_str());
+    o.f("      const KF mx = %s;", mx.c_str());
     if (v.mode == kSpecHardLoss) {
       for (size_t k = 0; k < c.size(); ++k) o.f("      km%d = a%d - mx;", vid + (int)k, c[k]);
     } else {
       std::string sum;
       for (size_t k = 0; k < c.size(); ++k) {
-        o.f("      const float q%d = ex2(a%d - mx);", c[k], c[k]);
+        o.f("      const KF q%d = ex2(a%d - mx);", c[k], c[k]);
         sum += (k ? " + q" : "q") + std::to_string(c[k]);
       }
-      o.f("      const float r = rcp(%s);", sum.c_str());
+      o.f("      const KF r = rcp(%s);", sum.c_str());
       for (size_t k = 0; k < c.size(); ++k) o.f("      km%d = q%d * r;", vid + (int)k, c[k]);
     }
     o.f("    }");
@@ -473,7 +621,7 @@ struct Gen {
     for (int n = t.C; n < t.NV; ++n) {
       const std::vector<int>& c = kids(n);
       if (c.size() <= 2 || team.part_of_node[n] != part) continue;
-      for (size_t k = 0; k < c.size(); ++k) o.f("    float km%d;", plan.value_slot[n] + (int)k);
+      for (size_t k = 0; k < c.size(); ++k) o.f("    KF km%d;", plan.value_slot[n] + (int)k);
     }
   }
 
@@ -485,7 +633,7 @@ struct Gen {
       stx(c, std::string(pre) + std::to_string(c));
       note(std::string(pre) + std::to_string(c));
     } else {
-      o.f("    { const float e = %s(%s%d); z2%d += e; pry = (posy == %d) ? %s%d : pry; }", (plan.knobs.expm & 1) ? "exp01m" : "exp01", pre, c, acc & 3, t.pos[c], pre, c);
+      o.f("    { const KF e = %s(%s%d); z2%d += e; pry = sel_eq(posy, %d, %s%d, pry); }", (plan.knobs.expm & 1) ? "exp01m" : "exp01", pre, c, acc & 3, t.pos[c], pre, c);
       note("z2" + std::to_string(acc & 3));
       ++acc;
     }
@@ -495,26 +643,32 @@ struct Gen {
     const std::vector<int>& c = kids(n);
     const int vid = plan.value_slot[n];
     if (c.size() == 1) {
-      o.f("    const float %s%d = %s;", pre, c[0], P.empty() ? "1.f" : P.c_str());
+      o.f("    const KF %s%d = %s;", pre, c[0], P.empty() ? "1.f" : P.c_str());
     } else if (binary(n)) {
       const std::string s = fenced(vget(vid));
       // the second traversal recomputes what the first one computed: without the opaque copy the compiler merges the two and
       // keeps every path probability of the first traversal alive (hundreds of spilled registers)
-      if (pre[0] == 'Q') o.f("    float %ss%d = %s; KA_OPAQUE(%ss%d);", pre, n, s.c_str(), pre, n);
-      else o.f("    const float %ss%d = %s;", pre, n, s.c_str());
-      if (P.empty()) o.f("    const float %sl%d = fabsf(%ss%d); const float %sh%d = 1.f - %sl%d;", pre, n, pre, n, pre, n, pre, n);
-      else o.f("    const float %sl%d = %s * fabsf(%ss%d); const float %sh%d = %s - %sl%d;", pre, n, P.c_str(), pre, n, pre, n, P.c_str(), pre, n);
-      o.f("    const float %s%d = first_is_hi(%ss%d) ? %sh%d : %sl%d; const float %s%d = first_is_hi(%ss%d) ? %sl%d : %sh%d;",
-          pre, c[0], pre, n, pre, n, pre, n, pre, c[1], pre, n, pre, n, pre, n);
+      if (pre[0] == 'Q') o.f("    KF %ss%d = %s; KA_OPAQUE(%ss%d);", pre, n, s.c_str(), pre, n);
+      else o.f("    const KF %ss%d = %s;", pre, n, s.c_str());
+      // s = -lo when the first child has the larger probability (1 - lo), +lo when it has the smaller one: with u = P or 0
+      // accordingly, P*p(first) = P*s + u and P*p(second) = (P - u) - P*s -- two fused multiply-adds, each rounded once
+      if (P.empty()) {
+        o.f("    const KF %su%d = sel_neg(%ss%d, 1.f, 0.f);", pre, n, pre, n);
+        o.f("    const KF %s%d = %ss%d + %su%d; const KF %s%d = (1.f - %su%d) - %ss%d;", pre, c[0], pre, n, pre, n, pre, c[1], pre, n, pre, n);
+      } else {
+        o.f("    const KF %su%d = sel_neg(%ss%d, %s, 0.f);", pre, n, pre, n, P.c_str());
+        o.f("    const KF %s%d = fmaf(%s, %ss%d, %su%d); const KF %s%d = fmaf(-%s, %ss%d, %s - %su%d);", pre, c[0], P.c_str(), pre, n, pre, n,
+            pre, c[1], P.c_str(), pre, n, P.c_str(), pre, n);
+      }
     } else {
       for (size_t k = 0; k < c.size(); ++k) {
         const std::string pk = kget(vid + (int)k);
         if (pre[0] == 'Q') {
-          o.f("    float %sk%d = %s; KA_OPAQUE(%sk%d);", pre, c[k], pk.c_str(), pre, c[k]);
-          if (P.empty()) o.f("    const float %s%d = %sk%d;", pre, c[k], pre, c[k]);
-          else o.f("    const float %s%d = %s * %sk%d;", pre, c[k], P.c_str(), pre, c[k]);
-        } else if (P.empty()) o.f("    const float %s%d = %s;", pre, c[k], pk.c_str());
-        else o.f("    const float %s%d = %s * %s;", pre, c[k], P.c_str(), pk.c_str());
+          o.f("    KF %sk%d = %s; KA_OPAQUE(%sk%d);", pre, c[k], pk.c_str(), pre, c[k]);
+          if (P.empty()) o.f("    const KF %s%d = %sk%d;", pre, c[k], pre, c[k]);
+          else o.f("    const KF %s%d = %s * %sk%d;", pre, c[k], P.c_str(), pre, c[k]);
+        } else if (P.empty()) o.f("    const KF %s%d = %s;", pre, c[k], pk.c_str());
+        else o.f("    const KF %s%d = %s * %s;", pre, c[k], P.c_str(), pk.c_str());
       }
     }
   }
@@ -532,7 +686,7 @@ struct Gen {
   // logits dm[c] = H[c] - p[c]*H[v], which REPLACES the node's probability value (register or slot).  Returns the name of
   // H[n].  Nothing is stored per leaf: the row's x stays in its slots for the final pass.
   std::string leaf_g(int k, const std::string& Q) {
-    o.f("    const float G%d = %s * (%s(%s) - ((posy == %d) ? Z : 0.f));", k, Q.c_str(), (plan.knobs.expm & 2) ? "exp01m" : "exp01", Q.c_str(), t.pos[k]);
+    o.f("    const KF G%d = %s * (%s(%s) - sel_eq(posy, %d, Z, 0.f));", k, Q.c_str(), (plan.knobs.expm & 2) ? "exp01m" : "exp01", Q.c_str(), t.pos[k]);
     return "G" + std::to_string(k);
   }
   void node_grad(int n, const std::string& H, const std::vector<std::string>& h, bool opaque) {
@@ -540,9 +694,10 @@ struct Gen {
     const int vid = plan.value_slot[n];
     if (binary(n)) {
       std::string sp = opaque ? "Qs" + std::to_string(n) : vget(vid);
-      o.f("    const float pa%d = first_is_hi(%s) ? 1.f - fabsf(%s) : fabsf(%s);", n, sp.c_str(), sp.c_str(), sp.c_str());
-      char e[96];
-      snprintf(e, sizeof e, "cA * fmaf(-pa%d, %s, %s)", n, H.c_str(), h[0].c_str());
+      // p(first) = s + (1 or 0), see child_probs: H[first] - p(first)*H = (H[first] - (H or 0)) - s*H
+      o.f("    const KF pa%d = %s - sel_neg(%s, %s, 0.f);", n, h[0].c_str(), sp.c_str(), H.c_str());
+      char e[128];
+      snprintf(e, sizeof e, "cA * fmaf(-%s, %s, pa%d)", sp.c_str(), H.c_str(), n);
       dset(vid, e);
     } else {
       for (size_t k = 0; k < c.size(); ++k) {
@@ -563,12 +718,12 @@ struct Gen {
     }
     const std::string H = "G" + std::to_string(n);
     if (c.size() == 1) {
-      o.f("    const float %s = %s;", H.c_str(), h[0].c_str());
+      o.f("    const KF %s = %s;", H.c_str(), h[0].c_str());
       return H;
     }
     std::string sum;
     for (size_t k = 0; k < h.size(); ++k) sum += (k ? " + " : "") + h[k];
-    o.f("    const float %s = %s;", H.c_str(), sum.c_str());
+    o.f("    const KF %s = %s;", H.c_str(), sum.c_str());
     note(H);
     node_grad(n, H, h, true);
     return H;
@@ -584,7 +739,7 @@ struct Gen {
     const std::string H = "G" + std::to_string(n);
     std::string sum;
     for (size_t k = 0; k < h.size(); ++k) sum += (k ? " + " : "") + h[k];
-    o.f("    const float %s = %s;", H.c_str(), sum.c_str());
+    o.f("    const KF %s = %s;", H.c_str(), sum.c_str());
     note(H);
     if (c.size() > 1) node_grad(n, H, h, false);
     return H;
@@ -605,11 +760,11 @@ struct Gen {
     auto an = [&](int k) { return std::string(ap) + std::to_string(k); };
     auto fma_a = [&](int child, const std::string& d) {
       const std::string inv = lit(1.0 / t.cnt[child]);
-      if (A.empty()) o.f("    const float %s%d = %s * %s;", ap, child, d.c_str(), inv.c_str());
-      else o.f("    const float %s%d = fmaf(%s, %s, %s);", ap, child, d.c_str(), inv.c_str(), A.c_str());
+      if (A.empty()) o.f("    const KF %s%d = %s * %s;", ap, child, d.c_str(), inv.c_str());
+      else o.f("    const KF %s%d = fmaf(%s, %s, %s);", ap, child, d.c_str(), inv.c_str(), A.c_str());
     };
     if (c.size() == 1) {
-      o.f("    const float %s%d = %s;", ap, c[0], A.empty() ? "0.f" : A.c_str());
+      o.f("    const KF %s%d = %s;", ap, c[0], A.empty() ? "0.f" : A.c_str());
     } else if (binary(n)) {
       const std::string d = fenced(dget(vid));
       fma_a(c[0], d);
@@ -637,36 +792,36 @@ struct Gen {
     auto onn = [&](int k) { return std::string(op) + std::to_string(k); };
     auto fma_a = [&](int child, const std::string& d) {
       const std::string inv = lit(1.0 / t.cnt[child]);
-      if (A.empty()) o.f("    const float %s%d = %s * %s;", ap, child, d.c_str(), inv.c_str());
-      else o.f("    const float %s%d = fmaf(%s, %s, %s);", ap, child, d.c_str(), inv.c_str(), A.c_str());
+      if (A.empty()) o.f("    const KF %s%d = %s * %s;", ap, child, d.c_str(), inv.c_str());
+      else o.f("    const KF %s%d = fmaf(%s, %s, %s);", ap, child, d.c_str(), inv.c_str(), A.c_str());
     };
     if (c.size() == 1) {
-      o.f("    const float %s%d = %s; const float %s%d = %s;", op, c[0], onv.c_str(), ap, c[0], A.empty() ? "0.f" : A.c_str());
+      o.f("    const KF %s%d = %s; const KF %s%d = %s;", op, c[0], onv.c_str(), ap, c[0], A.empty() ? "0.f" : A.c_str());
     } else if (binary(n)) {
       const int a = c[0], b = c[1];
-      o.f("    const float %s%d = (posy < %d) ? %s : 0.f; const float %s%d = %s - %s%d;", op, a, t.end[a], onv.c_str(), op, b, onv.c_str(), op, a);
-      o.f("    const float ht%d = %s; const float hq%d = ex2(-fabsf(ht%d)); const float hd%d = 1.f + hq%d; const float hr%d = rcp(hd%d);",
+      o.f("    const KF %s%d = sel_lt(posy, %d, %s, 0.f); const KF %s%d = %s - %s%d;", op, a, t.end[a], onv.c_str(), op, b, onv.c_str(), op, a);
+      o.f("    const KF ht%d = %s; const KF hq%d = ex2(-fabsf(ht%d)); const KF hd%d = 1.f + hq%d; const KF hr%d = rcp(hd%d);",
           n, fenced(vget(vid)).c_str(), n, n, n, n, n, n);
-      o.f("    const float pa%d = ht%d >= 0.f ? hr%d : hq%d * hr%d;", n, n, n, n, n);
+      o.f("    const KF pa%d = sel_ge0(ht%d, hr%d, hq%d * hr%d);", n, n, n, n, n);
       // -log2 p(child) = log2(1 + 2^-|t|) + max(-t, 0) for the first child, + max(t, 0) for the second
       o.f("    lp = fmaf(%s, lg2(hd%d), lp); lp = fmaf(%s%d, fmaxf(-ht%d, 0.f), lp); lp = fmaf(%s%d, fmaxf(ht%d, 0.f), lp);",
           onv.c_str(), n, op, a, n, op, b, n);
-      o.f("    const float d%d = nkg * fmaf(-pa%d, %s, %s%d);", n, n, onv.c_str(), op, a);
+      o.f("    const KF d%d = nkg * fmaf(-pa%d, %s, %s%d);", n, n, onv.c_str(), op, a);
       fma_a(a, "d" + std::to_string(n));
       fma_a(b, "-d" + std::to_string(n));
     } else {
       std::string sum;
       for (size_t k = 0; k < c.size(); ++k) {
         const int ck = c[k];
-        o.f("    const float %s%d = ((unsigned)(posy - %d) < %du) ? %s : 0.f;", op, ck, t.beg[ck], t.cnt[ck], onv.c_str());
-        o.f("    const float km_%d = %s; const float kq_%d = ex2(km_%d);", ck, kget(vid + (int)k).c_str(), ck, ck);
+        o.f("    const KF %s%d = sel_in(posy, %d, %d, %s, 0.f);", op, ck, t.beg[ck], t.cnt[ck], onv.c_str());
+        o.f("    const KF km_%d = %s; const KF kq_%d = ex2(km_%d);", ck, kget(vid + (int)k).c_str(), ck, ck);
         sum += (k ? " + kq_" : "kq_") + std::to_string(ck);
       }
-      o.f("    const float hs%d = %s; const float hr%d = rcp(hs%d);", n, sum.c_str(), n, n);
+      o.f("    const KF hs%d = %s; const KF hr%d = rcp(hs%d);", n, sum.c_str(), n, n);
       o.f("    lp = fmaf(%s, lg2(hs%d), lp);", onv.c_str(), n);
       for (int ck : c) {
         o.f("    lp = fmaf(-%s%d, km_%d, lp);", op, ck, ck);
-        o.f("    const float dk%d = nkg * fmaf(-kq_%d * hr%d, %s, %s%d);", ck, ck, n, onv.c_str(), op, ck);
+        o.f("    const KF dk%d = nkg * fmaf(-kq_%d * hr%d, %s, %s%d);", ck, ck, n, onv.c_str(), op, ck);
         fma_a(ck, "dk" + std::to_string(ck));
       }
     }
@@ -724,25 +879,25 @@ struct Gen {
       for (int pos = t.beg[team.cut_nodes[k]]; pos < t.end[team.cut_nodes[k]]; ++pos) own.push_back(t.leaf_at[pos]);
     const bool first = w == 0;
     o.f("// warp %d of %d: %d cut subtrees, %d leaves%s", w, W, (int)cuts.size(), (int)own.size(), first && teamed() ? " + the top tree" : "");
-    o.f("KA_DEV void ka_part%d(const KAParams& p, long long yy, bool live, KA_XSB xsb, u32 zr, float& loss_acc) {", w);
+    o.f("KA_DEV void ka_part%d(const KAParams& p, KY yy, KB live, KA_XSB xsb, u32 zr, float& loss_acc) {", w);
     if (loss_mode()) {
       // rows with an out-of-range target are ignored: zero loss, zero gradient (nn.CrossEntropyLoss's ignore_index rows; the
       // reference's class_index_to_child_index has no entry for them either).  They run the arithmetic on target 0 and are
       // masked at the two places where a row has an effect.
-      o.f("    const bool valid = (unsigned long long)yy < %dull;", C);
-      o.f("    const int y = valid ? (int)(unsigned)yy : 0;");
-      o.f("    const int posy = ka_pos[y];");
+      o.f("    const KB valid = ka_valid(yy);");
+      o.f("    const KI y = ka_target(yy, valid);");
+      o.f("    const KI posy = ka_lookup(ka_pos, y);");
       o.f("    const float kx = p.w_xent * p.inv_rows, kt = p.w_tree * p.inv_rows;");
       if (first) o.f("    KA_LDX_DYN(xy, y);");
       // max over the own leaves
-      o.f("    float m0 = -3.0e38f, m1 = m0, m2 = m0, m3 = m0;");
+      o.f("    KF m0 = -3.0e38f, m1 = m0, m2 = m0, m3 = m0;");
       for (size_t i = 0; i < own.size(); ++i) {
         const std::string xv = ldx(own[i]);
         o.f("    m%d = fmaxf(m%d, %s);", (int)(i & 3), (int)(i & 3), xv.c_str());
       }
-      o.f("    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));");
-      o.f("    const float nm = -mx * kLog2e;");
-      o.f("    float zx0 = 0.f, zx1 = 0.f, zx2 = 0.f, zx3 = 0.f;");
+      o.f("    const KF mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));");
+      o.f("    const KF nm = -mx * kLog2e;");
+      o.f("    KF zx0 = 0.f, zx1 = 0.f, zx2 = 0.f, zx3 = 0.f;");
     }
     // ---- pass 1 over the own subtrees ----
     declare_kary();
@@ -752,7 +907,7 @@ struct Gen {
       if (teamed()) stx(ex_p(k), "s" + std::to_string(r));
     }
     if (loss_mode()) {
-      o.f("    const float zxw = (zx0 + zx1) + (zx2 + zx3);");
+      o.f("    const KF zxw = (zx0 + zx1) + (zx2 + zx3);");
       if (teamed()) { stx(ex_w(0, w), "mx"); stx(ex_w(1, w), "zxw"); }
     }
     o.f("    KA_BAR();");
@@ -763,16 +918,16 @@ struct Gen {
         for (int u = 0; u < W; ++u) { ms.push_back(ldx(ex_w(0, u))); zs.push_back(ldx(ex_w(1, u))); }
         std::string mg = ms[0];
         for (int u = 1; u < W; ++u) mg = "fmaxf(" + mg + ", " + ms[u] + ")";
-        o.f("    const float mxg = %s;", mg.c_str());
-        o.f("    float zxg = 0.f;");
+        o.f("    const KF mxg = %s;", mg.c_str());
+        o.f("    KF zxg = 0.f;");
         for (int u = 0; u < W; ++u) o.f("    zxg = fmaf(%s, ex2((%s - mxg) * kLog2e), zxg);", zs[u].c_str(), ms[u].c_str());
       } else {
-        o.f("    const float mxg = mx, zxg = zxw;");
+        o.f("    const KF mxg = mx, zxg = zxw;");
       }
-      o.f("    const float l2zx = lg2(zxg);");
-      o.f("    const float lse1 = fmaf(l2zx, kLn2, mxg);");
+      o.f("    const KF l2zx = lg2(zxg);");
+      o.f("    const KF lse1 = fmaf(l2zx, kLn2, mxg);");
       o.f("    const float cx = kx * p.grad_scale;");
-      o.f("    const float nl = -fmaf(mxg, kLog2e, l2zx);");
+      o.f("    const KF nl = -fmaf(mxg, kLog2e, l2zx);");
     }
     // ---- top tree, pass 1 and the way down (warp 0) ----
     if (teamed()) {
@@ -780,7 +935,7 @@ struct Gen {
         top = true;
         up(t.root);
         if (v.mode == kSpecHardLoss) {
-          o.f("    float lp = 0.f;");
+          o.f("    KF lp = 0.f;");
           o.f("    const float nkg = -kt * p.grad_scale;");
           hard(t.root, "", "");
         } else {
@@ -795,8 +950,8 @@ struct Gen {
       for (int k : cuts) {
         const int r = team.cut_nodes[k];
         std::string P = teamed() ? ldx(ex_p(k)) : "";
-        if (teamed()) { o.f("    const float P%d = %s;", r, P.c_str()); P = "P" + std::to_string(r); }
-        if (leaf(r)) { if (!teamed()) o.f("    const float P%d = 1.f;", r); leaf_prob(r, "P", 0); }
+        if (teamed()) { o.f("    const KF P%d = %s;", r, P.c_str()); P = "P" + std::to_string(r); }
+        if (leaf(r)) { if (!teamed()) o.f("    const KF P%d = 1.f;", r); leaf_prob(r, "P", 0); }
         else down(r, P, "P", 0);
       }
       o.f("}");
@@ -804,15 +959,15 @@ struct Gen {
     }
     if (v.mode == kSpecHardLoss) {
       if (!teamed()) {
-        o.f("    float lp = 0.f;");
+        o.f("    KF lp = 0.f;");
         o.f("    const float nkg = -kt * p.grad_scale;");
         hard(t.root, "", "");
       } else {
-        if (!first) { o.f("    float lp = 0.f;"); o.f("    const float nkg = -kt * p.grad_scale;"); }
+        if (!first) { o.f("    KF lp = 0.f;"); o.f("    const float nkg = -kt * p.grad_scale;"); }
         for (int k : cuts) {
           const int r = team.cut_nodes[k];
           const std::string on = ldx(ex_p(k)), A = ldx(ex_h(k));
-          o.f("    const float on%d = %s; const float A%d = %s;", r, on.c_str(), r, A.c_str());
+          o.f("    const KF on%d = %s; const KF A%d = %s;", r, on.c_str(), r, A.c_str());
           if (leaf(r)) leaf_out(r, "A" + std::to_string(r));
           else hard(r, "on" + std::to_string(r), "A" + std::to_string(r));
         }
@@ -821,40 +976,40 @@ struct Gen {
         if (first) {
           std::string s = "0.f";
           for (int u = 0; u < W; ++u) s += " + " + ldx(ex_w(3, u));
-          o.f("    const float lpg = %s;", s.c_str());
+          o.f("    const KF lpg = %s;", s.c_str());
         }
       }
-      if (first) o.f("    if (live && valid) loss_acc += kx * (lse1 - xy) + kt * kLn2 * %s;", teamed() ? "lpg" : "lp");
+      if (first) o.f("    loss_acc += ka_hsum(sel(both(live, valid), kx * (lse1 - xy) + (kt * kLn2) * %s, 0.f));", teamed() ? "lpg" : "lp");
     } else {
       // soft loss: sum exp(P) and P[target] over the own leaves
-      o.f("    float z20 = 0.f, z21 = 0.f, z22 = 0.f, z23 = 0.f, pry = 0.f;");
+      o.f("    KF z20 = 0.f, z21 = 0.f, z22 = 0.f, z23 = 0.f, pry = 0.f;");
       acc = 0;
       std::vector<std::string> Pr(cuts.size());
       for (size_t i = 0; i < cuts.size(); ++i) {
         const int k = cuts[i], r = team.cut_nodes[k];
-        if (teamed()) { Pr[i] = ldx(ex_p(k)); o.f("    const float P%d = %s;", r, Pr[i].c_str()); Pr[i] = "P" + std::to_string(r); }
-        if (leaf(r)) { if (!teamed()) o.f("    const float P%d = 1.f;", r); leaf_prob(r, "P", 1); }
+        if (teamed()) { Pr[i] = ldx(ex_p(k)); o.f("    const KF P%d = %s;", r, Pr[i].c_str()); Pr[i] = "P" + std::to_string(r); }
+        if (leaf(r)) { if (!teamed()) o.f("    const KF P%d = 1.f;", r); leaf_prob(r, "P", 1); }
         else down(r, Pr[i], "P", 1);
       }
-      o.f("    const float Zw = (z20 + z21) + (z22 + z23);");
+      o.f("    const KF Zw = (z20 + z21) + (z22 + z23);");
       if (teamed()) {
         stx(ex_w(2, w), "Zw"); stx(ex_w(3, w), "pry");
         o.f("    KA_BAR();");
         std::string sz = "0.f", sp = "0.f";
         for (int u = 0; u < W; ++u) { sz += " + " + ldx(ex_w(2, u)); sp += " + " + ldx(ex_w(3, u)); }
-        o.f("    const float Z = %s; const float pryg = %s;", sz.c_str(), sp.c_str());
+        o.f("    const KF Z = %s; const KF pryg = %s;", sz.c_str(), sp.c_str());
       } else {
-        o.f("    const float Z = Zw, pryg = pry;");
+        o.f("    const KF Z = Zw, pryg = pry;");
       }
-      if (first) o.f("    if (live && valid) loss_acc += kx * (lse1 - xy) + kt * (kLn2 * lg2(Z) - pryg);");
-      o.f("    const float cA = kt * p.grad_scale * rcp(Z);");
+      if (first) o.f("    loss_acc += ka_hsum(sel(both(live, valid), kx * (lse1 - xy) + kt * (kLn2 * lg2(Z) - pryg), 0.f));");
+      o.f("    const KF cA = kt * p.grad_scale * rcp(Z);");
       // the merged down/up traversal of the own subtrees
       for (size_t i = 0; i < cuts.size(); ++i) {
         const int k = cuts[i], r = team.cut_nodes[k];
         std::string Q = teamed() ? "Q" + std::to_string(r) : "";
-        if (teamed()) o.f("    float Q%d = %s; KA_OPAQUE(Q%d);", r, Pr[i].c_str(), r);
+        if (teamed()) o.f("    KF Q%d = %s; KA_OPAQUE(Q%d);", r, Pr[i].c_str(), r);
         std::string H;
-        if (leaf(r)) { if (!teamed()) o.f("    const float Q%d = 1.f;", r); H = leaf_g(r, "Q" + std::to_string(r)); }
+        if (leaf(r)) { if (!teamed()) o.f("    const KF Q%d = 1.f;", r); H = leaf_g(r, "Q" + std::to_string(r)); }
         else H = updown(r, Q);
         if (teamed()) stx(ex_h(k), H);
       }
@@ -871,16 +1026,18 @@ struct Gen {
       for (int k : cuts) {
         const int r = team.cut_nodes[k];
         std::string A = "";
-        if (teamed()) { A = ldx(ex_h(k)); o.f("    const float A%d = %s;", r, A.c_str()); A = "A" + std::to_string(r); }
+        if (teamed()) { A = ldx(ex_h(k)); o.f("    const KF A%d = %s;", r, A.c_str()); A = "A" + std::to_string(r); }
         if (leaf(r)) leaf_out(r, A.empty() ? "0.f" : A);
         else back(r, A);
       }
     }
     // the slots of the own leaves now hold dL/dx except for the one-hot of the plain cross-entropy term
-    if (teamed()) o.f("    if (ka_owner[y] == %d) KA_ADDX_DYN(y, -cx);", w);
-    else o.f("    KA_ADDX_DYN(y, -cx);");
-    o.f("    if (!valid) {");
-    for (int c : own) o.f("      KA_STX(xsb, %d, %d, 0.f);", c, soff(c));
+    if (teamed()) o.f("    KA_ADDX_DYN(ka_owned(ka_owner, y, %d), y, -cx);", w);
+    else o.f("    KA_ADDX_DYN(ka_true(), y, -cx);");
+    // an ignored row gets a zero gradient row (rare: a loop, not straight-line code)
+    o.f("    if (!ka_all(valid)) {");
+    if (teamed()) o.f("      for (int c = 0; c < KA_C; ++c) if (ka_owner[c] == %d) KA_ZERO_IF(ka_not(valid), c);", w);
+    else o.f("      for (int c = 0; c < KA_C; ++c) KA_ZERO_IF(ka_not(valid), c);");
     o.f("    }");
     o.f("}");
   }
@@ -891,7 +1048,8 @@ struct Gen {
     o.s.reserve((size_t)C * 2600);
     U = v.mode == kSpecSoftFwd ? std::min(pv, v.ovec / 4) : pv;
     K = ((C / U) & 31) | 1;
-    o.f("#define KA_C %d\n#define KA_W %d", C, W);
+    const int RB = 32 * R();  // rows per block
+    o.f("#define KA_C %d\n#define KA_W %d\n#define KA_R %d", C, W, R());
     o.f("#ifdef KA_HOST\n#define KA_TPB 1\n#else\n#define KA_TPB %d\n#endif\n#define KA_U %du\n#define KA_K %du", kTPB * W, U, K);
     o.s += kPrelude;
     auto table = [&](const char* type, const char* name, const std::vector<int>& vals) {
@@ -915,12 +1073,12 @@ struct Gen {
     o.f("KA_DEV void ka_sweep_a(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int tid) {");
     o.f("    const char* xb = reinterpret_cast<const char*>(p.x) + row0 * p.ld * %d;", esz());
     o.f("    int row = (tid * %d) / KA_C, col = (tid * %d) %% KA_C;", pv, pv);
-    const int nvecs = 32 * C / pv;                          // vectors per block
+    const int nvecs = RB * C / pv;                          // vectors per block
     const int nit = (nvecs + kTPB * W - 1) / (kTPB * W);    // per thread
     // full block of contiguous rows (the common case): every load has an immediate offset from one pointer and a whole group
     // of loads is in flight before the first store needs its data
     o.f("#ifndef KA_HOST");
-    o.f("    if (nrows == 32 && p.ld == KA_C) {");
+    o.f("    if (nrows == %d && p.ld == KA_C) {", RB);
     o.f("      const char* gp = xb + tid * %d;", v.vec);
     const int maxld = std::max(1, plan.knobs.maxld * 16 / v.vec);
     for (int g0 = 0; g0 < nit; g0 += maxld) {
@@ -934,7 +1092,7 @@ struct Gen {
       }
       for (int it = g0; it < g1; ++it) {
         const bool guard = (it + 1) * kTPB * W > nvecs;
-        o.f("      %s{ const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);", guard ? "if (row < 32) " : "");
+        o.f("      %s{ const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);", guard ? ("if (row < " + std::to_string(RB) + ") ").c_str() : "");
         for (int j = 0; j < pv; ++j) o.f("        KA_STD(a, %d, %d, %s);", j, eoff(j), elem("lv", it * pv + j).c_str());
         o.f("      }");
         coop_step(pv);
@@ -944,7 +1102,7 @@ struct Gen {
     o.f("    }");
     o.f("#endif");
     if (plan.knobs.unroll > 0) o.f("#pragma unroll %d", plan.knobs.unroll); else o.f("#pragma unroll");
-    o.f("#ifdef KA_HOST\n    const int nit = %d;\n#else\n    const int nit = %d;\n#endif", C / pv, nit);
+    o.f("#ifdef KA_HOST\n    const int nit = %d;\n#else\n    const int nit = %d;\n#endif", R() * C / pv, nit);
     o.f("    for (int it = 0; it < nit; ++it) {");
     o.f("      if (row < nrows) {");
     o.f("        const char* gp = xb + ((long long)row * p.ld + col) * %d;", esz());
@@ -959,7 +1117,7 @@ struct Gen {
     // ---- the row code, one function per warp of the team ----
     for (int w = 0; w < W; ++w) emit_part(w);
     o.f("#ifdef KA_HOST");
-    o.f("static void ka_part(int w, const KAParams& p, long long yy, bool live, KA_XSB xsb, u32 zr, float& loss_acc) {");
+    o.f("static void ka_part(int w, const KAParams& p, KY yy, KB live, KA_XSB xsb, u32 zr, float& loss_acc) {");
     o.f("  switch (w) {");
     for (int w = 0; w < W; ++w) o.f("    case %d: ka_part%d(p, yy, live, xsb, zr, loss_acc); break;", w, w);
     o.f("  }");
@@ -973,17 +1131,17 @@ struct Gen {
       const int ov = fwd ? v.ovec : v.vec;          // bytes per output vector
       const int po = fwd ? v.ovec / 4 : pv;         // elements per output vector
       const int oesz = fwd ? 4 : esz();
-      const int nvo = 32 * C / po;
+      const int nvo = RB * C / po;
       const int nito = (nvo + kTPB * W - 1) / (kTPB * W);
       if (fwd) o.f("    char* ob = reinterpret_cast<char*>(p.class_probs + row0 * KA_C); const long long old = KA_C;");
       else o.f("    char* ob = reinterpret_cast<char*>(p.grad) + row0 * p.ld * %d; const long long old = p.ld;", oesz);
       o.f("    int row = (tid * %d) / KA_C, col = (tid * %d) %% KA_C;", po, po);
       o.f("#ifndef KA_HOST");
-      o.f("    if (nrows == 32 && old == KA_C) {");
+      o.f("    if (nrows == %d && old == KA_C) {", RB);
       o.f("      char* op = ob + tid * %d;", ov);
       for (int it = 0; it < nito; ++it) {
         const bool guard = (it + 1) * kTPB * W > nvo;
-        o.f("      %s{ const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);", guard ? "if (row < 32) " : "");
+        o.f("      %s{ const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);", guard ? ("if (row < " + std::to_string(RB) + ") ").c_str() : "");
         std::vector<std::string> vals;
         for (int j = 0; j < po; ++j) {
           o.f("        KA_LDD(q%d, a, %d, %d);", j, j, eoff(j));
@@ -997,7 +1155,7 @@ struct Gen {
       o.f("    }");
       o.f("#endif");
       if (plan.knobs.unroll > 0) o.f("#pragma unroll %d", plan.knobs.unroll); else o.f("#pragma unroll");
-      o.f("#ifdef KA_HOST\n    const int nit = %d;\n#else\n    const int nit = %d;\n#endif", C / po, nito);
+      o.f("#ifdef KA_HOST\n    const int nit = %d;\n#else\n    const int nit = %d;\n#endif", R() * C / po, nito);
       o.f("    for (int it = 0; it < nit; ++it) {");
       o.f("      if (row < nrows) {");
       o.f("        const KA_XSB a = KA_SLOT_ADDR(xsw, col, row);");
@@ -1020,19 +1178,24 @@ struct Gen {
     o.f("  extern __shared__ float ka_smem[];");
     o.f("  const int tid = threadIdx.x, lane = tid & 31;");
     o.f("  const u32 xsw = (u32)__cvta_generic_to_shared(ka_smem);");
-    o.f("  const u32 xsb = xsw + ((lane * KA_K) & 31u) * 4u;");
+    o.f("  const u32 xsb = xsw + ((lane * KA_K) & 31u) * %du;", 4 * R());
     o.f("  float loss_acc = 0.f;");
     o.f("  const u32 zr = (u32)((unsigned long long)p.B >> 48);  // zero at run time, unknown at compile time (scheduling fences)");
-    o.f("  for (long long row0 = (long long)blockIdx.x * 32; row0 < p.B; row0 += (long long)gridDim.x * 32) {");
-    o.f("    const int nrows = (int)(p.B - row0 < 32 ? p.B - row0 : 32);");
-    o.f("    long long yy = 0;");
-    if (loss_mode()) o.f("    if (lane < nrows) yy = p.targets[row0 + lane];");
+    o.f("  for (long long row0 = (long long)blockIdx.x * %d; row0 < p.B; row0 += (long long)gridDim.x * %d) {", RB, RB);
+    o.f("    const int nrows = (int)(p.B - row0 < %d ? p.B - row0 : %d);", RB, RB);
+    if (R() == 1) {
+      o.f("    KY yy = 0; const KB live = lane < nrows;");
+      if (loss_mode()) o.f("    if (live) yy = p.targets[row0 + lane];");
+    } else {
+      o.f("    KY yy; yy.a = 0; yy.b = 0; const KB live = mkb(2 * lane < nrows, 2 * lane + 1 < nrows);");
+      if (loss_mode()) o.f("    if (live.a) yy.a = p.targets[row0 + 2 * lane]; if (live.b) yy.b = p.targets[row0 + 2 * lane + 1];");
+    }
     if (plan.knobs.prefetch > 0) {
       // the lines of a block further ahead go to L2 now, so that its sweep A pays an L2 hit instead of an HBM access
       o.f("    {");
-      o.f("      const long long pr0 = row0 + %dll * gridDim.x * 32;", plan.knobs.prefetch);
+      o.f("      const long long pr0 = row0 + %dll * gridDim.x * %d;", plan.knobs.prefetch, RB);
       o.f("      if (pr0 < p.B && p.ld <= 2 * KA_C) {");
-      o.f("        const long long pn = p.B - pr0 < 32 ? p.B - pr0 : 32;");
+      o.f("        const long long pn = p.B - pr0 < %d ? p.B - pr0 : %d;", RB, RB);
       o.f("        const char* pb = reinterpret_cast<const char*>(p.x) + pr0 * p.ld * %d;", esz());
       o.f("        const long long plen = ((pn - 1) * p.ld + KA_C) * %d;", esz());
       o.f("        for (long long po = tid * 128; po < plen; po += KA_TPB * 128) asm volatile(\"prefetch.global.L2 [%%0];\" :: \"l\"(pb + po));");
@@ -1043,11 +1206,11 @@ struct Gen {
     o.f("    %s;", W > 1 ? "__syncthreads()" : "__syncwarp()");
     if (W > 1) {
       o.f("    switch (tid >> 5) {");
-      for (int w = 0; w < W; ++w) o.f("      case %d: ka_part%d(p, yy, lane < nrows, xsb, zr, loss_acc); break;", w, w);
+      for (int w = 0; w < W; ++w) o.f("      case %d: ka_part%d(p, yy, live, xsb, zr, loss_acc); break;", w, w);
       o.f("    }");
     } else {
       // a single warp has no barriers inside the row function: threads without a row skip it
-      o.f("    if (lane < nrows) ka_part0(p, yy, true, xsb, zr, loss_acc);");
+      o.f("    if (lane * %d < nrows) ka_part0(p, yy, live, xsb, zr, loss_acc);", R());
     }
     o.f("    %s;", W > 1 ? "__syncthreads()" : "__syncwarp()");
     if (loss_mode()) o.f("    if (p.grad) ka_sweep_b(p, row0, nrows, xsw, tid);");
@@ -1123,6 +1286,12 @@ Team make_team(const KTree& t, int W) {
   return tm;
 }
 
+int auto_rows(const KTree& t, const Knobs& knobs) {
+  if (knobs.rows > 0) return knobs.rows;
+  (void)t;
+  return 1;
+}
+
 int auto_warps(const KTree& t) {
   // measured on B200 (gpurun_out/tune_v5.jsonl): one warp per row block is fastest up to ~128 leaves (12 resident warps
   // per SM); at 200 leaves one warp needs 255 registers and 30 KB (7 warps per SM) and a team of 4 wins
@@ -1136,6 +1305,7 @@ int auto_warps(const KTree& t) {
 Plan make_plan(const KTree& t, int max_smem, const Knobs& knobs) {
   Plan p;
   p.knobs = knobs;
+  p.default_knobs = knobs.is_default();
   p.team = make_team(t, knobs.warps > 0 ? knobs.warps : auto_warps(t));
   const int W = p.team.W;
   p.threads = kTPB * W;
@@ -1154,8 +1324,18 @@ Plan make_plan(const KTree& t, int max_smem, const Knobs& knobs) {
       if (u >= t.C) st.push_back({u, 0});
     }
   }
-  // register budget per thread: what a full SM of resident teams allows, minus the working set of the passes
-  const int regcap = W == 1 ? knobs.regcap : std::min(knobs.regcap, std::max(16, 65536 / (kTPB * W) - 72));
+  if (p.knobs.expm < 0) p.knobs.expm = W == 1 ? 1 : 3;
+  // Scheduling fences trade registers for instruction-level parallelism.  One warp per block, 65..128 leaves: no fences and at
+  // most 8 resident warps (255 registers, a few dozen bytes of local spills) beat fences every 8 nodes at 168 registers and 12
+  // warps (100 leaves: 42.8 % vs 39.7 % of the HBM peak); teams want the occupancy and a window of 16 nodes (200 leaves: 24.5 %
+  // vs 23.5 %); small hierarchies keep the round-1 setting.
+  const bool wide = W == 1 && t.C > 64;
+  if (p.knobs.fence < 0) p.knobs.fence = wide ? 0 : (W > 1 && t.C <= 256 ? 16 : 8);
+  p.rows = auto_rows(t, knobs);
+  const int R = p.rows;
+  // register budget per thread: what a full SM of resident teams allows, minus the working set of the passes; a value of a
+  // two-row thread is a register pair
+  const int regcap = (W == 1 ? knobs.regcap : std::min(knobs.regcap, std::max(16, 65536 / (kTPB * W) - 72))) / R;
   std::vector<int> in_regs(W, 0), nspill(W, 0);
   for (int n : order) {
     const size_t k = t.ch[n - t.C].size();
@@ -1173,11 +1353,12 @@ Plan make_plan(const KTree& t, int max_smem, const Knobs& knobs) {
   int maxregs = 0;
   for (int w = 0; w < W; ++w) { p.maxspill = std::max(p.maxspill, nspill[w]); maxregs = std::max(maxregs, in_regs[w]); }
   const int slots = t.C + W * p.maxspill + 2 * p.team.ncut() + 4 * W;
-  p.smem_bytes = (t.C * 32 + t.C + 36 + (slots - t.C) * 32) * 4;
-  const int regs = std::min(255, (maxregs + 64 + 7) / 8 * 8);
+  p.smem_bytes = (t.C * 32 + t.C + 36 + (slots - t.C) * 32) * 4 * R;
+  const int regs = std::min(255, (maxregs * R + (R == 1 ? 64 : 96) + 7) / 8 * 8);
   int by_regs = 65536 / (kTPB * W * regs);
   int by_smem = (max_smem > 0 ? max_smem : 227 * 1024) / std::max(1, p.smem_bytes + 1024);
   p.min_blocks = std::max(1, std::min(32, std::min(by_regs, by_smem)));
+  if (wide && knobs.fence < 0) p.min_blocks = std::min(p.min_blocks, 8);
   if (knobs.minb > 0) p.min_blocks = knobs.minb;
   return p;
 }
@@ -1231,8 +1412,9 @@ int compile_cubin(const std::string& src, std::vector<char>* cubin, std::string*
   Nvrtc::prog prog = nullptr;
   int rc = n->CreateProgram(&prog, src.c_str(), "nbdt_tree_ka.cu", 0, nullptr, nullptr);
   if (rc) { *log = std::string("nvrtcCreateProgram: ") + n->GetErrorString(rc); return -1; }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "--ptxas-options=-v", "-default-device"};
-  rc = n->CompileProgram(prog, 5, opts);
+  // -lineinfo quadruples the cubin (5.5 MB at 1000 leaves): only for profiling (ncu --import-source), NBDT_B200_KA_LINEINFO=1
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--ptxas-options=-v", "-default-device", "-lineinfo"};
+  rc = n->CompileProgram(prog, getenv("NBDT_B200_KA_LINEINFO") ? 5 : 4, opts);
   size_t ls = 0;
   if (n->GetProgramLogSize(prog, &ls) == 0 && ls > 1) {
     log->resize(ls);
@@ -1299,10 +1481,10 @@ std::vector<std::string> cache_read_dirs() {
   return v;
 }
 
-std::string variant_name(const KTree& t, const Variant& v, const Knobs& k) {
+std::string variant_name(const KTree& t, const Variant& v, const Knobs& k, bool dflt) {
   char b[192];
   int n = snprintf(b, sizeof b, "ka%d_%016llx_m%d_t%d_v%d_o%d", kGeneratorVersion, t.hash, v.mode, v.dtype, v.vec, v.ovec);
-  if (!k.is_default()) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d_w%d_e%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence, k.warps, k.expm);
+  if (!dflt) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d_w%d_e%d_x%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence, k.warps, k.expm, k.rows);
   return b;
 }
 
@@ -1363,7 +1545,7 @@ int jit_policy() {
 
 // cubin for one variant: cache hit, or generate + compile + store.  Returns 0 on success.
 int obtain_cubin(const KTree& t, const Plan& plan, const Variant& v, int policy, std::vector<char>* cubin, std::string* log) {
-  const std::string name = variant_name(t, v, plan.knobs);
+  const std::string name = variant_name(t, v, plan.knobs, plan.default_knobs);
   for (const std::string& d : cache_read_dirs())
     if (read_file(d + "/" + name + ".cubin", cubin)) return 0;
   if (policy < 2) { *log = "not in the kernel cache and NBDT_B200_TREE_JIT=cache"; return -1; }
@@ -1437,7 +1619,7 @@ int tree_jit_launch(TreeJit* t, int mode, int dtype, const SpecParams& p, void* 
       std::string log;
       if (obtain_cubin(t->tree, t->plan, v, t->policy, &cubin, &log)) {
         L->failed = true;
-        if (getenv("NBDT_B200_TREE_JIT_VERBOSE")) fprintf(stderr, "[nbdt_b200] tree JIT unavailable for %s: %s\n", variant_name(t->tree, v, t->plan.knobs).c_str(), log.c_str());
+        if (getenv("NBDT_B200_TREE_JIT_VERBOSE")) fprintf(stderr, "[nbdt_b200] tree JIT unavailable for %s: %s\n", variant_name(t->tree, v, t->plan.knobs, t->plan.default_knobs).c_str(), log.c_str());
         return -1;
       }
       cudaError_t e = cudaLibraryLoadData(&L->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
@@ -1457,9 +1639,10 @@ int tree_jit_launch(TreeJit* t, int mode, int dtype, const SpecParams& p, void* 
         return -1;
       }
     }
-    t->last_variant = variant_name(t->tree, v, t->plan.knobs);
+    t->last_variant = variant_name(t->tree, v, t->plan.knobs, t->plan.default_knobs);
   }
-  long long grid = (p.B + 31) / 32;
+  const int rb = 32 * t->plan.rows;
+  long long grid = (p.B + rb - 1) / rb;
   grid = std::min<long long>(grid, (long long)t->sm_count * L->blocks_per_sm);
   if (grid < 1) grid = 1;
   SpecParams sp = p;

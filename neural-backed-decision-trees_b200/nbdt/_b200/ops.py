@@ -156,6 +156,88 @@ class SoftRulesFunction(torch.autograd.Function):
         return soft_backward(ctx.tree, logits, grad_probs).reshape(logits.shape), None
 
 
+def _node_tables(dt, device):
+    """(M, seg) for the backward of node_outputs, cached on the device tree: M (S x C fp32) maps a gradient on the packed node
+    logits to the class logits -- M[e, c] = 1/#leaves(e) for the classes c under child edge e (a node logit is the MEAN of the
+    class logits under the child, reference nbdt/model.py:83-97) -- and seg (S int64) is the inner node every edge belongs to."""
+    cache = dt.__dict__.setdefault("_node_tables", {})
+    key = str(device)
+    if key not in cache:
+        import numpy as np
+
+        C, N = dt.num_classes, dt.num_inodes
+        ptr, node = dt.child_ptr, dt.child_node
+        under = {}
+        stack = [int(dt.root) + C]
+        while stack:  # iterative post-order: hierarchies may be deep chains
+            n = stack[-1]
+            kids = [int(k) for k in node[ptr[n - C]:ptr[n - C + 1]]]
+            todo = [k for k in kids if k >= C and k not in under]
+            if todo:
+                stack.extend(todo)
+                continue
+            under[n] = [c for k in kids for c in ([k] if k < C else under[k])]
+            stack.pop()
+        S = int(ptr[N])
+        M = np.zeros((S, C), dtype=np.float32)
+        seg = np.zeros((S,), dtype=np.int64)
+        for i in range(N):
+            for e in range(int(ptr[i]), int(ptr[i + 1])):
+                k = int(node[e])
+                leaves = [k] if k < C else under[k]
+                M[e, leaves] = 1.0 / len(leaves)
+                seg[e] = i
+        cache[key] = (torch.from_numpy(M).to(device), torch.from_numpy(seg).to(device))
+    return cache[key]
+
+
+class NodeOutputsFunction(torch.autograd.Function):
+    """Differentiable per-node outputs (node logits, child probabilities, entropy; the predictions are integers).  The reference
+    builds them from autograd ops (nbdt/model.py:83-123), so criteria or analyses written on top of `get_node_logits`,
+    `get_all_node_outputs` / `forward_nodes` get gradients there; here the forward is the fused kernel and the backward is the
+    softmax / entropy chain rule on the saved probabilities followed by ONE product with the edge-to-class mean matrix
+    (csrc/linear.cu).  Not a hot path: the training losses use the fused loss kernels."""
+
+    @staticmethod
+    def forward(ctx, logits, tree):
+        nl, pr, preds, ent, _ = node_outputs(tree, logits)
+        ctx.tree, ctx.shape, ctx.dtype = tree, logits.shape, logits.dtype
+        ctx.save_for_backward(pr)
+        ctx.mark_non_differentiable(preds)
+        return nl, pr, preds, ent
+
+    @staticmethod
+    def backward(ctx, g_nl, g_pr, _g_preds, g_ent):
+        (pr,) = ctx.saved_tensors
+        dev = pr.device
+        dt = ctx.tree.device_tree(dev)
+        M, seg = _node_tables(dt, dev)
+        B, S = pr.shape
+        g = torch.zeros_like(pr) if g_nl is None else g_nl.float().clone()
+        t = None if g_pr is None else g_pr.float()
+        if g_ent is not None:  # entropy = -sum p ln p  ->  d/dp = -(ln p + 1)
+            te = g_ent.float()[:, seg] * (-(torch.log(pr.clamp_min(1e-30)) + 1.0))
+            t = te if t is None else t + te
+        if t is not None:      # softmax over the children of every node
+            dot = torch.zeros((B, dt.num_inodes), dtype=torch.float32, device=dev).index_add_(1, seg, t * pr)
+            g += pr * (t - dot[:, seg])
+        g = g.contiguous()
+        C = dt.num_classes
+        grad = torch.empty((B, C), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            L.check(L.load().nbdt_sgemm(B, C, S, _p(g), S, 1, _p(M), C, 1, _p(grad), C, None, 0, L.stream_ptr(dev)))
+        _count()
+        return grad.to(ctx.dtype).reshape(ctx.shape), None
+
+
+def node_outputs_autograd(tree, logits):
+    """node_outputs() that records an autograd graph when the logits ask for one: (logits, probs, preds, entropy, device tree)."""
+    if logits.requires_grad and torch.is_grad_enabled():
+        nl, pr, preds, ent = NodeOutputsFunction.apply(logits, tree)
+        return nl, pr, preds, ent, tree.device_tree(logits.device)
+    return node_outputs(tree, logits)
+
+
 class FusedTreeLossFunction(torch.autograd.Function):
     """loss and dloss/dlogits from ONE kernel launch; backward only rescales the saved gradient."""
 

@@ -57,7 +57,7 @@ class EmbeddedDecisionRules(nn.Module):
             "Either pass node or (new_to_old_classes mapping and num_classes)"
         )
         if node is not None and not new_to_old_classes and not num_classes and not node.has_other:
-            nl, _, _, _, dt = ops.node_outputs(node.tree, outputs)
+            nl, _, _, _, dt = ops.node_outputs_autograd(node.tree, outputs)
             i = [n.wnid for n in node.tree.inodes].index(node.wnid)
             return nl[:, int(dt.child_ptr[i]) : int(dt.child_ptr[i + 1])].to(outputs.dtype)
         ops.L.require_cuda(outputs, "get_node_logits")
@@ -74,7 +74,7 @@ class EmbeddedDecisionRules(nn.Module):
         if not nodes:
             return {}
         tree = nodes[0].tree
-        nl, pr, preds, ent, dt = ops.node_outputs(tree, outputs)
+        nl, pr, preds, ent, dt = ops.node_outputs_autograd(tree, outputs)
         index = {n.wnid: i for i, n in enumerate(tree.inodes)}
         out = {}
         for node in nodes:

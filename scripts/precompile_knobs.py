@@ -30,12 +30,16 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
 
 procs = []
 for arg in sys.argv[1:]:
+    if arg.startswith("--"):
+        continue
     vals = arg.split(",")
     env = dict(os.environ, KNOBS=arg)
     for k, v in zip(KNOBS, vals):
         env[k] = v
     for name in WANT:
         if "--small" in sys.argv and name.startswith("Imagenet"):
+            continue
+        if os.environ.get("TUNE_CASES") and {"CIFAR100": "100", "TinyImagenet200": "200", "Imagenet1000": "1000"}[name] not in os.environ["TUNE_CASES"].split(","):
             continue
         procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--one", name], env=env))
 for p in procs:

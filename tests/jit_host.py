@@ -66,33 +66,31 @@ static pthread_barrier_t ka_bar;
 static bool ka_bar_on = false;
 static void ka_host_bar() { if (ka_bar_on) pthread_barrier_wait(&ka_bar); }
 #define KA_BAR() ka_host_bar()
-#define KA_LDX(dst, base, slot, off) const float dst = (base)[slot]
-#define KA_STX(base, slot, off, val) (base)[slot] = (val)
-#define KA_ADDX_DYN(idx, val) xsb[idx] += (val)
-#define KA_OPAQUE(x)
-#define KA_LDX_DYN(dst, idx) const float dst = xsb[idx]
-#define KA_STX_DYN(idx, val) xsb[idx] = (val)
-#define KA_SLOT_ADDR(base, col, row) ((base) + (col))
-#define KA_STD(a, k, off, val) (a)[k] = (val)
-#define KA_LDD(dst, a, k, off) const float dst = (a)[k]
 #include "gen.cu"
 extern "C" void ka_run(const KAParams* p, float* loss) {
-  static float Xs[65536];
+  static float Xs[131072];
   float total = 0.f;
   if (KA_W > 1) { pthread_barrier_init(&ka_bar, nullptr, KA_W); ka_bar_on = true; }
-  for (long long row = 0; row < p->B; ++row) {  // KA_TPB == 1 on the host: a "block" is one row, its warps are host threads
-    ka_sweep_a(*p, row, 1, Xs, 0);
-    const long long yy = p->targets ? p->targets[row] : 0;
+  for (long long row = 0; row < p->B; row += KA_R) {  // KA_TPB == 1 on the host: a "block" is the KA_R rows of one thread, its warps are host threads
+    const int nrows = (int)(p->B - row < KA_R ? p->B - row : KA_R);
+    ka_sweep_a(*p, row, nrows, Xs, 0);
+#if KA_R == 1
+    const KY yy = p->targets ? p->targets[row] : 0;
+    const KB live = true;
+#else
+    KY yy; yy.a = p->targets ? p->targets[row] : 0; yy.b = (p->targets && nrows > 1) ? p->targets[row + 1] : 0;
+    const KB live = mkb(true, nrows > 1);
+#endif
     float acc[KA_W] = {0.f};
     if (KA_W == 1) {
-      ka_part(0, *p, yy, true, Xs, 0u, acc[0]);
+      ka_part(0, *p, yy, live, Xs, 0u, acc[0]);
     } else {
       std::vector<std::thread> th;
-      for (int w = 0; w < KA_W; ++w) th.emplace_back([&, w] { ka_part(w, *p, yy, true, Xs, 0u, acc[w]); });
+      for (int w = 0; w < KA_W; ++w) th.emplace_back([&, w] { ka_part(w, *p, yy, live, Xs, 0u, acc[w]); });
       for (auto& t : th) t.join();
     }
     for (int w = 0; w < KA_W; ++w) total += acc[w];
-    if (p->grad || p->class_probs) ka_sweep_b(*p, row, 1, Xs, 0);
+    if (p->grad || p->class_probs) ka_sweep_b(*p, row, nrows, Xs, 0);
   }
   if (KA_W > 1) { pthread_barrier_destroy(&ka_bar); ka_bar_on = false; }
   if (loss) *loss = total;

@@ -133,6 +133,40 @@ def test_get_node_logits_variants():
     assert sum(sel) == sub.shape[0] == len(tgt)
 
 
+@pytest.mark.parametrize("dataset,hierarchy", [("CIFAR10", "induced-ResNet18"), ("CIFAR100", "wordnet-single"), ("TinyImagenet200", "induced")])
+def test_node_outputs_carry_gradients(dataset, hierarchy):
+    """Criteria written on the per-node entry points (`forward_nodes`, `get_node_logits`) are differentiable in the reference
+    (autograd ops, nbdt/model.py:83-123); here the forward is the fused kernel and the backward an autograd.Function: the
+    gradient of a made-up criterion over node logits, child probabilities and entropies equals that of the same criterion written
+    in plain torch ops on a double-precision copy."""
+    from nbdt.model import HardEmbeddedDecisionRules
+    from nbdt.tree import Tree
+
+    tree = Tree(dataset, hierarchy=hierarchy)
+    rules = HardEmbeddedDecisionRules(tree=tree)
+    C = len(tree.classes)
+    torch.manual_seed(3)
+    x = (2 * torch.randn(5, C, device=DEV)).requires_grad_(True)
+    out = rules.forward_nodes(x)
+    loss = sum((o["logits"].float() ** 2).sum() * 0.1 + (o["probs"] ** 2).sum() + 0.5 * o["entropy"].sum() for o in out.values())
+    node = tree.inodes[len(tree.inodes) // 2]
+    loss = loss + rules.get_node_logits(x, node).float().sum()
+    loss.backward()
+
+    xr = x.detach().double().requires_grad_(True)
+    want = 0
+    for n in tree.inodes:
+        nl = torch.stack([xr[:, list(n.child_index_to_class_index[k])].mean(1) for k in range(n.num_classes)], 1)
+        p = torch.softmax(nl, 1)
+        want = want + (nl ** 2).sum() * 0.1 + (p ** 2).sum() - 0.5 * (p * torch.log(p)).sum()
+        if n is node:
+            want = want + nl.sum()
+    want.backward()
+    assert abs(loss.item() - want.item()) <= 1e-4 * abs(want.item())
+    np.testing.assert_allclose(x.grad.double().cpu().numpy(), xr.grad.cpu().numpy(), rtol=2e-4, atol=2e-5 * xr.grad.abs().max().item())
+    assert not out[tree.inodes[0].wnid]["preds"].requires_grad
+
+
 def test_seg_nbdt_shapes():
     from nbdt.model import SoftSegNBDT
 
