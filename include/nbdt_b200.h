@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NBDT_B200_VERSION 102 /* 102: run-time specialised tree kernels (nbdt_tree_jit_*, nbdt_tree_kernel_variant); out-of-range targets are ignored rows */
+#define NBDT_B200_VERSION 103 /* 103: BatchNorm statistics from the convolution epilogue (nbdt_conv2d_fwd_stats, nbdt_bn_finalize_partials); 102: run-time specialised tree kernels (nbdt_tree_jit_*, nbdt_tree_kernel_variant); out-of-range targets are ignored rows */
 
 enum { NBDT_OK = 0, NBDT_EINVAL = 1, NBDT_ECUDA = 2, NBDT_ETREE = 3, NBDT_ETOOLARGE = 4 };
 enum { NBDT_F32 = 0, NBDT_BF16 = 1, NBDT_F16 = 2 };
@@ -133,6 +133,16 @@ int nbdt_tree_jit_precompile(const nbdt_tree_desc* desc, int mode, int dtype);
 int nbdt_conv2d_fwd(const void* x, const void* wpack, void* y, const void* residual, int N, int H, int W,
                     int Cin, int Cout, int ksize, int stride, void* stream);
 
+/* The same convolution, with the BatchNorm batch statistics of y accumulated in its epilogue: every CTA writes one row of
+ * per-channel partial sums, partials[cta][0][c] = sum y[...,c], partials[cta][1][c] = sum y[...,c]^2 (of the bf16 values it
+ * stored).  partials: nbdt_conv2d_stats_floats(Cout) floats (0 = more channels than the fused path covers: use nbdt_bn_stats);
+ * *parts (host) = rows written.  nbdt_bn_finalize_partials turns them into the consumer BatchNorm's coefficients; the separate
+ * statistics pass over y is gone.  Replaces the batch-statistics half of F.batch_norm behind the nn.BatchNorm2d modules that
+ * follow a convolution in the reference's backbones (nbdt/models/resnet.py:47-54,69-74; pytorchcv pre-activation WRN units). */
+int nbdt_conv2d_fwd_stats(const void* x, const void* wpack, void* y, const void* residual, int N, int H, int W,
+                          int Cin, int Cout, int ksize, int stride, float* partials, int* parts, void* stream);
+long long nbdt_conv2d_stats_floats(int Cout);
+
 /* dx[N,H,W,Cin] = data gradient of the above for dy[N,H/s,W/s,Cout] (+ accumulate, same shape as dx; may
  * alias dx).  wpack_t: bf16 [ksize*ksize][Cin][Cout] from nbdt_conv_pack_weights. */
 int nbdt_conv2d_dgrad(const void* dy, const void* wpack_t, void* dx, const void* accumulate, int N, int H,
@@ -173,6 +183,10 @@ long long nbdt_bn_scratch_floats(int C);
 int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, float* sums,
                   float* mean_invstd, float* scale_shift, void* stream);
+/* The same from per-CTA partial sums [nparts][2][C] over M rows in total (written by nbdt_conv2d_fwd_stats). */
+int nbdt_bn_finalize_partials(const float* partials, int nparts, long long M, int C, int c_real, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                              float* mean_invstd, float* scale_shift, void* stream);
 /* Eval mode: scale_shift from the running statistics. */
 int nbdt_bn_eval_scale(int C, int c_real, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale_shift, void* stream);

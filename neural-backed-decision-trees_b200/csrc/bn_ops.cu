@@ -617,6 +617,21 @@ int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* ga
   return NBDT_OK;
 }
 
+// Training-mode BatchNorm coefficients from per-CTA partial sums somebody else produced: partials[part][0][c] = sum x,
+// [1][c] = sum x^2 over M rows in total -- the rows nbdt_conv2d_fwd_stats (conv_gemm.cu) writes from the convolution's
+// epilogue.  Same finalize kernel as nbdt_bn_stats (fp64 reduction in a fixed order, running-statistics update).
+int nbdt_bn_finalize_partials(const float* partials, int nparts, long long M, int C, int c_real, const float* gamma,
+                              const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                              float* mean_invstd, float* scale_shift, void* stream) {
+  NBDT_REQUIRE(partials && gamma && beta && mean_invstd && scale_shift, "NULL tensor");
+  NBDT_REQUIRE(C % 8 == 0 && C <= 8192 && M > 0 && nparts > 0, "bad shape M=%lld C=%d parts=%d", M, C, nparts);
+  bn_finalize_kernel<<<(C + 31) / 32, kFinalizeThreads, 0, (cudaStream_t)stream>>>(partials, nparts, M, C, c_real, gamma, beta,
+                                                                                running_mean, running_var, momentum, eps,
+                                                                                mean_invstd, scale_shift);
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
 // Floats the `sums` / `dsums` scratch buffers of nbdt_bn_stats / nbdt_bn_backward must hold for C channels:
 // reduced result [2][C] + gradient coefficients [3][C] + per-CTA partial sums.
 long long nbdt_bn_scratch_floats(int C) { return (long long)(kReduceCtasPerSm * sm_count()) * 2 * C + 5LL * C; }

@@ -59,6 +59,8 @@ struct TapGemmParams {
   long long out_sn, out_sh, out_sw;  // output strides in elements (channel stride 1)
   __nv_bfloat16* out;
   const __nv_bfloat16* residual;  // same geometry as out, or nullptr
+  float* stats;                   // nullptr, or [gridDim.x][2][Cout]: every CTA's sum and sum of squares per output channel of the
+                                  // bf16 values it stored (BatchNorm batch statistics of the consumer, bn_ops.cu finalizes them)
   int tap_map[kMaxTaps];
   int tap_dh[kMaxTaps];
   int tap_dw[kMaxTaps];
@@ -68,6 +70,38 @@ struct TapGemmParams {
   int grp_dh[3][3];
   int grp_wrow[3][3];
 };
+
+// BatchNorm statistics in the epilogue.  An epilogue warp holds 32 output rows x 32 channels of every chunk it stores: a
+// butterfly transpose-reduce (5 rounds, 31 shuffles per statistic) leaves channel j's sum and sum of squares over the 32 rows
+// in lane j, which adds them to the CTA's accumulators in shared memory; at the end of the kernel every CTA writes ONE row of
+// partial sums (no global atomics, deterministic finalize in bn_ops.cu).  The statistics are those of the bf16 values that
+// are stored, i.e. exactly what the separate pass over the tensor (bn_stats_kernel) would have read again.
+constexpr int kStatsMaxC = 1024;                     // output channels the shared accumulators cover
+constexpr int kStatsBytes = 2 * kStatsMaxC * 4;      // appended to every tap GEMM's dynamic shared memory
+
+__device__ __forceinline__ void stats_accumulate(const uint32_t (&o)[16], int lane, float* s_sum, float* s_sq) {
+  float a[32], b[32];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    a[2 * e] = __uint_as_float(o[e] << 16);
+    a[2 * e + 1] = __uint_as_float(o[e] & 0xffff0000u);
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) b[i] = a[i] * a[i];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;  // this lane keeps the upper half of what is left, its partner the lower half
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float sa = up ? a[i] : a[i + off], ka = up ? a[i + off] : a[i];
+      const float sb = up ? b[i] : b[i + off], kb = up ? b[i + off] : b[i];
+      a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+      b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+    }
+  }
+  atomicAdd(s_sum + lane, a[0]);
+  atomicAdd(s_sq + lane, b[0]);
+}
 
 // One pipeline stage holds kUnits consecutive (tap, 64-channel k-block) units: the MMA thread's per-stage
 // handshake (barrier probe, fence, commit ~ 160 cycles + ~32 cycles per tcgen05.mma issue, measured with
@@ -81,7 +115,7 @@ struct TapGemmCfg {
   static constexpr int kStageBytes = kUnits * kUnitBytes;
   static constexpr int kStages = (216 * 1024) / kStageBytes > 6 ? 6 : (216 * 1024) / kStageBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatsBytes;
 };
 
 template <int BLOCK_N>
@@ -99,6 +133,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
   uint64_t* tmem_full = bars + 2 * Cfg::kStages; // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [2][Cout] when p.stats
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) s_stats[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -243,6 +280,9 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_ld_wait();
+        uint32_t ow[16];  // the chunk as stored (bf16 pairs); zeros for rows outside the tensor
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ow[e] = 0u;
         if (in_range) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
           const uint4* res = p.residual ? reinterpret_cast<const uint4*>(p.residual + off + c0) : nullptr;
@@ -268,7 +308,13 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
               o[e] = *reinterpret_cast<const uint32_t*>(&b);
             }
             dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ow[q * 4 + e] = o[e];
           }
+        }
+        if (p.stats) {
+          float* acc_c = s_stats + n_tile * BLOCK_N + c0;
+          stats_accumulate(ow, lane, acc_c, acc_c + p.Cout);
         }
       }
       tc_fence_before();
@@ -281,6 +327,10 @@ tap_gemm_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    float* row = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) row[i] = s_stats[i];
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -308,7 +358,7 @@ struct TapGemm2Cfg {
   static constexpr int kStageBytes = kUnits * kUnitBytes;
   static constexpr int kStages = (216 * 1024) / kStageBytes > 6 ? 6 : (216 * 1024) / kStageBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kStatsBytes;
   static_assert(kUnitBytes % 1024 == 0 && kABytes % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
 };
 
@@ -326,6 +376,9 @@ tap_gemm2_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_consta
   uint64_t* tmem_full = bars + 2 * Cfg::kStages; // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]        (used in the leader CTA only)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [2][Cout] when p.stats
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) s_stats[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -472,6 +525,9 @@ tap_gemm2_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_consta
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_ld_wait();
+        uint32_t ow[16];  // the chunk as stored (bf16 pairs); zeros for rows outside the tensor
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ow[e] = 0u;
         if (in_range) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
           const uint4* res = p.residual ? reinterpret_cast<const uint4*>(p.residual + off + c0) : nullptr;
@@ -497,7 +553,13 @@ tap_gemm2_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_consta
               o[e] = *reinterpret_cast<const uint32_t*>(&b);
             }
             dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ow[q * 4 + e] = o[e];
           }
+        }
+        if (p.stats) {
+          float* acc_c = s_stats + n_tile * BLOCK_N + c0;
+          stats_accumulate(ow, lane, acc_c, acc_c + p.Cout);
         }
       }
       tc_fence_before();
@@ -510,6 +572,10 @@ tap_gemm2_kernel(const __grid_constant__ CUtensorMap tm_in0, const __grid_consta
 
   tc_fence_before();
   cluster_sync();  // no CTA may exit (or free TMEM) while its peer still reads its shared memory / signals its barriers
+  if (p.stats) {
+    float* row = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) row[i] = s_stats[i];
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem2_dealloc(tmem_base, Cfg::kTmemCols);
@@ -533,7 +599,7 @@ struct TapGemm2hCfg {
   static constexpr int kStageBytes = kAHaloBytes + 3 * kBBytes;
   static constexpr int kStages = (216 * 1024) / kStageBytes > 6 ? 6 : (216 * 1024) / kStageBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kStatsBytes;
   static_assert(kStageBytes % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
 };
 
@@ -550,6 +616,9 @@ tap_gemm2h_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
   uint64_t* tmem_full = bars + 2 * Cfg::kStages; // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]        (leader CTA only)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);  // [2][Cout] when p.stats
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) s_stats[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -688,6 +757,9 @@ tap_gemm2h_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
         uint32_t v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_ld_wait();
+        uint32_t ow[16];  // the chunk as stored (bf16 pairs); zeros for rows outside the tensor
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ow[e] = 0u;
         if (in_range) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
           const uint4* res = p.residual ? reinterpret_cast<const uint4*>(p.residual + off + c0) : nullptr;
@@ -713,7 +785,13 @@ tap_gemm2h_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
               o[e] = *reinterpret_cast<const uint32_t*>(&b);
             }
             dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ow[q * 4 + e] = o[e];
           }
+        }
+        if (p.stats) {
+          float* acc_c = s_stats + n_tile * BLOCK_N + c0;
+          stats_accumulate(ow, lane, acc_c, acc_c + p.Cout);
         }
       }
       tc_fence_before();
@@ -726,6 +804,10 @@ tap_gemm2h_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
 
   tc_fence_before();
   cluster_sync();
+  if (p.stats) {
+    float* row = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
+    for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) row[i] = s_stats[i];
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem2_dealloc(tmem_base, Cfg::kTmemCols);
@@ -790,8 +872,10 @@ struct Tap {
 };
 
 // Launch the tap GEMM: out view (strided) = sum over taps of W_t * in_view[tap.map] shifted.
+// stats / stats_parts: optional BatchNorm partial sums of the output ([CTAs][2][Cout] floats) and the number of CTA rows written.
 int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int num_taps, const __nv_bfloat16* wpack,
-                    int w_rows, int Cin, const View4& out, const __nv_bfloat16* residual, cudaStream_t stream) {
+                    int w_rows, int Cin, const View4& out, const __nv_bfloat16* residual, cudaStream_t stream,
+                    float* stats = nullptr, int* stats_parts = nullptr) {
   NBDT_REQUIRE(num_taps >= 1 && num_taps <= kMaxTaps, "bad tap count %d", num_taps);
   NBDT_REQUIRE(num_views >= 1 && num_views <= 4, "bad view count %d", num_views);
   NBDT_REQUIRE(Cin % 16 == 0, "input channels (%d) must be a multiple of 16 (pad the activation)", Cin);
@@ -819,6 +903,8 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
   p.out_sn = out.sn; p.out_sh = out.sh; p.out_sw = out.sw;
   p.out = const_cast<__nv_bfloat16*>(out.base);
   p.residual = residual;
+  p.stats = stats;
+  NBDT_REQUIRE(!stats || Cout <= kStatsMaxC, "fused BatchNorm statistics cover at most %d output channels (got %d)", kStatsMaxC, Cout);
   for (int t = 0; t < num_taps; ++t) {
     p.tap_map[t] = taps[t].map; p.tap_dh[t] = taps[t].dh; p.tap_dw[t] = taps[t].dw; p.tap_wrow[t] = taps[t].wrow;
   }
@@ -874,6 +960,7 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
       if (int rc = make_tmap(&tm_w2, wpack, 2, dims, strides, box)) return rc;
     }
     const int grid2 = std::min(total_pairs, info.sm_count / 2) * 2;
+    if (stats_parts) *stats_parts = grid2;
 #define NBDT_LAUNCH_TAP2H(BN)                                                                                   \
   {                                                                                                             \
     auto kern = tap_gemm2h_kernel<BN>;                                                                          \
@@ -896,6 +983,7 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
       if (int rc = make_tmap(&tm_w2, wpack, 2, dims, strides, box)) return rc;
     }
     const int grid2 = std::min(total_pairs, info.sm_count / 2) * 2;
+    if (stats_parts) *stats_parts = grid2;
 #define NBDT_LAUNCH_TAP2(BN)                                                                                    \
   {                                                                                                             \
     auto kern = tap_gemm2_kernel<BN>;                                                                           \
@@ -910,6 +998,7 @@ int launch_tap_gemm(const View4* in_views, int num_views, const Tap* taps, int n
     return NBDT_OK;
   }
   const int grid = std::min(total_tiles, info.sm_count);
+  if (stats_parts) *stats_parts = grid;
 #define NBDT_LAUNCH_TAP(BN)                                                                                     \
   {                                                                                                             \
     auto kern = tap_gemm_kernel<BN>;                                                                            \
@@ -1376,8 +1465,8 @@ extern "C" {
 
 // y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) (+ residual), ksize in {1,3} (pad = ksize/2), stride in {1,2}.
 // wpack: bf16 [ksize*ksize][Cout][Cin] (tap-major, K contiguous), from nbdt_conv_pack_weights.
-int nbdt_conv2d_fwd(const void* x, const void* wpack, void* y, const void* residual, int N, int H, int W, int Cin,
-                    int Cout, int ksize, int stride, void* stream) {
+static int conv2d_fwd_impl(const void* x, const void* wpack, void* y, const void* residual, int N, int H, int W, int Cin,
+                           int Cout, int ksize, int stride, float* stats, int* stats_parts, void* stream) {
   NBDT_REQUIRE(x && wpack && y, "NULL tensor");
   NBDT_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "unsupported conv %dx%d stride %d", ksize, ksize, stride);
   NBDT_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), "stride-2 conv needs even H, W");
@@ -1404,7 +1493,34 @@ int nbdt_conv2d_fwd(const void* x, const void* wpack, void* y, const void* resid
       }
   }
   return launch_tap_gemm(views, nv, taps, nt, reinterpret_cast<const __nv_bfloat16*>(wpack), ksize * ksize * Cout, Cin,
-                         out, reinterpret_cast<const __nv_bfloat16*>(residual), (cudaStream_t)stream);
+                         out, reinterpret_cast<const __nv_bfloat16*>(residual), (cudaStream_t)stream, stats, stats_parts);
+}
+
+int nbdt_conv2d_fwd(const void* x, const void* wpack, void* y, const void* residual, int N, int H, int W, int Cin,
+                    int Cout, int ksize, int stride, void* stream) {
+  return conv2d_fwd_impl(x, wpack, y, residual, N, H, W, Cin, Cout, ksize, stride, nullptr, nullptr, stream);
+}
+
+// The same convolution, and in its epilogue the BatchNorm batch statistics of y: every CTA writes one row of per-channel partial
+// sums, partials[cta][0][c] = sum of y[..., c], partials[cta][1][c] = sum of y[..., c]^2 over the pixels the CTA stored (the bf16
+// values).  `partials` holds nbdt_conv2d_stats_floats(Cout) floats; *parts receives the number of rows written (host int, known
+// at launch time).  nbdt_bn_finalize_partials (bn_ops.cu) turns them into the scale / shift of the BatchNorm that consumes y --
+// the separate statistics pass over y (nbdt_bn_stats) disappears.  Replaces the F.batch_norm statistics of the reference's
+// nn.BatchNorm2d modules that follow a convolution (nbdt/models/resnet.py:47-54,69-74 and the pytorchcv WRN units).
+int nbdt_conv2d_fwd_stats(const void* x, const void* wpack, void* y, const void* residual, int N, int H, int W, int Cin,
+                          int Cout, int ksize, int stride, float* partials, int* parts, void* stream) {
+  NBDT_REQUIRE(partials && parts, "NULL statistics buffer");
+  return conv2d_fwd_impl(x, wpack, y, residual, N, H, W, Cin, Cout, ksize, stride, partials, parts, stream);
+}
+
+// floats nbdt_conv2d_fwd_stats needs in `partials` for Cout output channels (0: too many channels for the fused statistics)
+long long nbdt_conv2d_stats_floats(int Cout) {
+  if (Cout > kStatsMaxC || Cout <= 0) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  nbdt::DeviceInfo info;
+  if (nbdt::device_info(dev, &info)) return 0;
+  return (long long)info.sm_count * 2 * Cout;
 }
 
 // dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w) (+ accumulate), the data gradient of nbdt_conv2d_fwd.

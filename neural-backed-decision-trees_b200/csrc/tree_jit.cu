@@ -48,7 +48,7 @@
 
 namespace {
 
-constexpr int kGeneratorVersion = 12;   // part of the cache key: bump when the emitted code changes
+constexpr int kGeneratorVersion = 13;   // part of the cache key: bump when the emitted code changes
 constexpr int kMaxLeaves = 1536;       // 32 rows x 132 B per leaf of shared memory per block: 1000 leaves (ImageNet) use 16 warps on 150 KB
 constexpr int kTPB = 32;               // one warp per CTA: rows are thread-private, only __syncwarp around the cooperative I/O sweeps
 // Shared-memory layout of a 32-row block: slot c (class c, later prefix / gradient) of row r lives at word
@@ -195,6 +195,7 @@ struct Plan {
   Team team;
   Knobs knobs;                     // with the automatic choices resolved
   bool default_knobs = true;       // nothing set in the environment: the variant name carries no knob suffix
+  bool wide = false;               // soft loss without scheduling fences at <= 8 resident warps (see make_plan)
 };
 
 struct Out {
@@ -464,7 +465,12 @@ struct Gen {
   std::string last;
   std::string base = "xsb";
   void note(const std::string& name) { last = name; ++since; }
-  bool fence_due() const { return plan.knobs.fence > 0 && since >= plan.knobs.fence && !last.empty(); }
+  // the no-fence / 8-warp setting was measured on the soft loss only (its two traversals carry the long dependency chains);
+  // the hard loss and the soft forward keep the fenced code at full occupancy (hard loss, 100 leaves: 58 % vs 51 %)
+  bool wide_mode() const { return plan.wide && v.mode == kSpecSoftLoss; }
+  int fence_every() const { return plan.wide && !wide_mode() ? 8 : plan.knobs.fence; }
+  int min_blocks() const { return wide_mode() ? std::min(plan.min_blocks, 8) : plan.min_blocks; }
+  bool fence_due() const { return fence_every() > 0 && since >= fence_every() && !last.empty(); }
   std::string fenced(const std::string& val) {
     if (!fence_due()) return val;
     since = 0;
@@ -1174,7 +1180,7 @@ struct Gen {
 
     // ---- kernel: one team per CTA, 32 rows per iteration ----
     o.f("#ifndef KA_HOST");
-    o.f("extern \"C\" __global__ void __launch_bounds__(KA_TPB, %d) nbdt_tree_ka(const KAParams p) {", plan.min_blocks);
+    o.f("extern \"C\" __global__ void __launch_bounds__(KA_TPB, %d) nbdt_tree_ka(const KAParams p) {", min_blocks());
     o.f("  extern __shared__ float ka_smem[];");
     o.f("  const int tid = threadIdx.x, lane = tid & 31;");
     o.f("  const u32 xsw = (u32)__cvta_generic_to_shared(ka_smem);");
@@ -1330,6 +1336,7 @@ Plan make_plan(const KTree& t, int max_smem, const Knobs& knobs) {
   // warps (100 leaves: 42.8 % vs 39.7 % of the HBM peak); teams want the occupancy and a window of 16 nodes (200 leaves: 24.5 %
   // vs 23.5 %); small hierarchies keep the round-1 setting.
   const bool wide = W == 1 && t.C > 64;
+  p.wide = wide && p.knobs.fence < 0 && knobs.minb == 0;
   if (p.knobs.fence < 0) p.knobs.fence = wide ? 0 : (W > 1 && t.C <= 256 ? 16 : 8);
   p.rows = auto_rows(t, knobs);
   const int R = p.rows;
@@ -1358,7 +1365,6 @@ Plan make_plan(const KTree& t, int max_smem, const Knobs& knobs) {
   int by_regs = 65536 / (kTPB * W * regs);
   int by_smem = (max_smem > 0 ? max_smem : 227 * 1024) / std::max(1, p.smem_bytes + 1024);
   p.min_blocks = std::max(1, std::min(32, std::min(by_regs, by_smem)));
-  if (wide && knobs.fence < 0) p.min_blocks = std::min(p.min_blocks, 8);
   if (knobs.minb > 0) p.min_blocks = knobs.minb;
   return p;
 }

@@ -9,6 +9,14 @@ from . import lib as L
 from .conv_ops import pad64
 from .nn_ops import AvgPoolFunction, BatchNormActFunction, ConvFunction, LinearFunction, StemFunction
 
+# BatchNorm statistics from the convolution epilogue (csrc/conv_gemm.cu: nbdt_conv2d_fwd_stats + nbdt_bn_finalize_partials) instead
+# of a separate pass over the convolution output: NBDT_B200_BN_FUSED_STATS=1.  Off by default -- measured on one B200 in the same
+# run (profiles/r02_conv_bn_stats_ab.md): the butterfly reduction in the epilogue costs the forward convolutions what the
+# statistics pass cost (WRN-28-10 step 19.05 vs 19.03 ms), it only moves the time into the tensor-core kernels.
+import os as _os
+
+_FUSED_BN_STATS = _os.environ.get("NBDT_B200_BN_FUSED_STATS", "0") == "1"
+
 BACKBONE_STATUS = "own kernels: tcgen05/TMA implicit-GEMM conv fwd/dgrad/wgrad, fused BN+ReLU(+residual), pool, stem"
 
 
@@ -33,20 +41,28 @@ def _check_conv(conv_mod):
     return s
 
 
-def conv(x, conv_mod, residual=None):
-    """NHWC bf16 (N,H,W,Cin) -> (N,H/s,W/s,Cout), optionally + residual (fused in the epilogue)."""
+def conv(x, conv_mod, residual=None, bn_stats=False):
+    """NHWC bf16 (N,H,W,Cin) -> (N,H/s,W/s,Cout), optionally + residual (fused in the epilogue).
+
+    bn_stats=True (the output goes into a BatchNorm, possibly in the next module): in training mode the epilogue also
+    accumulates the per-channel sum and sum of squares of the output; they travel with the returned tensor and bn_act() uses
+    them instead of reading the tensor once more for its batch statistics."""
     stride = _check_conv(conv_mod)
+    if bn_stats and conv_mod.training and _FUSED_BN_STATS:
+        y, partials = ConvFunction.apply(x, conv_mod.weight, stride, residual, True)
+        y._nbdt_bn_partials = partials if partials.numel() else None
+        return y
     return ConvFunction.apply(x, conv_mod.weight, stride, residual)
 
 
 def bn_act(x, bn, relu=True, residual=None, want_skip=False):
     """act(bn(x) (+ residual)).  want_skip=True returns (y, x_skip): use x_skip as the identity branch so that its
     gradient is added inside the BN-backward kernel."""
-    return BatchNormActFunction.apply(x, *_bn_args(bn), relu, residual, want_skip)
+    return BatchNormActFunction.apply(x, *_bn_args(bn), relu, residual, want_skip, getattr(x, "_nbdt_bn_partials", None))
 
 
 def conv_bn_act(x, conv_mod, bn, relu=True, residual=None):
-    return bn_act(conv(x, conv_mod), bn, relu=relu, residual=residual)
+    return bn_act(conv(x, conv_mod, bn_stats=True), bn, relu=relu, residual=residual)
 
 
 def stem(x, conv_mod, bn):

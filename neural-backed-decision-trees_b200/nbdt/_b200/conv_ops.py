@@ -2,6 +2,8 @@
 
 Activations are NHWC bf16 tensors of shape (N, H, W, C) with C a multiple of 64; weights stay fp32 OIHW
 (`nn.Conv2d.weight`) and are repacked to bf16 tap-major matrices per call."""
+import ctypes
+
 import torch
 
 from . import lib as L
@@ -53,8 +55,10 @@ def pack_weights(weight, cin_pad=None, cout_pad=None, want=(True, True)):
     return wp, wpt
 
 
-def conv_fwd(x, wp, ksize, stride, residual=None, real=None):
-    """real = (Cout, Cin) of the layer: the FLOP count bench.py reports is the algorithmic one, not that of the padded channels."""
+def conv_fwd(x, wp, ksize, stride, residual=None, real=None, bn_stats=False):
+    """real = (Cout, Cin) of the layer: the FLOP count bench.py reports is the algorithmic one, not that of the padded channels.
+    bn_stats: also accumulate the BatchNorm batch statistics of y in the epilogue; returns (y, partials) where partials is None
+    (too many channels for the fused path) or a fp32 tensor [parts][2][Cout] of per-CTA partial sums."""
     _check_act(x, "conv_fwd input")
     N, H, W, cin = x.shape
     taps, cout, cin_w = wp.shape
@@ -64,11 +68,23 @@ def conv_fwd(x, wp, ksize, stride, residual=None, real=None):
         _check_act(residual, "conv_fwd residual")
         assert residual.shape == y.shape
     flops = 2.0 * y.numel() * cin * ksize * ksize if real is None else 2.0 * N * (H // stride) * (W // stride) * real[0] * real[1] * ksize * ksize
-    with torch.cuda.device(x.device), _timed("fwd", flops):
-        L.check(L.load().nbdt_conv2d_fwd(_p(x), _p(wp), _p(y), _p(residual), N, H, W, cin, cout, ksize, stride,
-                                         L.stream_ptr(x.device)))
+    lib = L.load()
+    partials = None
+    with torch.cuda.device(x.device):
+        nfloats = lib.nbdt_conv2d_stats_floats(cout) if bn_stats else 0
+        buf = torch.empty((nfloats,), dtype=torch.float32, device=x.device) if nfloats > 0 else None
+        parts = ctypes.c_int(0)
+        with _timed("fwd", flops):
+            if nfloats > 0:
+                L.check(lib.nbdt_conv2d_fwd_stats(_p(x), _p(wp), _p(y), _p(residual), N, H, W, cin, cout, ksize, stride, _p(buf),
+                                                  ctypes.byref(parts), L.stream_ptr(x.device)))
+            else:
+                L.check(lib.nbdt_conv2d_fwd(_p(x), _p(wp), _p(y), _p(residual), N, H, W, cin, cout, ksize, stride,
+                                            L.stream_ptr(x.device)))
+        if nfloats > 0:
+            partials = buf[: parts.value * 2 * cout].view(parts.value, 2, cout)
     _count()
-    return y
+    return (y, partials) if bn_stats else y
 
 
 def conv_dgrad(dy, wpt, in_hw, ksize, stride, accumulate=None, real=None):

@@ -47,6 +47,8 @@ SIGNATURES = {
     "nbdt_soft_loss": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_ptr, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "nbdt_hard_loss": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_ptr, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "nbdt_conv2d_fwd": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 7 + [c_ptr]),
+    "nbdt_conv2d_fwd_stats": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 7 + [c_ptr, ctypes.POINTER(ctypes.c_int), c_ptr]),
+    "nbdt_conv2d_stats_floats": (ctypes.c_longlong, [ctypes.c_int]),
     "nbdt_conv2d_dgrad": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 7 + [c_ptr]),
     "nbdt_conv2d_wgrad": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 7 + [c_ptr]),
     "nbdt_conv_pack_weights": (ctypes.c_int, [c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 5 + [c_ptr]),
@@ -54,6 +56,7 @@ SIGNATURES = {
     "nbdt_conv_unpack_wgrad_batch": (ctypes.c_int, [c_ptr, ctypes.c_int, ctypes.c_int, c_ptr]),
     "nbdt_conv_unpack_wgrad": (ctypes.c_int, [c_ptr, c_ptr] + [ctypes.c_int] * 6 + [c_ptr]),
     "nbdt_bn_scratch_floats": (ctypes.c_longlong, [ctypes.c_int]),
+    "nbdt_bn_finalize_partials": (ctypes.c_int, [c_ptr, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "nbdt_bn_stats": (ctypes.c_int, [c_ptr, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nbdt_bn_eval_scale": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_ptr]),
     "nbdt_bn_apply": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, ctypes.c_longlong, ctypes.c_int, c_ptr, ctypes.c_int, c_ptr]),

@@ -99,7 +99,7 @@ class ConvFunction(torch.autograd.Function):
     instead of unpack + autograd's accumulate)."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, residual):
+    def forward(ctx, x, weight, stride, residual, bn_stats=False):
         cout, cin, k, _ = weight.shape
         cin_phys = x.shape[3]
         assert cin_phys >= cin
@@ -110,17 +110,27 @@ class ConvFunction(torch.autograd.Function):
             wp, wpt = bank.packed(weight, cin_phys, cout_phys)
         else:
             wp, wpt = C.pack_weights(weight, cin_pad=cin_phys, cout_pad=cout_phys)
-        y = C.conv_fwd(x, wp, k, stride, residual, real=(cout, cin))
+        partials = None
+        if bn_stats:  # second output: per-CTA partial sums of y for the BatchNorm that consumes it (not differentiable)
+            y, partials = C.conv_fwd(x, wp, k, stride, residual, real=(cout, cin), bn_stats=True)
+        else:
+            y = C.conv_fwd(x, wp, k, stride, residual, real=(cout, cin))
+        ctx.bn_stats = bn_stats
         ctx.save_for_backward(x, wpt)
         ctx.meta = (tuple(weight.shape), k, stride, residual is not None)
         ctx.direct_grad = weight.grad if getattr(weight, "_nbdt_direct_grad", False) else None
         ctx.param = weight if ctx.direct_grad is not None else None
         ctx.bank = bank if (bank is not None and ctx.direct_grad is not None and bank.defer_unpack) else None
         ctx.pads = (cin_phys, cout_phys)
+        if bn_stats:
+            if partials is None:
+                partials = torch.empty((0,), dtype=torch.float32, device=x.device)
+            ctx.mark_non_differentiable(partials)
+            return y, partials
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dpartials=None):
         x, wpt = ctx.saved_tensors
         wshape, k, stride, has_res = ctx.meta
         dy = dy.contiguous()
@@ -156,7 +166,7 @@ class ConvFunction(torch.autograd.Function):
             if ctx.param is not None:
                 for cb in GRAD_WRITTEN_CALLBACKS:
                     cb(ctx.param)
-        return dx, dw, None, (dy if has_res else None)
+        return dx, dw, None, (dy if has_res else None), None
 
 
 class BatchNormActFunction(torch.autograd.Function):
@@ -167,7 +177,8 @@ class BatchNormActFunction(torch.autograd.Function):
     autograd accumulation pass over the tensor."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual, want_skip=False):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps, relu, residual, want_skip=False,
+                partials=None):
         C._check_act(x, "batch norm input")
         N, H, W, Cp = x.shape
         M = N * H * W
@@ -178,10 +189,16 @@ class BatchNormActFunction(torch.autograd.Function):
         mean_invstd = torch.empty((2, Cp), dtype=torch.float32, device=dev)
         lib = L.load()
         with torch.cuda.device(dev):
-            if training:
+            rm = running_mean if running_mean is not None else None
+            rv = running_var if running_var is not None else None
+            if training and partials is not None and partials.numel() > 0:
+                # the producing convolution already summed x and x^2 per channel in its epilogue (csrc/conv_gemm.cu)
+                assert partials.shape[1:] == (2, Cp), (partials.shape, Cp)
+                L.check(lib.nbdt_bn_finalize_partials(_p(partials), partials.shape[0], M, Cp, c_real, _p(g), _p(b), _p(rm), _p(rv),
+                                                      float(momentum), float(eps), _p(mean_invstd), _p(scale_shift), _stream(x)))
+                _count()
+            elif training:
                 sums = torch.empty((lib.nbdt_bn_scratch_floats(Cp),), dtype=torch.float32, device=dev)
-                rm = running_mean if running_mean is not None else None
-                rv = running_var if running_var is not None else None
                 L.check(lib.nbdt_bn_stats(_p(x), M, Cp, c_real, _p(g), _p(b), _p(rm), _p(rv), float(momentum), float(eps),
                                           _p(sums), _p(mean_invstd), _p(scale_shift), _stream(x)))
                 _count(2)
@@ -214,7 +231,7 @@ class BatchNormActFunction(torch.autograd.Function):
         x, act, scale_shift, g, mean_invstd = ctx.saved_tensors
         M, Cp, c_real, relu, has_res = ctx.meta
         if dy is None:
-            return (dskip,) + (None,) * 10
+            return (dskip,) + (None,) * 11
         dy = dy.contiguous()
         extra = dskip.contiguous() if dskip is not None else None
         dx = torch.empty_like(x)
@@ -228,7 +245,7 @@ class BatchNormActFunction(torch.autograd.Function):
                 L.check(L.load().nbdt_bn_backward(_p(x), _p(act), _p(scale_shift), _p(dy), _p(extra), _p(dx), _p(dres), M,
                                                   Cp, c_real, _p(g), _p(mean_invstd), _p(dsums), _stream(x)))
         _count(3)
-        return dx, dsums[Cp:Cp + c_real], dsums[:c_real], None, None, None, None, None, None, dres, None
+        return dx, dsums[Cp:Cp + c_real], dsums[:c_real], None, None, None, None, None, None, dres, None, None
 
 
 class AvgPoolFunction(torch.autograd.Function):

@@ -62,9 +62,9 @@ class PreResUnit(nn.Module):
             identity = B.conv(a, self.identity_conv)
         else:  # the identity branch re-enters through the BN function so its gradient is fused into BN backward
             a, identity = B.bn_act(x, self.body.conv1.bn, relu=True, want_skip=True)
-        y = B.conv(a, self.body.conv1.conv)
+        y = B.conv(a, self.body.conv1.conv, bn_stats=True)   # -> body.conv2.bn
         y = B.bn_act(y, self.body.conv2.bn, relu=True)
-        return B.conv(y, self.body.conv2.conv, residual=identity)
+        return B.conv(y, self.body.conv2.conv, residual=identity, bn_stats=True)   # -> the next unit's (or the final) BatchNorm
 
 
 class PreResActivation(nn.Module):

@@ -130,3 +130,63 @@ def test_conv_fwd_dgrad_large(shape):
     test_conv_fwd(shape)
     test_conv_dgrad(shape)
     test_conv_wgrad(shape)
+
+
+def _check_fused_stats(shape, with_residual):
+    """y of the statistics variant is bit-identical to the plain forward; the per-CTA partial rows add up to the per-channel sum
+    and sum of squares of the stored bf16 values (what the BatchNorm statistics pass would have read)."""
+    from nbdt._b200 import conv_ops as C
+
+    N, H, W, cin, cout, k, stride = shape
+    x, w, dy = make(*shape, seed=5)
+    wp, _ = C.pack_weights(w, cin_pad=cin, cout_pad=cout)
+    res = dy if with_residual else None
+    y0 = C.conv_fwd(x, wp, k, stride, res)
+    y, partials = C.conv_fwd(x, wp, k, stride, res, bn_stats=True)
+    assert torch.equal(y, y0)
+    assert partials is not None and partials.dim() == 3 and partials.shape[1:] == (2, cout)
+    yd = y.double().reshape(-1, cout)
+    got = partials.double().sum(0)
+    want_s, want_q = yd.sum(0), (yd * yd).sum(0)
+    tol_s = 2e-5 * yd.abs().sum(0).max().item() + 1e-6
+    assert (got[0] - want_s).abs().max().item() <= tol_s, ((got[0] - want_s).abs().max().item(), tol_s)
+    assert (got[1] - want_q).abs().max().item() <= 2e-5 * want_q.max().item() + 1e-6
+
+
+@pytest.mark.parametrize("with_residual", [False, True])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_fwd_fused_bn_statistics(shape, with_residual):
+    _check_fused_stats(shape, with_residual)
+
+
+@pytest.mark.parametrize("shape", [(3, 32, 32, 160, 160, 3, 1), (5, 16, 16, 320, 640, 3, 1), (1, 32, 32, 64, 64, 3, 1), (3, 8, 8, 320, 640, 3, 2),
+                                   (160, 32, 32, 160, 160, 3, 1), (301, 8, 8, 128, 160, 3, 1)])
+def test_conv_fwd_fused_bn_statistics_pair_kernels(shape, force_pair_kernels):
+    """cta_group::2 kernels (with and without the H-halo tiles), odd tile counts, several tiles per CTA."""
+    _check_fused_stats(shape, True)
+
+
+def test_batchnorm_from_fused_statistics_equals_the_separate_pass():
+    """bn_act() on a convolution output that carries its partial sums gives the same result, coefficients and running
+    statistics as the statistics kernel reading the tensor (the sums are the same numbers added in a different order)."""
+    import torch.nn as nn
+    from nbdt._b200 import backbone as B
+
+    torch.manual_seed(0)
+    conv = nn.Conv2d(160, 320, 3, stride=2, padding=1, bias=False).to(DEV).train()
+    bns = [nn.BatchNorm2d(320).to(DEV).train() for _ in range(2)]
+    x = torch.randn((6, 16, 16, 160), device=DEV).bfloat16()
+    y_plain = B.conv(x, conv)
+    y_stats = B.conv(x, conv, bn_stats=True)
+    assert getattr(y_stats, "_nbdt_bn_partials", None) is not None and not hasattr(y_plain, "_nbdt_bn_partials")
+    a = B.bn_act(y_plain, bns[0], relu=True)
+    b = B.bn_act(y_stats, bns[1], relu=True)
+    close(b, a.float(), 1e-2)
+    assert (b.float() - a.float()).abs().max().item() <= 2 ** -6 * a.float().abs().max().item()
+    torch.testing.assert_close(bns[1].running_mean, bns[0].running_mean, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(bns[1].running_var, bns[0].running_var, rtol=1e-4, atol=1e-6)
+    # the gradient flows through both outputs of the convolution function
+    w0 = conv.weight.detach().clone().requires_grad_(True)
+    conv.weight = nn.Parameter(w0.detach().clone())
+    B.bn_act(B.conv(x, conv, bn_stats=True), bns[1], relu=True).float().square().sum().backward()
+    assert conv.weight.grad is not None and torch.isfinite(conv.weight.grad).all() and bns[1].weight.grad is not None
