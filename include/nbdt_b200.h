@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NBDT_B200_VERSION 103 /* 103: BatchNorm statistics from the convolution epilogue (nbdt_conv2d_fwd_stats, nbdt_bn_finalize_partials); 102: run-time specialised tree kernels (nbdt_tree_jit_*, nbdt_tree_kernel_variant); out-of-range targets are ignored rows */
+#define NBDT_B200_VERSION 104 /* 104: class-major tree entry points (nbdt_*_nchw); 103: BatchNorm statistics from the convolution epilogue (nbdt_conv2d_fwd_stats, nbdt_bn_finalize_partials); 102: run-time specialised tree kernels (nbdt_tree_jit_*, nbdt_tree_kernel_variant); out-of-range targets are ignored rows */
 
 enum { NBDT_OK = 0, NBDT_EINVAL = 1, NBDT_ECUDA = 2, NBDT_ETREE = 3, NBDT_ETOOLARGE = 4 };
 enum { NBDT_F32 = 0, NBDT_BF16 = 1, NBDT_F16 = 2 };
@@ -111,11 +111,24 @@ int nbdt_hard_loss(const nbdt_tree* tree, const void* logits, int dtype, const i
  * (nn.CrossEntropyLoss's ignore_index rows, reference loss.py:266 / model.py:127-143); the mean is still taken over
  * batch_rows, so pass the number of non-ignored rows there to reproduce CrossEntropyLoss's normalisation. */
 
+/* Class-major variants for the segmentation wrappers: logits, gradient and class probabilities are (N, C, H, W) contiguous,
+ * targets / predictions (N, H, W); row r of the hierarchy = pixel r % hw of image r / hw, hw = H*W.  They replace the
+ * coerce_tensor / uncoerce_tensor permute + reshape copies (reference nbdt/utils.py:338-347) around the rules in
+ * SegNBDT.forward (nbdt/model.py:376-399) and SoftSegTreeSupLoss.forward (nbdt/loss.py:318-327).  Run-time specialised kernels
+ * when hw % 32 == 0, the table-driven kernel otherwise; arguments as in the row-major calls. */
+int nbdt_soft_forward_nchw(const nbdt_tree* tree, const void* logits, int dtype, int64_t N, int64_t hw,
+                           float* class_probs, void* stream);
+int nbdt_hard_forward_nchw(const nbdt_tree* tree, const void* logits, int dtype, int64_t N, int64_t hw, int64_t* pred,
+                           void* stream);
+int nbdt_soft_loss_nchw(const nbdt_tree* tree, const void* logits, int dtype, const int64_t* targets, int64_t N,
+                        int64_t hw, int64_t batch_rows, float w_xent, float w_tree, float grad_scale, float* loss,
+                        void* grad_logits, void* stream);
+
 /* Hierarchy-specialised kernels (csrc/tree_jit.cu).  nbdt_soft_forward / nbdt_soft_loss / nbdt_hard_loss run, for any
  * hierarchy of up to 1536 leaves, a straight-line kernel generated from the nbdt_tree_desc and compiled with NVRTC on
  * first use (cached on disk next to the library; NBDT_B200_TREE_JIT=0 disables, =cache uses only cached kernels).  The
  * two calls below need no device: the generated CUDA source (tests compile it for the host and check it against the
- * oracle; mode 0 soft loss, 1 hard loss, 2 soft forward; vec = bytes per logits vector access), and ahead-of-time
+ * oracle; mode 0 soft loss, 1 hard loss, 2 soft forward; vec = bytes per logits vector access, 0 = the class-major variant), and ahead-of-time
  * compilation into the cache (the build does this for the shipped hierarchies). */
 long long nbdt_tree_jit_source(const nbdt_tree_desc* desc, int mode, int dtype, int vec, char* buf, long long cap);
 int nbdt_tree_jit_precompile(const nbdt_tree_desc* desc, int mode, int dtype);

@@ -82,6 +82,7 @@ struct Params {
   float w_tree;           // w_t  (hard: w_t * tsw * 2 / N)
   float inv_rows;         // 1 / batch_rows
   float grad_scale;
+  long long hw;           // > 0: class-major (N, C, H, W) logits / gradient / class probabilities, hw pixels per image (see elem_off)
 };
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
@@ -123,6 +124,17 @@ __device__ __forceinline__ void sweep_up(const TreeDev& t, float* __restrict__ v
   }
 }
 
+// Element (row, class c) of the logits (and of the gradient / class-probability outputs, which share the layout): row-major with
+// stride ld, or class-major (N, C, H, W) when hw > 0 -- the segmentation variants' tensors, addressed in place instead of through
+// the reference's permute + reshape copy (nbdt/utils.py:338-347, model.py:376-399, loss.py:318-327).
+__device__ __forceinline__ long long elem_off(long long row, int c, long long ld, long long hw, int C) {
+  if (hw > 0) {
+    const long long img = row / hw;
+    return (img * C + c) * hw + (row - img * hw);
+  }
+  return row * ld + c;
+}
+
 template <int G, int MODE, typename T>
 __global__ void __launch_bounds__(512) tree_kernel(const Params p) {
   extern __shared__ float smem[];
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(512) tree_kernel(const Params p) {
       const int rr = __umulhi((unsigned)e, t.magicC);
       const int c = e - rr * C;
       float val = 0.f;
-      if (rr < nrows) val = to_f<T>(x[(row0 + rr) * p.ld + c]);
+      if (rr < nrows) val = to_f<T>(x[elem_off(row0 + rr, c, p.ld, p.hw, C)]);
       V1[rr * NVp + c] = val;
     }
     __syncwarp();
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(512) tree_kernel(const Params p) {
       for (int e = lane; e < RPW * C; e += 32) {
         const int rr = __umulhi((unsigned)e, t.magicC);
         const int c = e - rr * C;
-        if (rr < nrows) p.class_probs[(row0 + rr) * C + c] = __expf(V2[rr * NVp + c]);
+        if (rr < nrows) p.class_probs[elem_off(row0 + rr, c, C, p.hw, C)] = __expf(V2[rr * NVp + c]);
       }
       __syncwarp();
       continue;
@@ -393,7 +405,7 @@ __global__ void __launch_bounds__(512) tree_kernel(const Params p) {
         const float l1 = __shfl_sync(0xffffffffu, lse1, rr * G);
         const int yy = __shfl_sync(0xffffffffu, y, rr * G);
         if (e < RPW * C && rr < nrows) {
-          const long long o = (row0 + rr) * p.ld + c;
+          const long long o = elem_off(row0 + rr, c, p.ld, p.hw, C);
           float gx = V1[rr * NVp + c];
           if (MODE != kSoftBwd) gx = yy < 0 ? 0.f : gx + kgx * (__expf(to_f<T>(x[o]) - l1) - (c == yy ? 1.f : 0.f));
           g[o] = from_f<T>(gx);
@@ -456,7 +468,7 @@ unsigned long long tree_hash(const nbdt_tree_desc* d) {
 // Launch the specialised kernel if one exists for this tree/mode/dtype and the rows are aligned for its
 // vector width.  Returns -1 when the generic kernel must be used.
 int try_launch_spec(const nbdt_tree* t, int spec_mode, int dtype, const Params& p, cudaStream_t stream) {
-  if (!t->spec || t->force_g || dtype < 0 || dtype > 2) return -1;
+  if (!t->spec || t->force_g || dtype < 0 || dtype > 2 || p.hw > 0) return -1;
   const int esz = dtype == NBDT_F32 ? 4 : 2;
   const int row_bytes = t->dev.C * esz;
   const int vec = row_bytes % 16 == 0 ? 16 : (row_bytes % 8 == 0 ? 8 : (row_bytes % 4 == 0 ? 4 : esz));
@@ -466,6 +478,7 @@ int try_launch_spec(const nbdt_tree* t, int spec_mode, int dtype, const Params& 
   SpecParams sp;
   sp.x = p.x; sp.B = p.B; sp.ld = p.ld; sp.targets = p.targets; sp.class_probs = p.class_probs; sp.loss = p.loss;
   sp.grad = p.grad; sp.w_xent = p.w_xent; sp.w_tree = p.w_tree; sp.inv_rows = p.inv_rows; sp.grad_scale = p.grad_scale;
+  sp.hw = 0;
   const void* fn = t->spec->fn[spec_mode][dtype];
   long long grid = (p.B + 127) / 128;
   grid = std::min<long long>(grid, (long long)t->sm_count * 12);
@@ -534,14 +547,16 @@ int launch(const nbdt_tree* t, int dtype, const Params& p, cudaStream_t stream) 
     SpecParams sp;
     sp.x = p.x; sp.B = p.B; sp.ld = p.ld; sp.targets = p.targets; sp.class_probs = p.class_probs; sp.loss = p.loss;
     sp.grad = p.grad; sp.w_xent = p.w_xent; sp.w_tree = p.w_tree; sp.inv_rows = p.inv_rows; sp.grad_scale = p.grad_scale;
+    sp.hw = p.hw;
     rc = tree_jit_launch(t->jit, MODE == kSoftLoss ? kSpecSoftLoss : (MODE == kHardLoss ? kSpecHardLoss : kSpecSoftFwd),
                          dtype, sp, stream);
     if (rc >= 0) which = 2;
   }
-  if (rc < 0 && t->v2 && !t->force_g && (MODE == kSoftLoss || MODE == kHardLoss || MODE == kSoftFwd)) {
+  if (rc < 0 && t->v2 && !t->force_g && p.hw == 0 && (MODE == kSoftLoss || MODE == kHardLoss || MODE == kSoftFwd)) {
     SpecParams sp;
     sp.x = p.x; sp.B = p.B; sp.ld = p.ld; sp.targets = p.targets; sp.class_probs = p.class_probs; sp.loss = p.loss;
     sp.grad = p.grad; sp.w_xent = p.w_xent; sp.w_tree = p.w_tree; sp.inv_rows = p.inv_rows; sp.grad_scale = p.grad_scale;
+    sp.hw = 0;
     rc = tree_v2_launch(t->v2, MODE == kSoftLoss ? kSpecSoftLoss : (MODE == kHardLoss ? kSpecHardLoss : kSpecSoftFwd),
                         dtype, sp, stream);
   }
@@ -835,6 +850,57 @@ int nbdt_hard_loss(const nbdt_tree* tree, const void* logits, int dtype, const i
   const float wt = w_tree * tsw * 2.0f / (float)tree->dev.N;
   return loss_common(kHardLoss, tree, logits, dtype, targets, B, ld, batch_rows, w_xent, wt, grad_scale, loss,
                      grad_logits, stream);
+}
+
+// ---- class-major (N, C, H, W) logits: the segmentation variants without the permute + reshape copy ----
+// Row r of the hierarchy kernels = pixel r % hw of image r / hw (hw = H*W); logits, gradient and class probabilities are all
+// (N, C, H, W) contiguous; targets and predictions are (N, H, W) = one entry per row.  Replace coerce_tensor / uncoerce_tensor
+// around the rules in SegNBDT.forward (nbdt/model.py:376-399) and SoftSegTreeSupLoss.forward (nbdt/loss.py:318-327).
+// Run-time specialised kernels when hw is a multiple of 32 (a block of 32 rows is 32 consecutive pixels of one image: every
+// class is one coalesced 128-byte line), the table-driven kernel otherwise.
+int nbdt_soft_forward_nchw(const nbdt_tree* tree, const void* logits, int dtype, int64_t N, int64_t hw, float* class_probs,
+                           void* stream) {
+  NBDT_REQUIRE(tree != nullptr && N >= 0 && hw > 0, "bad arguments");
+  if (int rc = check_common(tree, logits, N * hw, tree->dev.C)) return rc;
+  if (N == 0) return NBDT_OK;
+  NBDT_REQUIRE(class_probs != nullptr, "class_probs is NULL");
+  Params p = base_params(tree, logits, N * hw, tree->dev.C);
+  p.hw = hw;
+  p.class_probs = class_probs;
+  return launch<kSoftFwd>(tree, dtype, p, (cudaStream_t)stream);
+}
+
+int nbdt_hard_forward_nchw(const nbdt_tree* tree, const void* logits, int dtype, int64_t N, int64_t hw, int64_t* pred,
+                           void* stream) {
+  NBDT_REQUIRE(tree != nullptr && N >= 0 && hw > 0, "bad arguments");
+  if (int rc = check_common(tree, logits, N * hw, tree->dev.C)) return rc;
+  if (N == 0) return NBDT_OK;
+  NBDT_REQUIRE(pred != nullptr, "pred is NULL");
+  Params p = base_params(tree, logits, N * hw, tree->dev.C);
+  p.hw = hw;
+  p.pred = reinterpret_cast<long long*>(pred);
+  return launch<kHardFwd>(tree, dtype, p, (cudaStream_t)stream);
+}
+
+int nbdt_soft_loss_nchw(const nbdt_tree* tree, const void* logits, int dtype, const int64_t* targets, int64_t N, int64_t hw,
+                        int64_t batch_rows, float w_xent, float w_tree, float grad_scale, float* loss, void* grad_logits,
+                        void* stream) {
+  NBDT_REQUIRE(tree != nullptr && N >= 0 && hw > 0, "bad arguments");
+  if (int rc = check_common(tree, logits, N * hw, tree->dev.C)) return rc;
+  NBDT_REQUIRE(loss != nullptr, "loss is NULL");
+  NBDT_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+  if (N == 0) return NBDT_OK;
+  NBDT_REQUIRE(targets != nullptr, "targets is NULL");
+  Params p = base_params(tree, logits, N * hw, tree->dev.C);
+  p.hw = hw;
+  p.targets = reinterpret_cast<const long long*>(targets);
+  p.loss = loss;
+  p.grad = grad_logits;
+  p.w_xent = w_xent;
+  p.w_tree = w_tree;
+  p.inv_rows = 1.0f / (float)(batch_rows > 0 ? batch_rows : N * hw);
+  p.grad_scale = grad_scale;
+  return launch<kSoftLoss>(tree, dtype, p, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -48,7 +48,7 @@
 
 namespace {
 
-constexpr int kGeneratorVersion = 13;   // part of the cache key: bump when the emitted code changes
+constexpr int kGeneratorVersion = 14;   // part of the cache key: bump when the emitted code changes
 constexpr int kMaxLeaves = 1536;       // 32 rows x 132 B per leaf of shared memory per block: 1000 leaves (ImageNet) use 16 warps on 150 KB
 constexpr int kTPB = 32;               // one warp per CTA: rows are thread-private, only __syncwarp around the cooperative I/O sweeps
 // Shared-memory layout of a 32-row block: slot c (class c, later prefix / gradient) of row r lives at word
@@ -162,7 +162,10 @@ struct Variant {
   int dtype;   // NBDT_F32 / BF16 / F16
   int vec;     // bytes per logits/gradient vector access (16, 8, 4, 2)
   int ovec;    // bytes per class_probs vector store (soft forward)
-  int key() const { return ((mode * 4 + dtype) * 32 + vec) * 32 + ovec; }
+  int layout = 0;  // 0: rows with stride ld.  1: class-major (N, C, H, W) logits / outputs, H*W a multiple of 32: the 32 rows of
+                   // a block are 32 consecutive pixels of one image, every class is one coalesced line, and a thread fills its own
+                   // slots (no cooperative transposition; the shared-memory layout needs no skew)
+  int key() const { return (((mode * 4 + dtype) * 32 + vec) * 32 + ovec) * 2 + layout; }
 };
 
 // A team of W warps shares one block of 32 rows: the hierarchy is cut into disjoint subtrees ("cut subtrees", at most about
@@ -233,6 +236,7 @@ const char* kPrelude = R"SRC(
 struct KAParams {
   const void* x; long long B, ld; const long long* targets; float* class_probs; float* loss; void* grad;
   float w_xent, w_tree, inv_rows, grad_scale;
+  long long hw;  // class-major variants: pixels per image
 };
 #ifndef KA_HOST
 #define KA_DEV __device__ __forceinline__
@@ -368,6 +372,7 @@ KA_DEV KB ka_owned(const unsigned char* tab, KI y, int w) { return mkb(tab[y.a] 
 #define KA_LDX(dst, base, slot, off) const KF dst = (base)[slot]
 #define KA_STX(base, slot, off, val) (base)[slot] = (val)
 #define KA_LDX_DYN(dst, idx) const KF dst = xsb[idx]
+#define KA_STX_DYN(idx, val) xsb[idx] = (val)
 #define KA_ADDX_DYN(cond, idx, val) if (cond) xsb[idx] += (val)
 #define KA_ZERO_IF(cond, idx) if (cond) xsb[idx] = 0.f
 #else
@@ -390,6 +395,7 @@ KA_DEV KB ka_owned(const unsigned char* tab, KI y, int w) { return mkb(tab[y.a] 
 #define KA_STX(base, slot, off, val) asm volatile("st.shared.f32 [%0+" #off "], %1;" :: "r"(base), "f"((KF)(val)))
 #define KA_OPAQUE(x) asm volatile("" : "+f"(x))
 #define KA_LDX_DYN(dst, idx) KF dst; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dst) : "r"(xsb + KA_DYN_OFF(idx)))
+#define KA_STX_DYN(idx, val) asm volatile("st.shared.f32 [%0], %1;" :: "r"(xsb + KA_DYN_OFF(idx)), "f"((KF)(val)))
 #define KA_ADDX_DYN(cond, idx, val) if (cond) { float dv_; const u32 da_ = xsb + KA_DYN_OFF(idx); asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dv_) : "r"(da_)); dv_ += (val); asm volatile("st.shared.f32 [%0], %1;" :: "r"(da_), "f"(dv_)); }
 #define KA_ZERO_IF(cond, idx) if (cond) asm volatile("st.shared.f32 [%0], %1;" :: "r"(xsb + KA_DYN_OFF(idx)), "f"(0.f))
 #else
@@ -1048,12 +1054,51 @@ struct Gen {
     o.f("}");
   }
 
+  // Class-major tensors (layout 1): lane = pixel.  Class c of the block's 32 pixels is 32 consecutive elements, so one warp-wide
+  // load / store per class is one coalesced line, and every thread fills (reads) its own slot c.  The warps of a team share the
+  // classes round-robin.  A block never straddles two images (hw % 32 == 0).
+  void emit_sweeps_class_major() {
+    const int W = team.W;
+    const char* ldf = v.dtype == NBDT_F32 ? "u2f(ld4(src))" : (v.dtype == NBDT_BF16 ? "u2f(ld2(src) << 16)" : "h2f(ld2(src))");
+    o.f("KA_DEV void ka_sweep_a(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int tid) {");
+    o.f("#ifdef KA_HOST\n    const int lane = 0, c_first = 0, c_step = 1;\n    const KA_XSB xsb = xsw;");
+    o.f("#else\n    const int lane = tid & 31, c_first = tid >> 5, c_step = %d;\n    const KA_XSB xsb = xsw + lane * 4u;\n#endif", W);
+    o.f("    const long long img = row0 / p.hw, pix = row0 - img * p.hw + lane;");
+    o.f("    const char* xb = reinterpret_cast<const char*>(p.x) + (img * KA_C * p.hw + pix) * %d;", esz());
+    o.f("    if (lane < nrows) {");
+    o.f("#pragma unroll 8");
+    o.f("      for (int c = c_first; c < KA_C; c += c_step) {");
+    o.f("        const char* src = xb + (long long)c * p.hw * %d;", esz());
+    o.f("        KA_STX_DYN(c, %s);", ldf);
+    o.f("      }");
+    o.f("    }");
+    o.f("}");
+    const bool fwd = v.mode == kSpecSoftFwd;
+    const int oesz = fwd ? 4 : esz();
+    o.f("KA_DEV void ka_sweep_b(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int tid) {");
+    o.f("#ifdef KA_HOST\n    const int lane = 0, c_first = 0, c_step = 1;\n    const KA_XSB xsb = xsw;");
+    o.f("#else\n    const int lane = tid & 31, c_first = tid >> 5, c_step = %d;\n    const KA_XSB xsb = xsw + lane * 4u;\n#endif", W);
+    o.f("    const long long img = row0 / p.hw, pix = row0 - img * p.hw + lane;");
+    o.f("    char* ob = reinterpret_cast<char*>(%s) + (img * KA_C * p.hw + pix) * %d;", fwd ? "p.class_probs" : "p.grad", oesz);
+    o.f("    if (lane < nrows) {");
+    o.f("#pragma unroll 8");
+    o.f("      for (int c = c_first; c < KA_C; c += c_step) {");
+    o.f("        KA_LDX_DYN(q, c);");
+    o.f("        char* dst = ob + (long long)c * p.hw * %d;", oesz);
+    if (fwd || v.dtype == NBDT_F32) o.f("        st4(dst, f2u(q));");
+    else o.f("        st2(dst, %s(q, 0.f));", v.dtype == NBDT_BF16 ? "pack_bf16" : "pack_f16");
+    o.f("      }");
+    o.f("    }");
+    o.f("}");
+  }
+
   std::string run() {
     const int C = t.C, W = team.W;
     const int pv = per_vec();
     o.s.reserve((size_t)C * 2600);
     U = v.mode == kSpecSoftFwd ? std::min(pv, v.ovec / 4) : pv;
     K = ((C / U) & 31) | 1;
+    if (v.layout == 1) { U = 1 << 20; K = 1; }  // thread-private slots only: plain [class][lane]
     const int RB = 32 * R();  // rows per block
     o.f("#define KA_C %d\n#define KA_W %d\n#define KA_R %d", C, W, R());
     o.f("#ifdef KA_HOST\n#define KA_TPB 1\n#else\n#define KA_TPB %d\n#endif\n#define KA_U %du\n#define KA_K %du", kTPB * W, U, K);
@@ -1075,6 +1120,8 @@ struct Gen {
     o.f("// hierarchy %016llx: %d leaves, %d inner nodes; mode %d dtype %d vec %d; %d node values; %d warps per row block, %d cut subtrees, %d top nodes",
         t.hash, C, t.N, v.mode, v.dtype, v.vec, plan.nvalues, W, team.ncut(), team.ntop);
 
+    if (v.layout == 1) emit_sweeps_class_major();
+    else {
     // ---- sweep A: the block's rows, coalesced, into the transposed slots ----
     o.f("KA_DEV void ka_sweep_a(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int tid) {");
     o.f("    const char* xb = reinterpret_cast<const char*>(p.x) + row0 * p.ld * %d;", esz());
@@ -1119,6 +1166,7 @@ struct Gen {
     coop_step(pv);
     o.f("    }");
     o.f("}");
+    }
 
     // ---- the row code, one function per warp of the team ----
     for (int w = 0; w < W; ++w) emit_part(w);
@@ -1131,6 +1179,7 @@ struct Gen {
     o.f("#endif");
 
     // ---- sweep B: coalesced write of the block's gradient rows / class probabilities (the slots hold the final values) ----
+    if (v.layout == 0) {
     o.f("KA_DEV void ka_sweep_b(const KAParams& p, long long row0, int nrows, KA_XSB xsw, int tid) {");
     {
       const bool fwd = v.mode == kSpecSoftFwd;
@@ -1177,6 +1226,7 @@ struct Gen {
       o.f("    }");
     }
     o.f("}");
+    }
 
     // ---- kernel: one team per CTA, 32 rows per iteration ----
     o.f("#ifndef KA_HOST");
@@ -1489,7 +1539,7 @@ std::vector<std::string> cache_read_dirs() {
 
 std::string variant_name(const KTree& t, const Variant& v, const Knobs& k, bool dflt) {
   char b[192];
-  int n = snprintf(b, sizeof b, "ka%d_%016llx_m%d_t%d_v%d_o%d", kGeneratorVersion, t.hash, v.mode, v.dtype, v.vec, v.ovec);
+  int n = snprintf(b, sizeof b, "ka%d_%016llx_m%d_t%d_v%d_o%d%s", kGeneratorVersion, t.hash, v.mode, v.dtype, v.vec, v.ovec, v.layout ? "_nchw" : "");
   if (!dflt) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d_w%d_e%d_x%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence, k.warps, k.expm, k.rows);
   return b;
 }
@@ -1614,6 +1664,10 @@ int tree_jit_launch(TreeJit* t, int mode, int dtype, const SpecParams& p, void* 
   if (mode == kSpecSoftFwd)
     v.ovec = max_pow2_dividing(((unsigned long long)C * 4) | (unsigned long long)reinterpret_cast<uintptr_t>(p.class_probs) | 16ull, 16);
   if (v.ovec < 4) return -1;
+  if (p.hw > 0) {  // class-major tensors: 32 consecutive pixels of one image per block, element-wise accesses
+    if (p.hw % 32 != 0 || t->plan.rows != 1) return -1;
+    v.layout = 1; v.vec = esz; v.ovec = 4;
+  }
 
   TreeJit::Loaded* L;
   {
@@ -1672,6 +1726,10 @@ long long nbdt_tree_jit_source(const nbdt_tree_desc* desc, int mode, int dtype, 
   Variant v;
   v.mode = mode; v.dtype = dtype; v.vec = vec;
   v.ovec = mode == kSpecSoftFwd ? max_pow2_dividing(((unsigned long long)t.C * 4) | 16ull, 16) : 4;
+  if (vec == 0) {  // vec == 0 asks for the class-major (N, C, H, W) variant
+    if (plan.rows != 1) return -1;
+    v.layout = 1; v.vec = dtype == NBDT_F32 ? 4 : 2; v.ovec = 4;
+  }
   Gen g(t, v, plan);
   const std::string s = g.run();
   if (buf && cap > 0) {

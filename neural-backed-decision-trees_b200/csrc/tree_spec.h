@@ -11,6 +11,9 @@ struct SpecParams {
   float* loss;         // loss modes (pre-zeroed device scalar)
   void* grad;          // loss modes; may be NULL
   float w_xent, w_tree, inv_rows, grad_scale;
+  long long hw;        // 0: rows are contiguous (stride ld).  > 0: class-major (N, C, H, W) logits with hw = H*W pixels per image:
+                       // row r = (image r / hw, pixel r % hw), class c at image * C * hw + c * hw + pixel (segmentation variants).
+                       // Only the run-time specialised kernels read it.
 };
 
 struct SpecEntry {

@@ -44,6 +44,9 @@ SIGNATURES = {
     "nbdt_soft_backward": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_i64, c_i64, c_ptr, c_f32, c_ptr, c_ptr]),
     "nbdt_hard_forward": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nbdt_node_outputs": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "nbdt_soft_forward_nchw": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_i64, c_i64, c_ptr, c_ptr]),
+    "nbdt_hard_forward_nchw": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_i64, c_i64, c_ptr, c_ptr]),
+    "nbdt_soft_loss_nchw": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_ptr, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "nbdt_soft_loss": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_ptr, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "nbdt_hard_loss": (ctypes.c_int, [c_ptr, c_ptr, ctypes.c_int, c_ptr, c_i64, c_i64, c_i64, c_f32, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "nbdt_conv2d_fwd": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr] + [ctypes.c_int] * 7 + [c_ptr]),

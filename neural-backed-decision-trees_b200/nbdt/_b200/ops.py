@@ -238,6 +238,84 @@ def node_outputs_autograd(tree, logits):
     return node_outputs(tree, logits)
 
 
+# ---- class-major (N, C, H, W) tensors: the segmentation wrappers without coerce_tensor / uncoerce_tensor copies ----
+def _nchw(logits, what):
+    L.require_cuda(logits, what)
+    if logits.dim() != 4:
+        raise ValueError(f"{what}: expected (N, C, H, W) logits, got shape {tuple(logits.shape)}")
+    return logits if logits.is_contiguous() else logits.contiguous()
+
+
+def soft_forward_nchw(tree, logits):
+    """Class probabilities (N, C, H, W) fp32 of the soft rules, one row of the hierarchy per pixel (reference model.py:376-399)."""
+    logits = _nchw(logits, "soft rules (segmentation)")
+    dt = tree.device_tree(logits.device)
+    N, C, H, W = logits.shape
+    if C != dt.num_classes:
+        raise ValueError(f"logits have {C} classes, the hierarchy has {dt.num_classes}")
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        L.check(L.load().nbdt_soft_forward_nchw(dt.handle, _p(logits), L.dtype_code(logits.dtype), N, H * W, _p(out),
+                                                L.stream_ptr(logits.device)))
+    _count()
+    return out
+
+
+def hard_forward_nchw(tree, logits):
+    """Predicted class per pixel (N, H, W) int64 of the hard rules."""
+    logits = _nchw(logits, "hard rules (segmentation)")
+    dt = tree.device_tree(logits.device)
+    N, C, H, W = logits.shape
+    if C != dt.num_classes:
+        raise ValueError(f"logits have {C} classes, the hierarchy has {dt.num_classes}")
+    pred = torch.empty((N, H, W), dtype=torch.int64, device=logits.device)
+    with torch.cuda.device(logits.device):
+        L.check(L.load().nbdt_hard_forward_nchw(dt.handle, _p(logits), L.dtype_code(logits.dtype), N, H * W, _p(pred),
+                                                L.stream_ptr(logits.device)))
+    _count()
+    return pred
+
+
+def tree_loss_nchw(tree, logits, targets, w_xent, w_tree, batch_rows=0, want_grad=True):
+    """Fused soft tree-supervision loss over the pixels of (N, C, H, W) logits with (N, H, W) targets: (loss, gradient in the
+    logits' layout and dtype or None).  Reference: SoftSegTreeSupLoss.forward, nbdt/loss.py:318-327."""
+    logits = _nchw(logits, "tree-supervision loss (segmentation)")
+    L.require_cuda(targets, "tree-supervision loss targets")
+    dt = tree.device_tree(logits.device)
+    N, C, H, W = logits.shape
+    if C != dt.num_classes:
+        raise ValueError(f"logits have {C} classes, the hierarchy has {dt.num_classes}")
+    if tuple(targets.shape) != (N, H, W):
+        raise ValueError(f"targets must have shape {(N, H, W)}, got {tuple(targets.shape)}")
+    dev = logits.device
+    targets = targets.to(device=dev, dtype=torch.int64).contiguous()
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    grad = torch.empty_like(logits) if want_grad else None
+    with torch.cuda.device(dev):
+        L.check(L.load().nbdt_soft_loss_nchw(dt.handle, _p(logits), L.dtype_code(logits.dtype), _p(targets), N, H * W,
+                                             int(batch_rows), float(w_xent), float(w_tree), 1.0, _p(loss), _p(grad),
+                                             L.stream_ptr(dev)))
+    _count(2)
+    return loss, grad
+
+
+class FusedSegTreeLossFunction(torch.autograd.Function):
+    """w_xent * CE(logits) + w_tree * CE(class probabilities of the soft rules) per pixel, loss and gradient from one launch."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, tree, w_xent, w_tree, batch_rows):
+        loss, grad = tree_loss_nchw(tree, logits, targets, w_xent, w_tree, batch_rows, logits.requires_grad)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        if grad is None:
+            return (None,) * 6
+        return grad * grad_out.to(grad.dtype), None, None, None, None, None
+
+
 class FusedTreeLossFunction(torch.autograd.Function):
     """loss and dloss/dlogits from ONE kernel launch; backward only rescales the saved gradient."""
 

@@ -249,6 +249,11 @@ class SoftSegTreeSupLoss(SoftTreeSupLoss):
 
     def forward(self, outputs, targets):
         self.assert_output_not_nbdt(outputs)
+        if _is_plain_cross_entropy(self.criterion) and outputs.dim() == 4 and outputs.is_cuda:
+            # criterion(outputs) + tsw * criterion(bayesian) is the fused soft loss with one row per pixel, on the (N, C, H, W)
+            # tensor in place (no coerce / uncoerce copies, no materialised class probabilities)
+            return ops.FusedSegTreeLossFunction.apply(outputs, targets, self.tree, 1.0, float(self.tree_supervision_weight),
+                                                      self.batch_rows)
         loss = self.criterion(outputs, targets)
         bayesian = uncoerce_tensor(self.rules(coerce_tensor(outputs)), outputs.shape)
         return loss + self.criterion(bayesian, targets) * self.tree_supervision_weight

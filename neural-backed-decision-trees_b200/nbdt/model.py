@@ -285,6 +285,13 @@ class SegNBDT(NBDT):
         assert len(x.shape) == 4, "Input must be of shape (N,C,H,W) for segmentation"
         x = self.model(x)
         shape = x.shape
+        if x.is_cuda and not (x.requires_grad and torch.is_grad_enabled()):
+            # the (N, C, H, W) logits are addressed in place: no permute + reshape copies around the rules
+            if isinstance(self.rules, SoftEmbeddedDecisionRules):
+                return _flag(ops.soft_forward_nchw(self.rules.tree, x))
+            if isinstance(self.rules, HardEmbeddedDecisionRules):
+                pred = ops.hard_forward_nchw(self.rules.tree, x)
+                return _flag(torch.nn.functional.one_hot(pred, shape[1]).permute(0, 3, 1, 2).to(torch.float32))
         return uncoerce_tensor(self.rules.forward(coerce_tensor(x)), shape)
 
 

@@ -102,7 +102,7 @@ class KAParams(ctypes.Structure):
     _fields_ = [("x", ctypes.c_void_p), ("B", ctypes.c_longlong), ("ld", ctypes.c_longlong), ("targets", ctypes.c_void_p),
                 ("class_probs", ctypes.c_void_p), ("loss", ctypes.c_void_p), ("grad", ctypes.c_void_p),
                 ("w_xent", ctypes.c_float), ("w_tree", ctypes.c_float), ("inv_rows", ctypes.c_float),
-                ("grad_scale", ctypes.c_float)]
+                ("grad_scale", ctypes.c_float), ("hw", ctypes.c_longlong)]
 
 
 def tree_desc(tree):
@@ -178,24 +178,34 @@ def from_dtype_bytes(raw, dtype):
     return (raw.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
 
 
-def run_loss(tree, mode, dtype, vec, x, y, w_xent, w_tree, want_grad=True, batch_rows=None, grad_scale=1.0):
+def run_loss(tree, mode, dtype, vec, x, y, w_xent, w_tree, want_grad=True, batch_rows=None, grad_scale=1.0, hw=0):
+    """hw > 0 (with vec = 0): x is given as rows (B, C) and handed to the class-major variant as (B / hw, C, hw)."""
     lib = host_kernel(tree, mode, dtype, vec)
-    raw, _ = to_dtype_bytes(x, dtype)
     B, C = x.shape
+    if hw:
+        x = np.ascontiguousarray(x.reshape(B // hw, hw, C).transpose(0, 2, 1))
+    raw, _ = to_dtype_bytes(x, dtype)
     y = np.ascontiguousarray(y, dtype=np.int64)
     grad = np.zeros_like(raw)
     p = KAParams(raw.ctypes.data, B, C, y.ctypes.data, None, None, grad.ctypes.data if want_grad else None,
-                 w_xent, w_tree, 1.0 / (batch_rows or B), grad_scale)
+                 w_xent, w_tree, 1.0 / (batch_rows or B), grad_scale, hw)
     loss = ctypes.c_float()
     lib.ka_run(ctypes.byref(p), ctypes.byref(loss))
-    return loss.value, (from_dtype_bytes(grad, dtype) if want_grad else None)
+    g = from_dtype_bytes(grad, dtype) if want_grad else None
+    if hw and g is not None:
+        g = np.ascontiguousarray(g.reshape(B // hw, C, hw).transpose(0, 2, 1)).reshape(B, C)
+    return loss.value, g
 
 
-def run_soft_forward(tree, dtype, vec, x):
+def run_soft_forward(tree, dtype, vec, x, hw=0):
     lib = host_kernel(tree, 2, dtype, vec)
-    raw, _ = to_dtype_bytes(x, dtype)
     B, C = x.shape
-    out = np.zeros((B, C), dtype=np.float32)
-    p = KAParams(raw.ctypes.data, B, C, None, out.ctypes.data, None, None, 0, 0, 1, 1)
+    if hw:
+        x = np.ascontiguousarray(x.reshape(B // hw, hw, C).transpose(0, 2, 1))
+    raw, _ = to_dtype_bytes(x, dtype)
+    out = np.zeros(x.shape, dtype=np.float32)
+    p = KAParams(raw.ctypes.data, B, C, None, out.ctypes.data, None, None, 0, 0, 1, 1, hw)
     lib.ka_run(ctypes.byref(p), None)
+    if hw:
+        out = np.ascontiguousarray(out.reshape(B // hw, C, hw).transpose(0, 2, 1)).reshape(B, C)
     return out

@@ -131,3 +131,43 @@ def test_segmentation_variants_match_the_reference_golden():
         assert abs(loss.item() - float(g[f"seg_loss_tsw{tsw}"])) <= 2e-5 * abs(float(g[f"seg_loss_tsw{tsw}"]))
         want = g[f"seg_grad_tsw{tsw}"]
         np.testing.assert_allclose(xx.grad.cpu().numpy(), want, rtol=2e-4, atol=2e-6 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("shape", [(2, 19, 8, 8), (3, 19, 5, 7), (1, 19, 32, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_class_major_kernels_equal_the_permuted_row_kernels(shape, dtype):
+    """The segmentation wrappers address (N, C, H, W) tensors in place (nbdt_*_nchw): same numbers as the reference's route --
+    permute + reshape to rows, rules / loss on the rows, reshape + permute back -- through the row-major kernels; the run-time
+    specialised class-major kernel is the one that runs when H*W is a multiple of 32, the table-driven one otherwise."""
+    from nbdt._b200 import lib as L
+    from nbdt._b200 import ops
+    from nbdt.tree import Tree
+    from nbdt.utils import coerce_tensor, uncoerce_tensor
+
+    pkg = os.path.join(ROOT, "neural-backed-decision-trees_b200", "nbdt")
+    pg = os.path.join(pkg, "hierarchies", "Cityscapes", "graph-induced-HRNet-w18-v1.json")
+    pw = os.path.join(GOLDEN, "wnids_cityscapes.txt")
+    tree = Tree("Cityscapes", path_graph=pg, path_wnids=pw, classes=[f"c{i}" for i in range(19)])
+    N, C, H, W = shape
+    torch.manual_seed(N * H + W)
+    x = (2 * torch.randn(shape, device=DEV)).to(dtype)
+    y = torch.randint(C, (N, H, W), device=DEV)
+    rows = coerce_tensor(x).contiguous()
+    lp = dtype != torch.float32
+
+    soft = ops.soft_forward_nchw(tree, x)
+    want = uncoerce_tensor(ops.soft_forward(tree, rows), x.shape)
+    torch.testing.assert_close(soft, want, rtol=2e-5, atol=1e-7)
+    name = L.load().nbdt_tree_kernel_variant(tree.device_tree(torch.device(DEV)).handle).decode()
+    assert ("_nchw" in name) == ((H * W) % 32 == 0), name
+
+    pred = ops.hard_forward_nchw(tree, x)
+    want_pred, _ = ops.hard_forward(tree, rows)
+    assert torch.equal(pred.reshape(-1), want_pred)
+
+    for w_tree in (1.0, 0.5):
+        loss, grad = ops.tree_loss_nchw(tree, x, y, 1.0, w_tree)
+        want_l, want_g = ops.tree_loss(tree, rows, y.reshape(-1), "soft", 1.0, w_tree)
+        assert abs(loss.item() - want_l.item()) <= 2e-5 * abs(want_l.item())
+        want_g = uncoerce_tensor(want_g, x.shape).float()
+        torch.testing.assert_close(grad.float(), want_g, rtol=1e-2 if lp else 2e-4, atol=(8e-3 if lp else 2e-6) * want_g.abs().max().item())

@@ -24,7 +24,8 @@ def vec_for(C, dtype):
     raise AssertionError
 
 
-def check(tree, ot, C, dtype=0, rows=24, seed=0, warps=None):
+def check(tree, ot, C, dtype=0, rows=24, seed=0, warps=None, hw=0):
+    """hw > 0: the class-major variant (vec = 0), the rows being hw pixels of rows / hw images."""
     env = os.environ.pop("NBDT_B200_KA_WARPS", None)
     if warps:
         os.environ["NBDT_B200_KA_WARPS"] = str(warps)
@@ -32,22 +33,22 @@ def check(tree, ot, C, dtype=0, rows=24, seed=0, warps=None):
         rng = np.random.default_rng(seed)
         x = (3 * rng.standard_normal((rows, C))).astype(np.float32)
         y = rng.integers(0, C, rows)
-        vec = vec_for(C, dtype)
+        vec = 0 if hw else vec_for(C, dtype)
         _, xr = J.to_dtype_bytes(x, dtype)
         xd = xr.astype(np.float64)
         lp = dtype != 0
-        cp = J.run_soft_forward(tree, dtype, vec, x)
+        cp = J.run_soft_forward(tree, dtype, vec, x, hw=hw)
         np.testing.assert_allclose(cp, O.soft_probs(ot, xd), rtol=5e-6, atol=1e-12)
         n_in = len(ot.inodes)
         for mode, fn, wt in ((SOFT, O.soft_tree_sup_loss, 1.3), (HARD, O.hard_tree_sup_loss, 1.3 * 2.0 * 2.0 / n_in)):
             kw = {"tree_supervision_weight": 2.0} if mode == HARD else {}
             want_l, want_g = fn(ot, xd, y, xent_weight=0.7, tree_weight=1.3, **kw)
-            loss, grad = J.run_loss(tree, mode, dtype, vec, x, y, 0.7, wt)
+            loss, grad = J.run_loss(tree, mode, dtype, vec, x, y, 0.7, wt, hw=hw)
             assert abs(loss - want_l) <= 2e-6 * abs(want_l)
             scale = np.abs(want_g).max()
             np.testing.assert_allclose(grad, want_g, rtol=1e-2 if lp else 2e-5, atol=(5e-3 if lp else 1e-6) * scale)
             # forward only
-            loss2, _ = J.run_loss(tree, mode, dtype, vec, x, y, 0.7, wt, want_grad=False)
+            loss2, _ = J.run_loss(tree, mode, dtype, vec, x, y, 0.7, wt, want_grad=False, hw=hw)
             assert abs(loss2 - want_l) <= 2e-6 * abs(want_l)
     finally:
         os.environ.pop("NBDT_B200_KA_WARPS", None)
@@ -73,6 +74,14 @@ def shipped(dataset, hierarchy):
 def test_generated_code_matches_oracle_on_shipped_hierarchies(dataset, hierarchy, dtype, warps):
     tree, ot, C = shipped(dataset, hierarchy)
     check(tree, ot, C, dtype=dtype, warps=warps)
+
+
+@pytest.mark.parametrize("dataset,hierarchy,dtype,warps", [("PascalContext", "induced-HRNet-w48-cls59", 0, None), ("ADE20K", "induced-HRNet-w48", 1, None),
+                                                          ("CIFAR100", "wordnet", 2, 3), ("LookIntoPerson", "induced-HRNet-w48-cls20", 0, 2)])
+def test_class_major_variant_matches_oracle(dataset, hierarchy, dtype, warps):
+    """(N, C, H, W) tensors addressed in place (the segmentation wrappers): same results as the row-major kernels."""
+    tree, ot, C = shipped(dataset, hierarchy)
+    check(tree, ot, C, dtype=dtype, warps=warps, rows=24, hw=8)
 
 
 def test_generated_code_imagenet_team_of_16():
