@@ -425,6 +425,10 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     nn_ops._OVERLAP_WGRAD = overlap
     conv_prof, conv_ops.PROFILE = conv_ops.PROFILE, None
+    try:
+        hbm_rows = hbm_kernel_profile(lambda: step(dev_x, dev_y), dev, load_peaks()[0]["hbm_gbs"])
+    except Exception as e:  # noqa: BLE001
+        hbm_rows = [{"error": f"{type(e).__name__}: {str(e)[:120]}"}]
     # The loss launch at the BASELINE batch is a few microseconds: time it as 50 launches inside one CUDA graph (event pairs
     # around single eager launches measure the Python launch path once the GPU has caught up with the CPU).
     tree_ms = sum(a.elapsed_time(b) for a, b in tree_ev) / max(len(tree_ev), 1)
@@ -531,6 +535,9 @@ def run_b200(args, rank, world, local_rank):
                           "frac": tree_bytes / (tree_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "launch_us": tree_ms * 1e3,
                           "note": f"{tree_bytes} B per launch at the BASELINE batch: latency-bound; `saturating` is the same kernel on rows that fill HBM",
                           "saturating": sat},
+        "hbm_kernels": {"rows": hbm_rows, "bound": "hbm", "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "note": "memory-bound kernels of one eager step, CUDA events around each C-ABI call (device held back by a spin kernel while "
+                                "the host enqueues); bytes = algorithmic tensor traffic from the call's size arguments"},
         "step_tflops": cfg["flops"] * B * world / (ms_per_step / 1e3) / 1e12,
         "loss": {"first_step": loss_first, "after_timed_steps": loss_last},  # sanity: the same synthetic batch is being fitted
     }
@@ -547,6 +554,87 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# HBM roofline of the memory-bound kernels of a step, measured at the C ABI: every call of the functions below is bracketed by
+# CUDA events for one eager step; the algorithmic bytes come from the call's own size arguments (bf16 activations = 2 B).
+# ---------------------------------------------------------------------------------------------------------------------
+def _has(a):
+    return getattr(a, "value", a) is not None
+
+
+def _ceil_div(a, b):
+    return (a + b - 1) // b
+
+
+HBM_KERNELS = {
+    # name: (what, bytes(args))
+    "nbdt_bn_stats": ("BatchNorm batch statistics (read x)", lambda a: a[1] * a[2] * 2),
+    "nbdt_bn_apply": ("BatchNorm apply + activation (+ residual)", lambda a: a[3] * a[4] * 2 * (2 + _has(a[1]))),
+    "nbdt_bn_backward": ("BatchNorm backward: reduce pass + apply pass", lambda a: a[7] * a[8] * 2 * (5 + 2 * _has(a[1]) + _has(a[4]) + _has(a[6]))),
+    "nbdt_bn_backward_silu": ("BatchNorm + SiLU backward: reduce pass + apply pass", lambda a: a[5] * a[6] * 2 * (5 + _has(a[3]))),
+    "nbdt_avgpool_fwd": ("global average pool", lambda a: a[2] * a[3] * a[4] * 2),
+    "nbdt_avgpool_bwd": ("global average pool backward", lambda a: a[2] * a[3] * a[4] * 2),
+    "nbdt_dwconv_fwd": ("depthwise conv forward", lambda a: a[4] * a[7] * 2 * (a[5] * a[6] + _ceil_div(a[5], a[9]) * _ceil_div(a[6], a[9]))),
+    "nbdt_dwconv_dgrad": ("depthwise conv data gradient", lambda a: a[3] * a[6] * 2 * (a[4] * a[5] + _ceil_div(a[4], a[8]) * _ceil_div(a[5], a[8]))),
+    "nbdt_dwconv_wgrad": ("depthwise conv weight gradient (reads x and dy)", lambda a: a[3] * a[6] * 2 * (a[4] * a[5] + _ceil_div(a[4], a[8]) * _ceil_div(a[5], a[8]))),
+    "nbdt_se_scale": ("squeeze-excitation scaling", lambda a: a[3] * a[4] * a[5] * 2 * 2),
+    "nbdt_se_dscale": ("squeeze-excitation scale gradient (reads x and dy)", lambda a: a[3] * a[4] * a[5] * 2 * 2),
+    "nbdt_sgd_step": ("fused SGD (read p, g, m; write p, m)", lambda a: a[3] * 4 * 5),
+}
+
+
+def hbm_kernel_profile(step_once, dev, hbm_peak):
+    """One eager step with every HBM_KERNELS call timed by CUDA events -> per-function ms, GB/s and fraction of the HBM peak.
+    The GPU is held back by a spin kernel while the host enqueues, so that the events bracket back-to-back device execution
+    and not the Python launch path."""
+    from nbdt._b200 import lib as L_
+
+    lib = L_.load()
+    records, originals = [], {}
+
+    def wrap(name, fn, nbytes):
+        def call(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            try:
+                b = int(nbytes(a))
+            except Exception:  # noqa: BLE001
+                b = 0
+            records.append((name, b, e0, e1))
+            return rc
+        return call
+
+    for name, (_, nbytes) in HBM_KERNELS.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            continue
+        originals[name] = fn
+        setattr(lib, name, wrap(name, fn, nbytes))
+    try:
+        torch.cuda.synchronize(dev)
+        if hasattr(torch.cuda, "_sleep"):
+            torch.cuda._sleep(int(2.5e8))  # ~0.13 s at 1.9 GHz: the host gets ahead of the device
+        step_once()
+        torch.cuda.synchronize(dev)
+    finally:
+        for name, fn in originals.items():
+            setattr(lib, name, fn)
+    out = {}
+    for name, b, e0, e1 in records:
+        st = out.setdefault(name, [0, 0.0, 0])
+        st[0] += b
+        st[1] += e0.elapsed_time(e1)
+        st[2] += 1
+    rows = []
+    for name, (nb, ms, n) in sorted(out.items(), key=lambda kv: -kv[1][1]):
+        gbs = nb / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        rows.append({"abi_call": name, "what": HBM_KERNELS[name][0], "launches_per_step": n, "ms_per_step": round(ms, 4),
+                     "algorithmic_mb_per_step": round(nb / 1e6, 2), "gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)})
+    return rows
 
 
 def main():

@@ -118,16 +118,20 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
 
+@pytest.mark.parametrize("fused_bn_stats", [False, True])
 @pytest.mark.parametrize("arch", ["ResNet18", "wrn"])
-def test_network_forward_backward_matches_eager(arch):
+def test_network_forward_backward_matches_eager(arch, fused_bn_stats, monkeypatch):
     """Same parameters, same batch: B200 kernels (bf16 activations, fp32 accumulation) vs the fp32 eager oracle
     module.  Random-init 18/28-layer nets amplify bf16 rounding in the gradients, so the yardstick for the
     backward is the SAME eager module run under bf16 autocast (cuDNN): our per-parameter gradient agreement
-    with fp32 must be as good as autocast's (scripts/diag_network.py prints both: medians ~0.95)."""
+    with fp32 must be as good as autocast's (scripts/diag_network.py prints both: medians ~0.95).
+    fused_bn_stats: the same with the BatchNorm statistics accumulated in the convolution epilogues (NBDT_B200_BN_FUSED_STATS=1)."""
     from nbdt.loss import SoftTreeSupLoss
     from nbdt import models
+    from nbdt._b200 import backbone as B
     from oracle import torch_port as P
 
+    monkeypatch.setattr(B, "_FUSED_BN_STATS", fused_bn_stats)
     torch.manual_seed(0)
     if arch == "ResNet18":
         net, mk, hierarchy = models.ResNet18(num_classes=10).to(DEV), lambda: P.EagerResNet(num_classes=10), "induced-ResNet18"

@@ -156,10 +156,10 @@ def test_class_major_kernels_equal_the_permuted_row_kernels(shape, dtype):
     lp = dtype != torch.float32
 
     soft = ops.soft_forward_nchw(tree, x)
-    want = uncoerce_tensor(ops.soft_forward(tree, rows), x.shape)
-    torch.testing.assert_close(soft, want, rtol=2e-5, atol=1e-7)
     name = L.load().nbdt_tree_kernel_variant(tree.device_tree(torch.device(DEV)).handle).decode()
     assert ("_nchw" in name) == ((H * W) % 32 == 0), name
+    want = uncoerce_tensor(ops.soft_forward(tree, rows), x.shape)
+    torch.testing.assert_close(soft, want, rtol=2e-5, atol=1e-7)
 
     pred = ops.hard_forward_nchw(tree, x)
     want_pred, _ = ops.hard_forward(tree, rows)
@@ -167,6 +167,8 @@ def test_class_major_kernels_equal_the_permuted_row_kernels(shape, dtype):
 
     for w_tree in (1.0, 0.5):
         loss, grad = ops.tree_loss_nchw(tree, x, y, 1.0, w_tree)
+        name = L.load().nbdt_tree_kernel_variant(tree.device_tree(torch.device(DEV)).handle).decode()
+        assert ("_nchw" in name) == ((H * W) % 32 == 0), name
         want_l, want_g = ops.tree_loss(tree, rows, y.reshape(-1), "soft", 1.0, w_tree)
         assert abs(loss.item() - want_l.item()) <= 2e-5 * abs(want_l.item())
         want_g = uncoerce_tensor(want_g, x.shape).float()
