@@ -425,10 +425,12 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     nn_ops._OVERLAP_WGRAD = overlap
     conv_prof, conv_ops.PROFILE = conv_ops.PROFILE, None
+    nn_ops._OVERLAP_WGRAD = False  # as above: no weight-gradient kernels co-running on the side stream
     try:
         hbm_rows = hbm_kernel_profile(lambda: step(dev_x, dev_y), dev, load_peaks()[0]["hbm_gbs"])
     except Exception as e:  # noqa: BLE001
         hbm_rows = [{"error": f"{type(e).__name__}: {str(e)[:120]}"}]
+    nn_ops._OVERLAP_WGRAD = overlap
     # The loss launch at the BASELINE batch is a few microseconds: time it as 50 launches inside one CUDA graph (event pairs
     # around single eager launches measure the Python launch path once the GPU has caught up with the CPU).
     tree_ms = sum(a.elapsed_time(b) for a, b in tree_ev) / max(len(tree_ev), 1)

@@ -108,31 +108,43 @@ __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restric
 }
 
 // Totals of the per-CTA partials [nparts][2][C] for channel c (fixed order, fp64).  CTA = 1024 threads = 32 channels
-// (lanes) x 32 slices of the partial list (warps): a thread's chain of dependent L2 reads is nparts/64 iterations
-// with four loads in flight (the v1 finalize kernels read all partials from one thread per channel: ~20 us of pure
-// latency per BatchNorm).  The totals are returned to the threads of warp 0.
+// (lanes) x 32 slices of the partial list (warps): a thread's chain of dependent L2 reads is nparts/256 iterations
+// with sixteen loads in flight (the v1 finalize kernels read all partials from one thread per channel: ~20 us of pure
+// latency per BatchNorm; round 1's four loads in flight still took ten round trips).  The totals are returned to warp 0.
 constexpr int kFinalizeThreads = 1024;
 __device__ __forceinline__ void reduce_partials2(const float* __restrict__ partials, int nparts, int C, int c,
                                                  double& t0, double& t1) {
   __shared__ double slices[2][32][33];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+  // eight rows of the partial list per thread and iteration = sixteen independent L2 reads in flight: the 592 rows of a
+  // 4-CTAs-per-SM reduction are three dependent round trips instead of ten (the finalize kernels are pure latency)
+  constexpr int U = 8;
+  double a[U], bq[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) { a[u] = 0.0; bq[u] = 0.0; }
   if (c < C) {
     const long long n = 2LL * C;
     int b = slice;
-    for (; b + 32 < nparts; b += 64) {
-      a0 += (double)__ldg(partials + b * n + c);
-      b0 += (double)__ldg(partials + b * n + C + c);
-      a1 += (double)__ldg(partials + (b + 32) * n + c);
-      b1 += (double)__ldg(partials + (b + 32) * n + C + c);
+    for (; b + 32 * (U - 1) < nparts; b += 32 * U) {
+      float va[U], vb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        va[u] = __ldg(partials + (long long)(b + 32 * u) * n + c);
+        vb[u] = __ldg(partials + (long long)(b + 32 * u) * n + C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { a[u] += (double)va[u]; bq[u] += (double)vb[u]; }
     }
     for (; b < nparts; b += 32) {
-      a0 += (double)__ldg(partials + b * n + c);
-      b0 += (double)__ldg(partials + b * n + C + c);
+      a[0] += (double)__ldg(partials + (long long)b * n + c);
+      bq[0] += (double)__ldg(partials + (long long)b * n + C + c);
     }
   }
-  slices[0][slice][lane] = a0 + a1;
-  slices[1][slice][lane] = b0 + b1;
+  double sa = 0.0, sb = 0.0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) { sa += a[u]; sb += bq[u]; }
+  slices[0][slice][lane] = sa;
+  slices[1][slice][lane] = sb;
   __syncthreads();
   t0 = 0.0;
   t1 = 0.0;

@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -41,7 +42,9 @@ __device__ __forceinline__ float activate(float v, int act) {
 // vector) of a strip of TW consecutive output pixels of one output row: per kernel row it loads the
 // (TW-1)*S + K input vectors of that row once and slides the K taps over them (weights [K*K][C] fp32 through L1).
 // Work items are ordered channel-octet fastest, so a warp reads 512 contiguous bytes per input pixel.
-template <int K, int S, int TW>
+// FLIP: the taps are read in reverse order -- the stride-1 DATA GRADIENT is this same convolution of dy with the flipped filter
+// (dx[hi,wi] = sum w[K-1-r'][K-1-s'] * dy[hi+r'-PAD, wi+s'-PAD]), so nbdt_dwconv_dgrad runs this kernel for stride 1.
+template <int K, int S, int TW, bool FLIP = false>
 __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ scale_shift, uint4* __restrict__ y,
                                                          int N, int H, int W, int C, int Ho, int Wo, int act) {
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const uint4* __restrict
       }
 #pragma unroll
       for (int s = 0; s < K; ++s) {
-        const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(r * K + s) * C + o * 8);
+        const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(FLIP ? K * K - 1 - (r * K + s) : r * K + s) * C + o * 8);
         const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
         const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
@@ -246,6 +249,112 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const uint4* __restri
   }
 }
 
+// Weight gradient, ONE pass over x and dy (round 2; the kernel above makes K passes, one per kernel row, and ran at 7 % of the
+// HBM peak in the EfficientNet-B0 train step, profiles/r02_bench_c5_*.json).  A thread owns CG channels and ALL K x K taps of them
+// in registers (K*K*CG accumulators: 50 at K = 5 / CG = 2, 36 at K = 3 / CG = 4) and walks over work items = strips of TW
+// consecutive output pixels of one output row: per kernel row it loads the (TW-1)*S + K input vectors once and slides the K taps
+// over them against the strip's TW dy vectors -- (TW-1)*S + K loads for TW*K*CG fused multiply-adds.  Consecutive threads are
+// consecutive channel groups of the same pixel (a warp reads 128 or 256 contiguous bytes per pixel).  The threads of a CTA that
+// share a channel group are combined in shared memory, CTAs with fp32 atomics (dw zeroed by the caller).
+// bytes: (N*H*W + N*Ho*Wo)*C*2 read once (neighbouring rows / strips overlap in L1 / L2)
+template <int CG> struct DwVec;
+template <> struct DwVec<2> { typedef uint32_t type; };
+template <> struct DwVec<4> { typedef uint2 type; };
+__device__ __forceinline__ void dw_unpack(uint32_t v, float (&f)[2]) {
+  f[0] = __uint_as_float(v << 16);
+  f[1] = __uint_as_float(v & 0xffff0000u);
+}
+__device__ __forceinline__ void dw_unpack(uint2 v, float (&f)[4]) {
+  f[0] = __uint_as_float(v.x << 16);
+  f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16);
+  f[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t dw_zero(uint32_t) { return 0u; }
+__device__ __forceinline__ uint2 dw_zero(uint2) { return make_uint2(0u, 0u); }
+
+template <int K, int S, int CG>
+__global__ void __launch_bounds__(256) dwconv_wgrad1_kernel(const void* __restrict__ xv, const void* __restrict__ dyv,
+                                                            float* __restrict__ dw, int N, int H, int W, int C, int Ho,
+                                                            int Wo) {
+  typedef typename DwVec<CG>::type V;
+  constexpr int PAD = K / 2, TW = 4, IN = (TW - 1) * S + K;
+  __shared__ float red[256 * CG];
+  const V* __restrict__ x = reinterpret_cast<const V*>(xv);
+  const V* __restrict__ dy = reinterpret_cast<const V*>(dyv);
+  const int groups = C / CG;                              // channel groups of the tensor
+  const int g0 = blockIdx.y * 256;                        // first group of this CTA
+  const int G = min(groups - g0, 256);                    // groups of this CTA
+  const int slots = 256 / G;                              // threads per group (>= 1)
+  const int g = threadIdx.x % G, slot = threadIdx.x / G;
+  const bool active = slot < slots;
+  const int cg = g0 + g;
+  const unsigned strips = (Wo + TW - 1) / TW;
+  const unsigned total = (unsigned)N * Ho * strips;
+  float acc[K * K][CG];
+#pragma unroll
+  for (int t = 0; t < K * K; ++t)
+#pragma unroll
+    for (int e = 0; e < CG; ++e) acc[t][e] = 0.f;
+  if (active) {
+    for (unsigned item = blockIdx.x * slots + slot; item < total; item += gridDim.x * slots) {
+      const unsigned strip = item % strips;
+      unsigned t = item / strips;
+      const int ho = t % (unsigned)Ho;
+      const unsigned n = t / (unsigned)Ho;
+      const int wo0 = strip * TW;
+      const int wi0 = wo0 * S - PAD;
+      float gy[TW][CG];
+      const V* grow = dy + ((size_t)(n * Ho + ho) * Wo) * groups + cg;
+#pragma unroll
+      for (int i = 0; i < TW; ++i) {
+        const V v = (wo0 + i < Wo) ? __ldg(grow + (size_t)(wo0 + i) * groups) : dw_zero(V());
+        dw_unpack(v, gy[i]);
+      }
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        const int hi = ho * S + r - PAD;
+        if (hi < 0 || hi >= H) continue;
+        const V* row = x + ((size_t)(n * H + hi) * W) * groups + cg;
+        V in[IN];
+#pragma unroll
+        for (int j = 0; j < IN; ++j) {
+          const int wi = wi0 + j;
+          in[j] = (wi >= 0 && wi < W) ? __ldg(row + (size_t)wi * groups) : dw_zero(V());
+        }
+#pragma unroll
+        for (int j = 0; j < IN; ++j) {
+          float f[CG];
+          dw_unpack(in[j], f);
+          // input vector j meets output pixel i at tap s = j - i*S
+#pragma unroll
+          for (int i = 0; i < TW; ++i) {
+            const int sft = j - i * S;
+            if (sft >= 0 && sft < K) {
+#pragma unroll
+              for (int e = 0; e < CG; ++e) acc[r * K + sft][e] = fmaf(gy[i][e], f[e], acc[r * K + sft][e]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // combine the threads of this CTA that share a channel group (one tap at a time through shared memory), then one atomic per value
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) {
+    __syncthreads();
+    if (active)
+#pragma unroll
+      for (int e = 0; e < CG; ++e) red[(slot * G + g) * CG + e] = acc[t][e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < G * CG; c += 256) {
+      float v = 0.f;
+      for (int q = 0; q < slots; ++q) v += red[q * G * CG + c];
+      atomicAdd(dw + (size_t)t * C + g0 * CG + c, v);
+    }
+  }
+}
+
 // ds[n][c] = sum over the HW pixels of image n of x[n,p,c] * dy[n,p,c]  (gradient of the squeeze-excitation scale).
 // Same slicing as avgpool_fwd_kernel (bn_ops.cu): CTA (slice, image); slices combined with fp32 atomics into a zeroed output.
 __global__ void __launch_bounds__(256) se_dscale_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy,
@@ -355,10 +464,19 @@ int nbdt_dwconv_dgrad(const void* dy, const float* w, void* dx, int N, int H, in
   const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
   const long long items = (long long)N * H * W * (C / 8);
   NBDT_REQUIRE(items < (1LL << 31) - (1 << 24), "depthwise conv too large (%lld work items)", items);
-  const int grid = (int)std::min<long long>((items + 255) / 256, (long long)sm_count() * 16);
   cudaStream_t st = (cudaStream_t)stream;
   const uint4* gs = reinterpret_cast<const uint4*>(dy);
   uint4* xs = reinterpret_cast<uint4*>(dx);
+  if (stride == 1) {  // the forward kernel on dy with the flipped filter: strips of 4 pixels share their input loads
+    constexpr int TW = 4;
+    const long long fitems = (long long)N * H * ((W + TW - 1) / TW) * (C / 8);
+    const int fgrid = (int)std::min<long long>((fitems + 255) / 256, (long long)sm_count() * 16);
+    if (ksize == 3) dwconv_fwd_kernel<3, 1, TW, true><<<fgrid, 256, 0, st>>>(gs, w, nullptr, xs, N, H, W, C, H, W, 0);
+    else dwconv_fwd_kernel<5, 1, TW, true><<<fgrid, 256, 0, st>>>(gs, w, nullptr, xs, N, H, W, C, H, W, 0);
+    NBDT_CUDA_OK(cudaGetLastError());
+    return NBDT_OK;
+  }
+  const int grid = (int)std::min<long long>((items + 255) / 256, (long long)sm_count() * 16);
 #define NBDT_DWD(K, S) dwconv_dgrad_kernel<K, S><<<grid, 256, 0, st>>>(gs, w, xs, N, H, W, C, Ho, Wo)
   if (ksize == 3 && stride == 1) NBDT_DWD(3, 1);
   else if (ksize == 3) NBDT_DWD(3, 2);
@@ -380,6 +498,23 @@ int nbdt_dwconv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
   NBDT_REQUIRE((long long)N * Ho * Wo < (1LL << 31) - (1 << 24), "depthwise conv too large");
   cudaStream_t st = (cudaStream_t)stream;
   NBDT_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)ksize * ksize * C * sizeof(float), st));
+  static const bool k_passes = getenv("NBDT_B200_DWWGRAD_KPASS") != nullptr;  // the round-1 kernel, for A/B measurements
+  if (!k_passes) {
+    const int cg = ksize == 3 ? 4 : 2;
+    const int groups = C / cg;
+    const int slots = std::max(1, 256 / std::min(groups, 256));
+    const long long items = (long long)N * Ho * ((Wo + 3) / 4);
+    const int gx = (int)std::max<long long>(1, std::min<long long>((items + slots - 1) / slots, (long long)sm_count() * 2));
+    const dim3 grid(gx, (groups + 255) / 256);
+#define NBDT_DWW1(K, S, CG) dwconv_wgrad1_kernel<K, S, CG><<<grid, 256, 0, st>>>(x, dy, dw, N, H, W, C, Ho, Wo)
+    if (ksize == 3 && stride == 1) NBDT_DWW1(3, 1, 4);
+    else if (ksize == 3) NBDT_DWW1(3, 2, 4);
+    else if (stride == 1) NBDT_DWW1(5, 1, 2);
+    else NBDT_DWW1(5, 2, 2);
+#undef NBDT_DWW1
+    NBDT_CUDA_OK(cudaGetLastError());
+    return NBDT_OK;
+  }
   const int octets = C / 8;
   const int R = octets <= 256 ? 256 / octets : 1;
   const long long pix = (long long)N * Ho * Wo;
