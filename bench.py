@@ -573,6 +573,7 @@ def _ceil_div(a, b):
 HBM_KERNELS = {
     # name: (what, bytes(args))
     "nbdt_bn_stats": ("BatchNorm batch statistics (read x)", lambda a: a[1] * a[2] * 2),
+    "nbdt_bn_stats_apply": ("BatchNorm forward: statistics pass + apply pass (+ activation, + residual)", lambda a: a[3] * a[4] * 2 * (3 + _has(a[1]))),
     "nbdt_bn_apply": ("BatchNorm apply + activation (+ residual)", lambda a: a[3] * a[4] * 2 * (2 + _has(a[1]))),
     "nbdt_bn_backward": ("BatchNorm backward: reduce pass + apply pass", lambda a: a[7] * a[8] * 2 * (5 + 2 * _has(a[1]) + _has(a[4]) + _has(a[6]))),
     "nbdt_bn_backward_silu": ("BatchNorm + SiLU backward: reduce pass + apply pass", lambda a: a[5] * a[6] * 2 * (5 + _has(a[3]))),

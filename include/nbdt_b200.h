@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define NBDT_B200_VERSION 104 /* 104: class-major tree entry points (nbdt_*_nchw); 103: BatchNorm statistics from the convolution epilogue (nbdt_conv2d_fwd_stats, nbdt_bn_finalize_partials); 102: run-time specialised tree kernels (nbdt_tree_jit_*, nbdt_tree_kernel_variant); out-of-range targets are ignored rows */
+#define NBDT_B200_VERSION 105 /* 105: nbdt_bn_stats_apply (BatchNorm finalize folded into the consumer kernels); 104: class-major tree entry points (nbdt_*_nchw); 103: BatchNorm statistics from the convolution epilogue (nbdt_conv2d_fwd_stats, nbdt_bn_finalize_partials); 102: run-time specialised tree kernels (nbdt_tree_jit_*, nbdt_tree_kernel_variant); out-of-range targets are ignored rows */
 
 enum { NBDT_OK = 0, NBDT_EINVAL = 1, NBDT_ECUDA = 2, NBDT_ETREE = 3, NBDT_ETOOLARGE = 4 };
 enum { NBDT_F32 = 0, NBDT_BF16 = 1, NBDT_F16 = 2 };
@@ -196,6 +196,13 @@ long long nbdt_bn_scratch_floats(int C);
 int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, float* sums,
                   float* mean_invstd, float* scale_shift, void* stream);
+/* nbdt_bn_stats + nbdt_bn_apply in two launches instead of three: the statistics kernel accumulates into one fp64 [2][C]
+ * buffer (the head of `sums`, 8-byte aligned) and the apply kernel finalizes mean / invstd / scale / shift in its prologue,
+ * writes mean_invstd / scale_shift (for the backward pass) and updates the running statistics.  The training-mode
+ * nn.BatchNorm2d (+ F.relu, + residual) of the reference's blocks (nbdt/models/resnet.py:50-54,70-73). */
+int nbdt_bn_stats_apply(const void* x, const void* residual, void* y, long long M, int C, int c_real, const float* gamma,
+                        const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* sums,
+                        float* mean_invstd, float* scale_shift, int relu, void* stream);
 /* The same from per-CTA partial sums [nparts][2][C] over M rows in total (written by nbdt_conv2d_fwd_stats). */
 int nbdt_bn_finalize_partials(const float* partials, int nparts, long long M, int C, int c_real, const float* gamma,
                               const float* beta, float* running_mean, float* running_var, float momentum, float eps,

@@ -14,6 +14,8 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdint>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -68,8 +70,12 @@ __device__ __forceinline__ void load8(const float* __restrict__ p, float (&f)[8]
 //   void accum(pack, acc)        -- the arithmetic
 // Each CTA writes its partial sums to out[blockIdx.x][NACC][C]; reduce_partials2() adds them in a fixed order
 // (deterministic; same-address atomics serialise in L2).
+// acc64 (optional, only for C <= 8 * kThreads): instead of a partial row per CTA, every CTA adds its sums to ONE fp64
+// accumulator [NACC][C] (zeroed by the caller) and the CONSUMER kernel derives its coefficients from it in its prologue: the
+// separate finalize launch (five 1024-thread CTAs chasing ~600 partial rows: 10-15 us of pure latency per BatchNorm, 50 per
+// train step) disappears.  fp64 atomics: the order of the ~600 additions per channel changes the sum in the 16th digit only.
 template <int NACC, int UNROLL, typename Op>
-__device__ __forceinline__ void reduce_rows(long long M, int C, float* __restrict__ out, Op op) {
+__device__ __forceinline__ void reduce_rows(long long M, int C, float* __restrict__ out, Op op, double* __restrict__ acc64 = nullptr) {
   extern __shared__ float red[];  // [R][NACC][C]  (only when R > 1)
   const int octets = C / 8;
   float* part = out + (long long)blockIdx.x * NACC * C;
@@ -89,6 +95,13 @@ __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restric
       for (int u = 0; u < UNROLL; ++u) op.accum(pk[u], acc);
     }
     for (; row < M; row += stride) op.accum(op.load(row, o), acc);
+    if (R == 1 && acc64) {  // 128 <= octets <= 256: one thread per octet, nothing to combine inside the CTA
+#pragma unroll
+      for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(acc64 + (size_t)a * C + o * 8 + e, (double)acc[a][e]);
+      return;
+    }
     float* dst = R > 1 ? red + (size_t)(threadIdx.x / octets) * NACC * C : part;
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
@@ -102,7 +115,8 @@ __device__ __forceinline__ void reduce_rows(long long M, int C, float* __restric
     for (int i = threadIdx.x; i < NACC * C; i += kThreads) {
       float s = 0.f;
       for (int q = 0; q < R; ++q) s += red[(size_t)q * NACC * C + i];
-      part[i] = s;
+      if (acc64) atomicAdd(acc64 + i, (double)s);
+      else part[i] = s;
     }
   }
 }
@@ -175,9 +189,23 @@ struct StatsOp {
 
 // partials[cta][0][c] = sum_rows x, [1][c] = sum_rows x^2.          bytes: M*C*2 read
 __global__ void __launch_bounds__(kThreads, 4) bn_stats_kernel(const uint4* __restrict__ x, long long M, int C,
-                                                            float* __restrict__ partials) {
-  reduce_rows<2, 8>(M, C, partials, StatsOp{x, C / 8});
+                                                            float* __restrict__ partials, double* __restrict__ acc64) {
+  reduce_rows<2, 8>(M, C, partials, StatsOp{x, C / 8}, acc64);
 }
+
+// What the apply kernel needs to turn the accumulated sums into this BatchNorm's coefficients (and to publish them).
+struct BnFromSums {
+  const double* sums;  // [2][C]: sum x, sum x^2 over M rows; nullptr = coefficients are given
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* mean_invstd;  // out [2][C] (saved for the backward pass)
+  float* scale_shift;  // out [2][C]
+  long long M;
+  int c_real;
+  float momentum, eps;
+};
 
 // mean/invstd, affine scale/shift, running-stat update (momentum, unbiased variance).  grid = ceil(C/32) x 1024 threads.
 __global__ void __launch_bounds__(kFinalizeThreads) bn_finalize_kernel(const float* __restrict__ partials, int nparts, long long M,
@@ -228,12 +256,45 @@ __global__ void bn_eval_scale_kernel(int C, int c_real, const float* __restrict_
 template <bool RES>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res,
                                                             uint4* __restrict__ y, long long M, int C,
-                                                            const float* __restrict__ scale_shift, int relu) {
+                                                            const float* __restrict__ scale_shift, int relu, const BnFromSums fs) {
   const int octets = C / 8;
   for_octet_rows(octets, [&](int o, long long row, long long stride) {
     float sc[8], sh[8];
-    load8(scale_shift + o * 8, sc);
-    load8(scale_shift + C + o * 8, sh);
+    if (fs.sums) {
+      // every thread finalizes its own eight channels (same arithmetic as bn_finalize_kernel); the threads that start at row 0
+      // publish mean / invstd / scale / shift and move the running statistics
+      const bool publish = row == 0;
+      const double inv_m = 1.0 / (double)fs.M;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = o * 8 + e;
+        if (c >= fs.c_real) {  // zero-padded channel: stays exactly zero
+          sc[e] = 0.f; sh[e] = 0.f;
+          if (publish) { fs.mean_invstd[c] = 0.f; fs.mean_invstd[C + c] = 0.f; fs.scale_shift[c] = 0.f; fs.scale_shift[C + c] = 0.f; }
+          continue;
+        }
+        const double mean = fs.sums[c] * inv_m;
+        double var = fs.sums[C + c] * inv_m - mean * mean;
+        if (var < 0) var = 0;
+        const float invstd = (float)(1.0 / sqrt(var + (double)fs.eps));
+        sc[e] = fs.gamma[c] * invstd;
+        sh[e] = fs.beta[c] - (float)mean * sc[e];
+        if (publish) {
+          fs.mean_invstd[c] = (float)mean;
+          fs.mean_invstd[C + c] = invstd;
+          fs.scale_shift[c] = sc[e];
+          fs.scale_shift[C + c] = sh[e];
+          if (fs.running_mean) {
+            const double unbiased = fs.M > 1 ? var * (double)fs.M / (double)(fs.M - 1) : var;
+            fs.running_mean[c] = (1.f - fs.momentum) * fs.running_mean[c] + fs.momentum * (float)mean;
+            fs.running_var[c] = (1.f - fs.momentum) * fs.running_var[c] + fs.momentum * (float)unbiased;
+          }
+        }
+      }
+    } else {
+      load8(scale_shift + o * 8, sc);
+      load8(scale_shift + C + o * 8, sh);
+    }
     auto one = [&](long long rw, const uint4& vx, const uint4& vr) {
       float f[8], r[8];
       unpack8(vx, f);
@@ -324,12 +385,20 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_reduce_kernel(const uint4*
                                                                  const uint4* __restrict__ dy, long long M, int C,
                                                                  const float* __restrict__ mean_invstd,
                                                                  const float* __restrict__ scale_shift,
-                                                                 float* __restrict__ partials) {
+                                                                 float* __restrict__ partials, double* __restrict__ acc64) {
   BwdReduceOp<MASK> op;
   op.x = x; op.act = act; op.dy = dy; op.mean_invstd = mean_invstd; op.scale_shift = scale_shift;
   op.octets = C / 8; op.C = C;
-  reduce_rows<2, 4>(M, C, partials, op);
+  reduce_rows<2, 4>(M, C, partials, op, acc64);
 }
+
+struct BnBwdFromSums {
+  const double* sums;  // [2][C]: sum g, sum g (x - mean); nullptr = coef is given
+  const float* gamma;
+  const float* mean_invstd;
+  float* dsums;        // out [2][C]: dbeta, dgamma
+  int c_real;
+};
 
 // dsums[0][c] = dbeta = sum g, dsums[1][c] = dgamma = invstd * sum g (x - mean); coef[3][C] = (k1, a, b) with
 // dx = k1*g + a*x + b:  k1 = gamma*invstd, a = -k1*invstd*dgamma/M, b = -k1*dbeta/M - a*mean.
@@ -360,13 +429,28 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_kernel(const uint4* 
                                                                 const uint4* __restrict__ dy, const uint4* __restrict__ extra,
                                                                 uint4* __restrict__ dx, uint4* __restrict__ dres,
                                                                 long long M, int C, const float* __restrict__ coef,
-                                                                const float* __restrict__ scale_shift) {
+                                                                const float* __restrict__ scale_shift, const BnBwdFromSums fs) {
   const int octets = C / 8;
   for_octet_rows(octets, [&](int o, long long row, long long stride) {
     float k1[8], ka[8], kb[8], sc[8], sh[8];
-    load8(coef + o * 8, k1);
-    load8(coef + C + o * 8, ka);
-    load8(coef + 2 * C + o * 8, kb);
+    if (fs.sums) {  // the arithmetic of bn_bwd_finalize_kernel, per thread for its own eight channels
+      const bool publish = row == 0;
+      const float inv_m = 1.f / (float)M;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int c = o * 8 + e;
+        const float mean = fs.mean_invstd[c], invstd = fs.mean_invstd[C + c];
+        const float dbeta = (float)fs.sums[c], dgamma = (float)(fs.sums[C + c] * (double)invstd);
+        if (publish) { fs.dsums[c] = dbeta; fs.dsums[C + c] = dgamma; }
+        k1[e] = c < fs.c_real ? fs.gamma[c] * invstd : 0.f;
+        ka[e] = -k1[e] * invstd * dgamma * inv_m;
+        kb[e] = -k1[e] * dbeta * inv_m - ka[e] * mean;
+      }
+    } else {
+      load8(coef + o * 8, k1);
+      load8(coef + C + o * 8, ka);
+      load8(coef + 2 * C + o * 8, kb);
+    }
     if (MASK == kMaskRecompute || MASK == kMaskSiLU) {
       load8(scale_shift + o * 8, sc);
       load8(scale_shift + C + o * 8, sh);
@@ -622,7 +706,7 @@ int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* ga
   NBDT_REQUIRE(C % 8 == 0 && C <= 8192 && M > 0, "bad shape M=%lld C=%d", M, C);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = rows_grid(M, C, kReduceCtasPerSm);
-  bn_stats_kernel<<<grid, kThreads, reduce_smem(C), st>>>(reinterpret_cast<const uint4*>(x), M, C, sums);
+  bn_stats_kernel<<<grid, kThreads, reduce_smem(C), st>>>(reinterpret_cast<const uint4*>(x), M, C, sums, nullptr);
   bn_finalize_kernel<<<(C + 31) / 32, kFinalizeThreads, 0, st>>>(sums, grid, M, C, c_real, gamma, beta, running_mean, running_var,
                                                          momentum, eps, mean_invstd, scale_shift);
   NBDT_CUDA_OK(cudaGetLastError());
@@ -667,10 +751,41 @@ int nbdt_bn_apply(const void* x, const void* residual, void* y, long long M, int
   const uint4* xs = reinterpret_cast<const uint4*>(x);
   const uint4* rs = reinterpret_cast<const uint4*>(residual);
   uint4* ys = reinterpret_cast<uint4*>(y);
+  const BnFromSums none = {};
   if (residual)
-    bn_apply_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(xs, rs, ys, M, C, scale_shift, relu);
+    bn_apply_kernel<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(xs, rs, ys, M, C, scale_shift, relu, none);
   else
-    bn_apply_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(xs, rs, ys, M, C, scale_shift, relu);
+    bn_apply_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(xs, rs, ys, M, C, scale_shift, relu, none);
+  NBDT_CUDA_OK(cudaGetLastError());
+  return NBDT_OK;
+}
+
+// (Experiment, see bn_backward_impl: not faster than nbdt_bn_stats + nbdt_bn_apply; nbdt/_b200/nn_ops.py uses it only with
+// NBDT_B200_BN_FOLD_FINALIZE=1.)
+// Training-mode BatchNorm forward in two launches instead of three: the statistics kernel adds every CTA's sums to one fp64
+// accumulator (the first 4*C floats of `sums`, zeroed here), and the apply kernel derives mean / invstd / scale / shift from it in
+// its prologue (every thread for its own eight channels), publishes them for the backward pass and moves the running statistics.
+// Arguments: nbdt_bn_stats + nbdt_bn_apply.  (nbdt_bn_stats + nbdt_bn_apply remain for callers that need the coefficients first.)
+int nbdt_bn_stats_apply(const void* x, const void* residual, void* y, long long M, int C, int c_real, const float* gamma,
+                        const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* sums,
+                        float* mean_invstd, float* scale_shift, int relu, void* stream) {
+  NBDT_REQUIRE(x && y && gamma && beta && sums && mean_invstd && scale_shift, "NULL tensor");
+  NBDT_REQUIRE(C % 8 == 0 && C <= 8192 && M > 0, "bad shape M=%lld C=%d", M, C);
+  NBDT_REQUIRE((reinterpret_cast<uintptr_t>(sums) & 7) == 0, "sums must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc = reinterpret_cast<double*>(sums);
+  NBDT_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), st));
+  const int grid = rows_grid(M, C, kReduceCtasPerSm);
+  bn_stats_kernel<<<grid, kThreads, reduce_smem(C), st>>>(reinterpret_cast<const uint4*>(x), M, C, nullptr, acc);
+  BnFromSums fs;
+  fs.sums = acc; fs.gamma = gamma; fs.beta = beta; fs.running_mean = running_mean; fs.running_var = running_var;
+  fs.mean_invstd = mean_invstd; fs.scale_shift = scale_shift; fs.M = M; fs.c_real = c_real; fs.momentum = momentum; fs.eps = eps;
+  const int agrid = rows_grid(M, C, 6);
+  const uint4* xs = reinterpret_cast<const uint4*>(x);
+  const uint4* rs = reinterpret_cast<const uint4*>(residual);
+  uint4* ys = reinterpret_cast<uint4*>(y);
+  if (residual) bn_apply_kernel<true><<<agrid, kThreads, 0, st>>>(xs, rs, ys, M, C, nullptr, relu, fs);
+  else bn_apply_kernel<false><<<agrid, kThreads, 0, st>>>(xs, rs, ys, M, C, nullptr, relu, fs);
   NBDT_CUDA_OK(cudaGetLastError());
   return NBDT_OK;
 }
@@ -694,18 +809,28 @@ static int bn_backward_impl(int mask, const void* x, const void* act, const floa
   uint4* drs = reinterpret_cast<uint4*>(dres);
   const int grid = rows_grid(M, C, kReduceCtasPerSm);
   const size_t smem = reduce_smem(C);
+  // NBDT_B200_BN_FOLD_FINALIZE=1: two launches -- the reduce kernel adds into one fp64 accumulator (first 4*C floats of the partials
+  // area, zeroed here) and the apply kernel derives (k1, a, b) from it in its prologue and publishes dbeta / dgamma.  Measured
+  // SLOWER than the partial rows + finalize launch (WRN-28-10 step 19.2 vs 18.6 ms in one run, profiles/r02_bn_fold_finalize_ab.md:
+  // ~600 same-address fp64 atomics per channel serialise in L2 for as long as the finalize kernel takes), so it is off by default.
+  static const bool finalize_kernel = getenv("NBDT_B200_BN_FOLD_FINALIZE") == nullptr;
+  double* acc = finalize_kernel ? nullptr : reinterpret_cast<double*>(partials);
+  NBDT_REQUIRE(finalize_kernel || (reinterpret_cast<uintptr_t>(partials) & 7) == 0, "dsums must be 8-byte aligned");
+  if (acc) NBDT_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), st));
   if (mask == kMaskAct)
-    bn_bwd_reduce_kernel<kMaskAct><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
+    bn_bwd_reduce_kernel<kMaskAct><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc);
   else if (mask == kMaskRecompute)
-    bn_bwd_reduce_kernel<kMaskRecompute><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
+    bn_bwd_reduce_kernel<kMaskRecompute><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc);
   else if (mask == kMaskSiLU)
-    bn_bwd_reduce_kernel<kMaskSiLU><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
+    bn_bwd_reduce_kernel<kMaskSiLU><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc);
   else
-    bn_bwd_reduce_kernel<kMaskNone><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials);
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinalizeThreads, 0, st>>>(partials, grid, M, C, c_real, gamma, mean_invstd, dsums, coef);
+    bn_bwd_reduce_kernel<kMaskNone><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc);
+  BnBwdFromSums fs = {};
+  if (acc) { fs.sums = acc; fs.gamma = gamma; fs.mean_invstd = mean_invstd; fs.dsums = dsums; fs.c_real = c_real; }
+  else bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinalizeThreads, 0, st>>>(partials, grid, M, C, c_real, gamma, mean_invstd, dsums, coef);
   const int agrid = rows_grid(M, C, 4);
 #define NBDT_BWD_APPLY(MASK, EXTRA, DRES) \
-  bn_bwd_apply_kernel<MASK, EXTRA, DRES><<<agrid, kThreads, 0, st>>>(xs, as, gs, es, dxs, drs, M, C, coef, scale_shift)
+  bn_bwd_apply_kernel<MASK, EXTRA, DRES><<<agrid, kThreads, 0, st>>>(xs, as, gs, es, dxs, drs, M, C, coef, scale_shift, fs)
 #define NBDT_BWD_APPLY_M(MASK)                       \
   do {                                               \
     if (extra && dres) NBDT_BWD_APPLY(MASK, true, true);   \

@@ -59,6 +59,7 @@ SIGNATURES = {
     "nbdt_conv_unpack_wgrad_batch": (ctypes.c_int, [c_ptr, ctypes.c_int, ctypes.c_int, c_ptr]),
     "nbdt_conv_unpack_wgrad": (ctypes.c_int, [c_ptr, c_ptr] + [ctypes.c_int] * 6 + [c_ptr]),
     "nbdt_bn_scratch_floats": (ctypes.c_longlong, [ctypes.c_int]),
+    "nbdt_bn_stats_apply": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr]),
     "nbdt_bn_finalize_partials": (ctypes.c_int, [c_ptr, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "nbdt_bn_stats": (ctypes.c_int, [c_ptr, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "nbdt_bn_eval_scale": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_ptr]),

@@ -169,6 +169,10 @@ class ConvFunction(torch.autograd.Function):
         return dx, dw, None, (dy if has_res else None), None
 
 
+# NBDT_B200_BN_FOLD_FINALIZE=1: BatchNorm finalize folded into the consumer kernels (csrc/bn_ops.cu); measured slower, off by default
+_FOLD_BN_FINALIZE = os.environ.get("NBDT_B200_BN_FOLD_FINALIZE") is not None
+
+
 class BatchNormActFunction(torch.autograd.Function):
     """y = act(batch_norm(x) (+ residual)); training mode uses batch statistics and updates the running ones.
 
@@ -188,6 +192,10 @@ class BatchNormActFunction(torch.autograd.Function):
         scale_shift = torch.empty((2, Cp), dtype=torch.float32, device=dev)
         mean_invstd = torch.empty((2, Cp), dtype=torch.float32, device=dev)
         lib = L.load()
+        act = int(relu)  # activation code: 0 none, 1 ReLU, 2 SiLU
+        if act == 2 and residual is not None:
+            raise NotImplementedError("SiLU after a residual add is not implemented")
+        y = torch.empty_like(x)
         with torch.cuda.device(dev):
             rm = running_mean if running_mean is not None else None
             rv = running_var if running_var is not None else None
@@ -196,22 +204,26 @@ class BatchNormActFunction(torch.autograd.Function):
                 assert partials.shape[1:] == (2, Cp), (partials.shape, Cp)
                 L.check(lib.nbdt_bn_finalize_partials(_p(partials), partials.shape[0], M, Cp, c_real, _p(g), _p(b), _p(rm), _p(rv),
                                                       float(momentum), float(eps), _p(mean_invstd), _p(scale_shift), _stream(x)))
-                _count()
-            elif training:
+                L.check(lib.nbdt_bn_apply(_p(x), _p(residual), _p(y), M, Cp, _p(scale_shift), act, _stream(x)))
+                _count(2)
+            elif training and not _FOLD_BN_FINALIZE:
                 sums = torch.empty((lib.nbdt_bn_scratch_floats(Cp),), dtype=torch.float32, device=dev)
                 L.check(lib.nbdt_bn_stats(_p(x), M, Cp, c_real, _p(g), _p(b), _p(rm), _p(rv), float(momentum), float(eps),
                                           _p(sums), _p(mean_invstd), _p(scale_shift), _stream(x)))
+                L.check(lib.nbdt_bn_apply(_p(x), _p(residual), _p(y), M, Cp, _p(scale_shift), act, _stream(x)))
+                _count(3)
+            elif training:
+                # experiment (measured slower): statistics kernel -> fp64 accumulator, the apply kernel finalizes in its prologue
+                sums = torch.empty((lib.nbdt_bn_scratch_floats(Cp),), dtype=torch.float32, device=dev)
+                L.check(lib.nbdt_bn_stats_apply(_p(x), _p(residual), _p(y), M, Cp, c_real, _p(g), _p(b), _p(rm), _p(rv),
+                                                float(momentum), float(eps), _p(sums), _p(mean_invstd), _p(scale_shift), act,
+                                                _stream(x)))
                 _count(2)
             else:
                 L.check(lib.nbdt_bn_eval_scale(Cp, c_real, _p(g), _p(b), _p(running_mean), _p(running_var), float(eps),
                                                _p(scale_shift), _stream(x)))
-                _count()
-            act = int(relu)  # activation code: 0 none, 1 ReLU, 2 SiLU
-            if act == 2 and residual is not None:
-                raise NotImplementedError("SiLU after a residual add is not implemented")
-            y = torch.empty_like(x)
-            L.check(lib.nbdt_bn_apply(_p(x), _p(residual), _p(y), M, Cp, _p(scale_shift), act, _stream(x)))
-            _count()
+                L.check(lib.nbdt_bn_apply(_p(x), _p(residual), _p(y), M, Cp, _p(scale_shift), act, _stream(x)))
+                _count(2)
         ctx.training = training
         ctx.meta = (M, Cp, c_real, act, residual is not None)
         # ReLU mask in backward: recomputed from x and scale/shift (bit-identical fmaf) unless a residual was added
@@ -244,7 +256,7 @@ class BatchNormActFunction(torch.autograd.Function):
             else:
                 L.check(L.load().nbdt_bn_backward(_p(x), _p(act), _p(scale_shift), _p(dy), _p(extra), _p(dx), _p(dres), M,
                                                   Cp, c_real, _p(g), _p(mean_invstd), _p(dsums), _stream(x)))
-        _count(3)
+        _count(2 if _FOLD_BN_FINALIZE else 3)
         return dx, dsums[Cp:Cp + c_real], dsums[:c_real], None, None, None, None, None, None, dres, None, None
 
 

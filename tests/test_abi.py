@@ -26,7 +26,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, name), f"{name} declared in nbdt_b200.h but not exported"
         assert name in L.SIGNATURES, f"{name} has no ctypes signature in nbdt/_b200/lib.py"
     assert sorted(L.SIGNATURES) == declared
-    assert lib.nbdt_version() == 104
+    assert lib.nbdt_version() == 105
 
 
 def _desc(L, C, ptr, child, root=0):

@@ -187,3 +187,31 @@ def test_bench_tree_cpu_baseline_leg():
     assert r["unit"] == "GB/s" and r["value"] > 0 and r["cores"] >= 1 and r["kind"] == "port"
     r = mod.cpu_baseline_point("CIFAR100", "wordnet", 100, kind="hard", budget_s=0.05)
     assert r["value"] > 0 and "hard" in r["sample"]
+
+
+def test_bench_hbm_byte_model():
+    """bench.py's `hbm_kernels`: algorithmic bytes of the memory-bound C-ABI calls from their own size arguments (bf16 activations)."""
+    import ctypes
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    K = bench.HBM_KERNELS
+    P, NULL = ctypes.c_void_p(1234), ctypes.c_void_p()
+    M, C = 1000, 64
+    assert K["nbdt_bn_stats"][1]((P, M, C, C, P, P, P, P, 0.1, 1e-5, P, P, P, P)) == M * C * 2
+    assert K["nbdt_bn_apply"][1]((P, NULL, P, M, C, P, 1, P)) == 2 * M * C * 2
+    assert K["nbdt_bn_apply"][1]((P, P, P, M, C, P, 1, P)) == 3 * M * C * 2
+    # reduce pass reads x, dy; apply pass reads x, dy and writes dx; + act twice, + extra, + dres
+    assert K["nbdt_bn_backward"][1]((P, NULL, P, P, NULL, P, NULL, M, C, C, P, P, P, P)) == 5 * M * C * 2
+    assert K["nbdt_bn_backward"][1]((P, P, P, P, P, P, P, M, C, C, P, P, P, P)) == 9 * M * C * 2
+    assert K["nbdt_bn_backward_silu"][1]((P, P, P, P, P, M, C, C, P, P, P, P)) == 6 * M * C * 2
+    N, H, W = 2, 14, 14
+    assert K["nbdt_dwconv_fwd"][1]((P, P, NULL, P, N, H, W, C, 3, 2, 0, P)) == N * C * 2 * (H * W + 7 * 7)
+    assert K["nbdt_dwconv_wgrad"][1]((P, P, P, N, H, W, C, 5, 1, P)) == N * C * 2 * 2 * H * W
+    assert K["nbdt_dwconv_dgrad"][1]((P, P, P, N, H, W, C, 5, 2, P)) == N * C * 2 * (H * W + 7 * 7)
+    assert K["nbdt_se_scale"][1]((P, P, P, N, H * W, C, P)) == 2 * N * H * W * C * 2
+    assert K["nbdt_sgd_step"][1]((P, P, P, 1000, 0.1, 0.9, 5e-4, P)) == 20000
