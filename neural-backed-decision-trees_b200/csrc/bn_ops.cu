@@ -171,11 +171,16 @@ __device__ __forceinline__ void reduce_partials2(const float* __restrict__ parti
   }
 }
 
+// `last` (both reduction ops): M - 1 to walk the rows from the END of the tensor, -1 for the natural order.  The producer of the
+// tensor (convolution / data-gradient epilogue) wrote it front to back, so its tail is what the 126 MB L2 still holds when the
+// reduction starts; reading back to front turns that part into L2 hits, and leaves the FRONT hot for the apply pass that follows
+// (which walks front to back).  NBDT_B200_BN_REVERSE=0 restores the natural order (A/B).
 struct StatsOp {
   const uint4* x;
   int octets;
+  long long last;
   __device__ __forceinline__ void init(int) {}
-  __device__ __forceinline__ uint4 load(long long row, int o) const { return __ldg(x + row * octets + o); }
+  __device__ __forceinline__ uint4 load(long long row, int o) const { return __ldg(x + (last >= 0 ? last - row : row) * octets + o); }
   __device__ __forceinline__ void accum(const uint4& v, float (&acc)[2][8]) const {
     float f[8];
     unpack8(v, f);
@@ -189,8 +194,8 @@ struct StatsOp {
 
 // partials[cta][0][c] = sum_rows x, [1][c] = sum_rows x^2.          bytes: M*C*2 read
 __global__ void __launch_bounds__(kThreads, 4) bn_stats_kernel(const uint4* __restrict__ x, long long M, int C,
-                                                            float* __restrict__ partials, double* __restrict__ acc64) {
-  reduce_rows<2, 8>(M, C, partials, StatsOp{x, C / 8}, acc64);
+                                                            float* __restrict__ partials, double* __restrict__ acc64, long long last) {
+  reduce_rows<2, 8>(M, C, partials, StatsOp{x, C / 8, last}, acc64);
 }
 
 // What the apply kernel needs to turn the accumulated sums into this BatchNorm's coefficients (and to publish them).
@@ -345,6 +350,7 @@ struct BwdReduceOp {
   const float* mean_invstd;
   const float* scale_shift;
   int octets, C;
+  long long last;
   float mean[8], sc[8], sh[8];
   __device__ __forceinline__ void init(int o) {
     load8(mean_invstd + o * 8, mean);
@@ -355,9 +361,10 @@ struct BwdReduceOp {
   }
   __device__ __forceinline__ BwdPack load(long long row, int o) const {
     BwdPack p;
-    p.x = __ldg(x + row * octets + o);
-    p.g = __ldg(dy + row * octets + o);
-    if (MASK == kMaskAct) p.a = __ldg(act + row * octets + o);
+    const long long rr = last >= 0 ? last - row : row;
+    p.x = __ldg(x + rr * octets + o);
+    p.g = __ldg(dy + rr * octets + o);
+    if (MASK == kMaskAct) p.a = __ldg(act + rr * octets + o);
     return p;
   }
   __device__ __forceinline__ void accum(const BwdPack& p, float (&acc)[2][8]) const {
@@ -385,10 +392,10 @@ __global__ void __launch_bounds__(kThreads, 4) bn_bwd_reduce_kernel(const uint4*
                                                                  const uint4* __restrict__ dy, long long M, int C,
                                                                  const float* __restrict__ mean_invstd,
                                                                  const float* __restrict__ scale_shift,
-                                                                 float* __restrict__ partials, double* __restrict__ acc64) {
+                                                                 float* __restrict__ partials, double* __restrict__ acc64, long long last) {
   BwdReduceOp<MASK> op;
   op.x = x; op.act = act; op.dy = dy; op.mean_invstd = mean_invstd; op.scale_shift = scale_shift;
-  op.octets = C / 8; op.C = C;
+  op.octets = C / 8; op.C = C; op.last = last;
   reduce_rows<2, 4>(M, C, partials, op, acc64);
 }
 
@@ -692,6 +699,10 @@ size_t reduce_smem(int C) {
   return R > 1 ? (size_t)R * 2 * C * sizeof(float) : 0;
 }
 constexpr int kReduceCtasPerSm = 4;
+long long reverse_last(long long M) {
+  static const bool off = getenv("NBDT_B200_BN_REVERSE") && atoi(getenv("NBDT_B200_BN_REVERSE")) == 0;
+  return off ? -1 : M - 1;
+}
 
 }  // namespace
 
@@ -706,7 +717,7 @@ int nbdt_bn_stats(const void* x, long long M, int C, int c_real, const float* ga
   NBDT_REQUIRE(C % 8 == 0 && C <= 8192 && M > 0, "bad shape M=%lld C=%d", M, C);
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = rows_grid(M, C, kReduceCtasPerSm);
-  bn_stats_kernel<<<grid, kThreads, reduce_smem(C), st>>>(reinterpret_cast<const uint4*>(x), M, C, sums, nullptr);
+  bn_stats_kernel<<<grid, kThreads, reduce_smem(C), st>>>(reinterpret_cast<const uint4*>(x), M, C, sums, nullptr, reverse_last(M));
   bn_finalize_kernel<<<(C + 31) / 32, kFinalizeThreads, 0, st>>>(sums, grid, M, C, c_real, gamma, beta, running_mean, running_var,
                                                          momentum, eps, mean_invstd, scale_shift);
   NBDT_CUDA_OK(cudaGetLastError());
@@ -776,7 +787,7 @@ int nbdt_bn_stats_apply(const void* x, const void* residual, void* y, long long 
   double* acc = reinterpret_cast<double*>(sums);
   NBDT_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), st));
   const int grid = rows_grid(M, C, kReduceCtasPerSm);
-  bn_stats_kernel<<<grid, kThreads, reduce_smem(C), st>>>(reinterpret_cast<const uint4*>(x), M, C, nullptr, acc);
+  bn_stats_kernel<<<grid, kThreads, reduce_smem(C), st>>>(reinterpret_cast<const uint4*>(x), M, C, nullptr, acc, reverse_last(M));
   BnFromSums fs;
   fs.sums = acc; fs.gamma = gamma; fs.beta = beta; fs.running_mean = running_mean; fs.running_var = running_var;
   fs.mean_invstd = mean_invstd; fs.scale_shift = scale_shift; fs.M = M; fs.c_real = c_real; fs.momentum = momentum; fs.eps = eps;
@@ -818,13 +829,13 @@ static int bn_backward_impl(int mask, const void* x, const void* act, const floa
   NBDT_REQUIRE(finalize_kernel || (reinterpret_cast<uintptr_t>(partials) & 7) == 0, "dsums must be 8-byte aligned");
   if (acc) NBDT_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)2 * C * sizeof(double), st));
   if (mask == kMaskAct)
-    bn_bwd_reduce_kernel<kMaskAct><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc);
+    bn_bwd_reduce_kernel<kMaskAct><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc, reverse_last(M));
   else if (mask == kMaskRecompute)
-    bn_bwd_reduce_kernel<kMaskRecompute><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc);
+    bn_bwd_reduce_kernel<kMaskRecompute><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc, reverse_last(M));
   else if (mask == kMaskSiLU)
-    bn_bwd_reduce_kernel<kMaskSiLU><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc);
+    bn_bwd_reduce_kernel<kMaskSiLU><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc, reverse_last(M));
   else
-    bn_bwd_reduce_kernel<kMaskNone><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc);
+    bn_bwd_reduce_kernel<kMaskNone><<<grid, kThreads, smem, st>>>(xs, as, gs, M, C, mean_invstd, scale_shift, partials, acc, reverse_last(M));
   BnBwdFromSums fs = {};
   if (acc) { fs.sums = acc; fs.gamma = gamma; fs.mean_invstd = mean_invstd; fs.dsums = dsums; fs.c_real = c_real; }
   else bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinalizeThreads, 0, st>>>(partials, grid, M, C, c_real, gamma, mean_invstd, dsums, coef);
