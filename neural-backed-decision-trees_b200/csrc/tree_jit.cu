@@ -48,7 +48,7 @@
 
 namespace {
 
-constexpr int kGeneratorVersion = 14;   // part of the cache key: bump when the emitted code changes
+constexpr int kGeneratorVersion = 15;   // part of the cache key: bump when the emitted code changes
 constexpr int kMaxLeaves = 1536;       // 32 rows x 132 B per leaf of shared memory per block: 1000 leaves (ImageNet) use 16 warps on 150 KB
 constexpr int kTPB = 32;               // one warp per CTA: rows are thread-private, only __syncwarp around the cooperative I/O sweeps
 // Shared-memory layout of a 32-row block: slot c (class c, later prefix / gradient) of row r lives at word
@@ -75,7 +75,11 @@ struct Knobs {
                               //   (6 FFMA): bit 0 in the Z traversal, bit 1 in the gradient traversal; -1 = by team size (measured,
                               //   profiles/r02_tree_tune_v6.jsonl: one warp per block 1, teams 3)
   int rows = 0;               // NBDT_B200_KA_ROWS: rows per thread (1, or 2 = packed f32x2 arithmetic; 0 = by leaf count)
-  bool is_default() const { return regcap == kRegValueCap && minb == 0 && unroll == 8 && prefetch == 0 && maxld == 24 && fence == -1 && warps == 0 && expm == -1 && rows == 0; }
+  int teams = 0;              // NBDT_B200_KA_TEAMS: row blocks (teams) per CTA; the warps that run the SAME code for different row blocks
+                              //   meet at a named barrier every `lockstep` nodes so that a fetched instruction line serves all of
+                              //   them (0 = one team per CTA, no lock step)
+  int lockstep = 16;          // NBDT_B200_KA_LOCKSTEP: nodes between those barriers
+  bool is_default() const { return regcap == kRegValueCap && minb == 0 && unroll == 8 && prefetch == 0 && maxld == 24 && fence == -1 && warps == 0 && expm == -1 && rows == 0 && teams == 0 && lockstep == 16; }
 };
 Knobs read_knobs() {
   Knobs k;
@@ -89,6 +93,8 @@ Knobs read_knobs() {
   k.warps = std::max(0, std::min(16, geti("NBDT_B200_KA_WARPS", k.warps)));
   k.expm = std::max(-1, std::min(3, geti("NBDT_B200_KA_EXPMUFU", k.expm)));
   k.rows = std::max(0, std::min(2, geti("NBDT_B200_KA_ROWS", k.rows)));
+  k.teams = std::max(0, std::min(8, geti("NBDT_B200_KA_TEAMS", k.teams)));
+  k.lockstep = std::max(0, geti("NBDT_B200_KA_LOCKSTEP", k.lockstep));
   return k;
 }
 
@@ -195,6 +201,7 @@ struct Plan {
   int min_blocks = 1;              // __launch_bounds__ second argument
   int threads = kTPB;              // 32 * W
   int rows = 1;                    // rows per thread (2: packed pairs); a block is 32 * rows rows
+  int teams = 1;                   // row blocks per CTA (CTA = teams x W warps, teams x the shared memory of one block)
   Team team;
   Knobs knobs;                     // with the automatic choices resolved
   bool default_knobs = true;       // nothing set in the environment: the variant name carries no knob suffix
@@ -416,11 +423,25 @@ KA_DEV void ka_sts(u32 a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "
 #define KA_STD(a, k, off, val) asm volatile("st.shared.f32 [%0+" #off "], %1;" :: "r"(a), "f"(val))
 #define KA_LDD(dst, a, k, off) float dst; asm volatile("ld.shared.f32 %0, [%1+" #off "];" : "=f"(dst) : "r"(a))
 // the parts of a team meet here (all threads of the CTA); a single-warp kernel needs no barrier inside the row function
+#if KA_T > 1
+// several teams per CTA: a team's barrier is named barrier 1 + team (32 * KA_W threads); KA_LOCKSTEP is the named barrier of the
+// KA_T warps that run the same part for different row blocks
 #if KA_W > 1
-#define KA_BAR() asm volatile("bar.sync 0;" ::: "memory")
+#define KA_BAR() asm volatile("bar.sync %0, %1;" :: "r"(1u + threadIdx.x / (32u * KA_W)), "n"(32 * KA_W) : "memory")
 #else
 #define KA_BAR()
 #endif
+#define KA_LOCKSTEP() asm volatile("bar.sync %0, %1;" :: "r"(1u + KA_T + ((threadIdx.x >> 5) % KA_W)), "n"(32 * KA_T) : "memory")
+#elif KA_W > 1
+#define KA_BAR() asm volatile("bar.sync 0;" ::: "memory")
+#define KA_LOCKSTEP()
+#else
+#define KA_BAR()
+#define KA_LOCKSTEP()
+#endif
+#endif
+#ifdef KA_HOST
+#define KA_LOCKSTEP()
 #endif
 // exp(t), t in [0, 1] (a class probability): degree-6 interpolant on the FMA pipe, max rel. error 1.5e-7
 KA_DEV KF exp01(KF t) {
@@ -470,12 +491,19 @@ struct Gen {
   int tmp = 0, since = 0, nfence = 0;
   std::string last;
   std::string base = "xsb";
-  void note(const std::string& name) { last = name; ++since; }
+  int lock_since = 0;
+  void note(const std::string& name) {
+    last = name; ++since;
+    if (plan.teams > 1 && plan.knobs.lockstep > 0 && ++lock_since >= plan.knobs.lockstep) {
+      lock_since = 0;
+      o.f("    KA_LOCKSTEP();");
+    }
+  }
   // the no-fence / 8-warp setting was measured on the soft loss only (its two traversals carry the long dependency chains);
   // the hard loss and the soft forward keep the fenced code at full occupancy (hard loss, 100 leaves: 58 % vs 51 %)
   bool wide_mode() const { return plan.wide && v.mode == kSpecSoftLoss; }
   int fence_every() const { return plan.wide && !wide_mode() ? 8 : plan.knobs.fence; }
-  int min_blocks() const { return wide_mode() ? std::min(plan.min_blocks, 8) : plan.min_blocks; }
+  int min_blocks() const { return wide_mode() ? std::min(plan.min_blocks, std::max(1, 8 / plan.teams)) : plan.min_blocks; }
   bool fence_due() const { return fence_every() > 0 && since >= fence_every() && !last.empty(); }
   std::string fenced(const std::string& val) {
     if (!fence_due()) return val;
@@ -884,7 +912,7 @@ struct Gen {
   // ---- the straight-line code of one warp of the team for one row ----
   void emit_part(int w) {
     const int C = t.C, W = team.W;
-    part = w; top = false; acc = 0; since = 0; last.clear(); base = "xsb";
+    part = w; top = false; acc = 0; since = 0; lock_since = 0; last.clear(); base = "xsb";
     const std::vector<int>& cuts = team.cuts_of_part[w];
     std::vector<int> own;  // own leaves, DFS order
     for (int k : cuts)
@@ -1100,7 +1128,8 @@ struct Gen {
     K = ((C / U) & 31) | 1;
     if (v.layout == 1) { U = 1 << 20; K = 1; }  // thread-private slots only: plain [class][lane]
     const int RB = 32 * R();  // rows per block
-    o.f("#define KA_C %d\n#define KA_W %d\n#define KA_R %d", C, W, R());
+    const int T = plan.teams;
+    o.f("#define KA_C %d\n#define KA_W %d\n#define KA_R %d\n#ifdef KA_HOST\n#define KA_T 1\n#else\n#define KA_T %d\n#endif", C, W, R(), T);
     o.f("#ifdef KA_HOST\n#define KA_TPB 1\n#else\n#define KA_TPB %d\n#endif\n#define KA_U %du\n#define KA_K %du", kTPB * W, U, K);
     o.s += kPrelude;
     auto table = [&](const char* type, const char* name, const std::vector<int>& vals) {
@@ -1230,15 +1259,27 @@ struct Gen {
 
     // ---- kernel: one team per CTA, 32 rows per iteration ----
     o.f("#ifndef KA_HOST");
-    o.f("extern \"C\" __global__ void __launch_bounds__(KA_TPB, %d) nbdt_tree_ka(const KAParams p) {", min_blocks());
+    // CTA = KA_T teams of KA_W warps; `tid` is the thread's index within its team, which owns its own shared-memory block and its own
+    // row block; all teams make the same number of trips (a team past the end of the batch runs on zero live rows) because the
+    // warps that share a part meet at the lock-step barriers
+    const int team_bytes = plan.smem_bytes / T;
+    o.f("extern \"C\" __global__ void __launch_bounds__(KA_TPB * KA_T, %d) nbdt_tree_ka(const KAParams p) {", min_blocks());
     o.f("  extern __shared__ float ka_smem[];");
-    o.f("  const int tid = threadIdx.x, lane = tid & 31;");
-    o.f("  const u32 xsw = (u32)__cvta_generic_to_shared(ka_smem);");
+    o.f("  const int team = threadIdx.x / KA_TPB, tid = threadIdx.x - team * KA_TPB, lane = tid & 31;");
+    o.f("  const u32 xsw = (u32)__cvta_generic_to_shared(ka_smem) + team * %du;", team_bytes);
+    o.f("#if KA_T > 1");
+    o.f("#define KA_TEAM_SYNC() asm volatile(\"bar.sync %%0, %%1;\" :: \"r\"(1u + team), \"n\"(KA_TPB) : \"memory\")");
+    o.f("#elif KA_W > 1");
+    o.f("#define KA_TEAM_SYNC() __syncthreads()");
+    o.f("#else");
+    o.f("#define KA_TEAM_SYNC() __syncwarp()");
+    o.f("#endif");
     o.f("  const u32 xsb = xsw + ((lane * KA_K) & 31u) * %du;", 4 * R());
     o.f("  float loss_acc = 0.f;");
     o.f("  const u32 zr = (u32)((unsigned long long)p.B >> 48);  // zero at run time, unknown at compile time (scheduling fences)");
-    o.f("  for (long long row0 = (long long)blockIdx.x * %d; row0 < p.B; row0 += (long long)gridDim.x * %d) {", RB, RB);
-    o.f("    const int nrows = (int)(p.B - row0 < %d ? p.B - row0 : %d);", RB, RB);
+    o.f("  for (long long blk0 = (long long)blockIdx.x * KA_T * %d; blk0 < p.B; blk0 += (long long)gridDim.x * KA_T * %d) {", RB, RB);
+    o.f("    const long long row0 = blk0 + team * %d;", RB);
+    o.f("    const int nrows = (int)(p.B - row0 < %d ? (p.B - row0 > 0 ? p.B - row0 : 0) : %d);", RB, RB);
     if (R() == 1) {
       o.f("    KY yy = 0; const KB live = lane < nrows;");
       if (loss_mode()) o.f("    if (live) yy = p.targets[row0 + lane];");
@@ -1249,7 +1290,7 @@ struct Gen {
     if (plan.knobs.prefetch > 0) {
       // the lines of a block further ahead go to L2 now, so that its sweep A pays an L2 hit instead of an HBM access
       o.f("    {");
-      o.f("      const long long pr0 = row0 + %dll * gridDim.x * %d;", plan.knobs.prefetch, RB);
+      o.f("      const long long pr0 = row0 + %dll * gridDim.x * KA_T * %d;", plan.knobs.prefetch, RB);
       o.f("      if (pr0 < p.B && p.ld <= 2 * KA_C) {");
       o.f("        const long long pn = p.B - pr0 < %d ? p.B - pr0 : %d;", RB, RB);
       o.f("        const char* pb = reinterpret_cast<const char*>(p.x) + pr0 * p.ld * %d;", esz());
@@ -1258,20 +1299,20 @@ struct Gen {
       o.f("      }");
       o.f("    }");
     }
-    o.f("    ka_sweep_a(p, row0, nrows, xsw, tid);");
-    o.f("    %s;", W > 1 ? "__syncthreads()" : "__syncwarp()");
-    if (W > 1) {
+    o.f("    if (nrows > 0) ka_sweep_a(p, row0, nrows, xsw, tid);");
+    o.f("    KA_TEAM_SYNC();");
+    if (W > 1 || T > 1) {
       o.f("    switch (tid >> 5) {");
       for (int w = 0; w < W; ++w) o.f("      case %d: ka_part%d(p, yy, live, xsb, zr, loss_acc); break;", w, w);
       o.f("    }");
     } else {
-      // a single warp has no barriers inside the row function: threads without a row skip it
+      // a single warp per CTA has no barriers inside the row function: threads without a row skip it
       o.f("    if (lane * %d < nrows) ka_part0(p, yy, live, xsb, zr, loss_acc);", R());
     }
-    o.f("    %s;", W > 1 ? "__syncthreads()" : "__syncwarp()");
-    if (loss_mode()) o.f("    if (p.grad) ka_sweep_b(p, row0, nrows, xsw, tid);");
-    else o.f("    ka_sweep_b(p, row0, nrows, xsw, tid);");
-    o.f("    %s;", W > 1 ? "__syncthreads()" : "__syncwarp()");
+    o.f("    KA_TEAM_SYNC();");
+    if (loss_mode()) o.f("    if (p.grad && nrows > 0) ka_sweep_b(p, row0, nrows, xsw, tid);");
+    else o.f("    if (nrows > 0) ka_sweep_b(p, row0, nrows, xsw, tid);");
+    o.f("    KA_TEAM_SYNC();");
     o.f("  }");
     if (loss_mode()) {
       o.f("  if (tid < 32) {");
@@ -1416,6 +1457,20 @@ Plan make_plan(const KTree& t, int max_smem, const Knobs& knobs) {
   int by_smem = (max_smem > 0 ? max_smem : 227 * 1024) / std::max(1, p.smem_bytes + 1024);
   p.min_blocks = std::max(1, std::min(32, std::min(by_regs, by_smem)));
   if (knobs.minb > 0) p.min_blocks = knobs.minb;
+  // several teams per CTA: as many as would have been resident as separate CTAs, barrier ids 1..teams (team) and
+  // teams+1..teams+W (lock step) must stay below 16
+  p.teams = 1;
+  if (knobs.teams > 1) {
+    const int resident = p.wide ? std::min(p.min_blocks, 8) : p.min_blocks;  // CTAs per SM the single-team kernel would have had
+    int T = std::min(knobs.teams, std::max(1, resident));
+    while (T > 1 && (1 + T + W > 16 || (long long)T * p.smem_bytes > (max_smem > 0 ? max_smem : 227 * 1024) - 1024)) --T;
+    p.teams = T;
+    if (T > 1) {
+      p.min_blocks = std::max(1, resident / T);
+      p.smem_bytes *= T;
+      p.threads *= T;
+    }
+  }
   return p;
 }
 
@@ -1540,7 +1595,7 @@ std::vector<std::string> cache_read_dirs() {
 std::string variant_name(const KTree& t, const Variant& v, const Knobs& k, bool dflt) {
   char b[192];
   int n = snprintf(b, sizeof b, "ka%d_%016llx_m%d_t%d_v%d_o%d%s", kGeneratorVersion, t.hash, v.mode, v.dtype, v.vec, v.ovec, v.layout ? "_nchw" : "");
-  if (!dflt) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d_w%d_e%d_x%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence, k.warps, k.expm, k.rows);
+  if (!dflt) snprintf(b + n, sizeof b - n, "_r%d_b%d_u%d_p%d_l%d_f%d_w%d_e%d_x%d_g%d_k%d", k.regcap, k.minb, k.unroll, k.prefetch, k.maxld, k.fence, k.warps, k.expm, k.rows, k.teams, k.lockstep);
   return b;
 }
 
@@ -1702,7 +1757,8 @@ int tree_jit_launch(TreeJit* t, int mode, int dtype, const SpecParams& p, void* 
     t->last_variant = variant_name(t->tree, v, t->plan.knobs, t->plan.default_knobs);
   }
   const int rb = 32 * t->plan.rows;
-  long long grid = (p.B + rb - 1) / rb;
+  const long long rbt = (long long)rb * t->plan.teams;
+  long long grid = (p.B + rbt - 1) / rbt;
   grid = std::min<long long>(grid, (long long)t->sm_count * L->blocks_per_sm);
   if (grid < 1) grid = 1;
   SpecParams sp = p;

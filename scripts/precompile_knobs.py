@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "neural-backed-decision-trees_b200")
 KNOBS = ["NBDT_B200_KA_REGCAP", "NBDT_B200_KA_MINB", "NBDT_B200_KA_UNROLL", "NBDT_B200_KA_PREFETCH", "NBDT_B200_KA_MAXLD", "NBDT_B200_KA_FENCE",
-         "NBDT_B200_KA_WARPS", "NBDT_B200_KA_EXPMUFU", "NBDT_B200_KA_ROWS"]
+         "NBDT_B200_KA_WARPS", "NBDT_B200_KA_EXPMUFU", "NBDT_B200_KA_ROWS", "NBDT_B200_KA_TEAMS", "NBDT_B200_KA_LOCKSTEP"]
 WANT = ("CIFAR100", "TinyImagenet200", "Imagenet1000")   # hierarchy="induced", as scripts/tune_tree.py asks
 
 if len(sys.argv) > 1 and sys.argv[1] == "--one":

@@ -13,10 +13,10 @@ from bench_tree import peaks, time_point  # noqa: E402
 from nbdt._b200 import lib as L  # noqa: E402
 from nbdt.tree import Tree  # noqa: E402
 
-KNOBS = ["NBDT_B200_KA_REGCAP", "NBDT_B200_KA_MINB", "NBDT_B200_KA_UNROLL", "NBDT_B200_KA_PREFETCH", "NBDT_B200_KA_MAXLD", "NBDT_B200_KA_FENCE", "NBDT_B200_KA_WARPS", "NBDT_B200_KA_EXPMUFU", "NBDT_B200_KA_ROWS"]
-# (regcap, minb, unroll, prefetch, maxld, fence, warps, expmufu, rows)
-D = (168, 0, 8, 0, 24, 8, 0, 0, 0)
-E = [D, D[:7] + (1, 0), D[:7] + (1, 2)]
+KNOBS = ["NBDT_B200_KA_REGCAP", "NBDT_B200_KA_MINB", "NBDT_B200_KA_UNROLL", "NBDT_B200_KA_PREFETCH", "NBDT_B200_KA_MAXLD", "NBDT_B200_KA_FENCE", "NBDT_B200_KA_WARPS", "NBDT_B200_KA_EXPMUFU", "NBDT_B200_KA_ROWS", "NBDT_B200_KA_TEAMS", "NBDT_B200_KA_LOCKSTEP"]
+# (regcap, minb, unroll, prefetch, maxld, fence, warps, expmufu, rows, teams, lockstep); -1 = automatic
+D = (168, 0, 8, 0, 24, -1, 0, -1, 0, 0, 16)
+E = [D, D[:9] + (4, 16), D[:9] + (8, 16)]
 GRIDS = {100: E, 200: E, 1000: [D]}
 if len(sys.argv) > 1:
     g = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
