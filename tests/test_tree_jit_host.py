@@ -84,6 +84,17 @@ def test_class_major_variant_matches_oracle(dataset, hierarchy, dtype, warps):
     check(tree, ot, C, dtype=dtype, warps=warps, rows=24, hw=8)
 
 
+@pytest.mark.parametrize("env", [{"NBDT_B200_KA_ROWS": "2"}, {"NBDT_B200_KA_TEAMS": "4", "NBDT_B200_KA_LOCKSTEP": "8"},
+                                 {"NBDT_B200_KA_ROWS": "2", "NBDT_B200_KA_WARPS": "2"}, {"NBDT_B200_KA_FENCE": "8", "NBDT_B200_KA_EXPMUFU": "0"}])
+def test_generator_knob_variants_match_oracle(env, monkeypatch):
+    """The measured-and-rejected code shapes stay correct: two rows per thread on packed pairs (with and without teams), several
+    teams per CTA with lock-step barriers (no-ops on the host), and the round-1 fence / polynomial settings."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    tree, ot, C = shipped("CIFAR100", "wordnet")
+    check(tree, ot, C, dtype=0, rows=9, warps=int(env["NBDT_B200_KA_WARPS"]) if "NBDT_B200_KA_WARPS" in env else None)
+
+
 def test_generated_code_imagenet_team_of_16():
     tree, ot, C = shipped("Imagenet1000", "induced")
     check(tree, ot, C, dtype=0, rows=6)
